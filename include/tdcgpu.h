@@ -1,0 +1,109 @@
+/*
+ * tdcgpu — C ABI of the B200-native text index (SA / ISA / Phi / PLCP / LCP), BWT and lzss_lcp factoriser.
+ *
+ * This is the drop-in boundary for tudocomp's TextDS + lzss_lcp hot path.  Plain pointers and sizes only; no C++
+ * or torch types; nothing throws or aborts across this boundary.  Every function returns 0 on success and a
+ * negative code on failure (tdcgpu_last_error() describes it).  There is NO CPU fallback: without a CUDA device
+ * tdcgpu_create fails with TDCGPU_ERR_CUDA.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the tudocomp source tree).
+ *
+ * Text contract (same as the reference, ds/TextDS.hpp:132-138, ds/SADivSufSort.hpp:21-26, driver.cpp:268-270):
+ * `text` is the escaped input followed by exactly one 0 byte; n counts that byte; no other 0 occurs.
+ * All indices are 32-bit (len_t = uint32_t, def.hpp:103,114); n must be < 2^31 like the reference's divsufsort path.
+ */
+#ifndef TDCGPU_H
+#define TDCGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tdcgpu_ctx tdcgpu_ctx;
+
+/* ds::SA/ISA/LCP/PHI/PLCP bit values — ds/TextDSFlags.hpp:10-15 */
+#define TDCGPU_SA 0x01u
+#define TDCGPU_ISA 0x02u
+#define TDCGPU_LCP 0x04u
+#define TDCGPU_PHI 0x08u
+#define TDCGPU_PLCP 0x10u
+/* additional product of the same pass over SA: bwt::bwt, ds/bwt.hpp:19-22 */
+#define TDCGPU_BWT 0x100u
+
+#define TDCGPU_ERR_CUDA (-1)      /* CUDA runtime error (incl. no device) */
+#define TDCGPU_ERR_NOMEM (-2)     /* device scratch too small */
+#define TDCGPU_ERR_SENTINEL (-3)  /* text violates the sentinel contract ("Input has no sentinel!", TextDS.hpp:132-138) */
+#define TDCGPU_ERR_INTERNAL (-4)
+#define TDCGPU_ERR_ARG (-5)       /* bad argument (threshold 0, NULL, n >= 2^31, buffer too small) */
+#define TDCGPU_ERR_STATE (-6)     /* a required structure has not been built */
+
+/* lzss::Factor — compressors/lzss/LZSSFactors.hpp:13-20 (packed pos, src, len; len_compact_t = uint32_t) */
+typedef struct tdcgpu_factor {
+    uint32_t pos, src, len;
+} tdcgpu_factor;
+
+const char* tdcgpu_last_error(void);
+int tdcgpu_device_count(void);
+
+/* One context per device; owns a stream, the resident text, the index arrays and scratch. */
+int tdcgpu_create(int device, tdcgpu_ctx** out);
+void tdcgpu_destroy(tdcgpu_ctx* ctx);
+
+/* Make `text` (n bytes incl. the trailing 0) the context's text.  on_device != 0: `text` is a device pointer on the
+ * context's device (device-to-device copy); otherwise a host pointer (staged through pinned memory).
+ * Replaces the View handed to TextDS::TextDS (ds/TextDS.hpp:130-147). */
+int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_device);
+
+/* Build the requested structures on the device (they stay resident).  Replaces TextDS::require
+ * (ds/TextDS.hpp:247-292) and the provider constructors it calls: SADivSufSort.hpp:28-51, PhiFromSA.hpp:24-48,
+ * PLCPFromPhi.hpp:27-53, LCPFromPLCP.hpp:27-54, ISAFromSA.hpp:24-46.  Dependencies are built implicitly. */
+int tdcgpu_textds_build(tdcgpu_ctx* ctx, uint32_t flags);
+
+/* Copy one built structure to a caller buffer of n uint32_t (n bytes for TDCGPU_BWT).  `which` is a single flag.
+ * to_device != 0: dst is a device pointer.  The uint32_t layout is byte-identical to the reference's
+ * DynamicIntVector at width 32 (ds/BitPackingVector.hpp:259-271). */
+int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device);
+
+/* Device pointer of a built structure (valid until the next set_text/destroy); NULL if not built. */
+const void* tdcgpu_textds_device_ptr(tdcgpu_ctx* ctx, uint32_t which);
+
+/* max over PLCP[0..n-2] — PLCPFromPhi::max_lcp(), ds/PLCPFromPhi.hpp:40,55-57 */
+int tdcgpu_textds_max_lcp(tdcgpu_ctx* ctx, uint32_t* max_lcp);
+
+/* Greedy lzss_lcp factorisation — the "Factorize" phase of LZSSLCPCompressor::compress
+ * (compressors/LZSSLCPCompressor.hpp:60-115).  Needs SA, ISA, LCP (built on demand).  Results stay on the device;
+ * *count = number of factors, *min_len / *max_len = FactorBuffer::shortest_factor()/longest_factor()
+ * (lzss/LZSSFactors.hpp:33-47; 0xFFFFFFFF / 0 when there is no factor). */
+int tdcgpu_lzss_lcp_factorize(tdcgpu_ctx* ctx, uint32_t threshold, uint64_t* count, uint32_t* min_len, uint32_t* max_len);
+
+/* Copy the factor list (position order, FactorBuffer::is_sorted() holds) to a caller buffer of `cap` records. */
+int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t cap, int to_device);
+
+/* One-shot host-buffer convenience used by the C++ provider shims: text in, arrays out (NULL = not wanted).
+ * Same semantics as constructing TextDS<>(env, view, flags) and reading the providers. */
+int tdcgpu_textds_build_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp,
+                             uint32_t* phi, uint32_t* plcp, uint32_t* max_lcp);
+
+/* One-shot BWTCompressor::compress payload (compressors/BWTCompressor.hpp:29-47): n bytes out. */
+int tdcgpu_bwt_host(int device, const uint8_t* text, uint64_t n, uint8_t* out);
+
+/* Per-phase device times of the last build/factorize call, for StatPhase (tudocomp_stat/StatPhase.hpp:217-220).
+ * Returns the number of phases; name/ms of phase i via the getters (NULL / <0 when out of range). */
+int tdcgpu_phase_count(tdcgpu_ctx* ctx);
+const char* tdcgpu_phase_name(tdcgpu_ctx* ctx, int i);
+float tdcgpu_phase_ms(tdcgpu_ctx* ctx, int i);
+
+/* Work-model counters of the last SA build: [0] doubling rounds incl. the initial sort, [1] sum of
+ * active suffixes over rounds, [2] radix passes executed, [3] elements moved by those passes, [4] alphabet size,
+ * [5] symbols per initial key. */
+int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]);
+
+/* Block until all work queued on the context's stream is done. */
+int tdcgpu_sync(tdcgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,132 @@
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with `-m gpu` on the B200 box)")
+    config.addinivalue_line("markers", "sim: runs the kernels in the CPU interpreter tests/sim/cusim.h (test infrastructure)")
+
+
+def _P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Oracle:
+    """tests-only binding of oracle/libtdcoracle.so (the C restatement)."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "libtdcoracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "libtdcoracle.so"])
+        self.lib = ctypes.CDLL(path)
+        self.lib.tdcoracle_lzss_lcp_factorize.restype = ctypes.c_int64
+        self.lib.tdcoracle_plcp.restype = ctypes.c_uint32
+
+    def textds(self, t):
+        n = t.size
+        sa, isa, lcp, phi, plcp = (np.zeros(n, np.uint32) for _ in range(5))
+        mx = ctypes.c_uint32()
+        rc = self.lib.tdcoracle_textds(_P(t), ctypes.c_uint32(n), _P(sa), _P(isa), _P(lcp), _P(phi), _P(plcp), ctypes.byref(mx))
+        assert rc == 0, rc
+        return dict(sa=sa, isa=isa, lcp=lcp, phi=phi, plcp=plcp, max_lcp=int(mx.value))
+
+    def bwt(self, t, sa):
+        out = np.zeros(t.size, np.uint8)
+        self.lib.tdcoracle_bwt(_P(t), _P(sa), ctypes.c_uint32(t.size), _P(out))
+        return out
+
+    def factorize(self, ds, n, threshold):
+        out = np.zeros((max(n, 1), 3), np.uint32)
+        z = self.lib.tdcoracle_lzss_lcp_factorize(_P(ds["sa"]), _P(ds["isa"]), _P(ds["lcp"]), ctypes.c_uint32(n),
+                                                  ctypes.c_uint32(threshold), _P(out), ctypes.c_uint64(max(n, 1)))
+        assert z >= 0
+        return out[:z].copy()
+
+    def factor_stats(self, triples, n):
+        a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+        tr = np.ascontiguousarray(triples, np.uint32)
+        self.lib.tdcoracle_factor_stats(_P(tr), ctypes.c_uint64(len(tr)), ctypes.c_uint32(n), ctypes.byref(a),
+                                        ctypes.byref(b), ctypes.byref(c))
+        return int(a.value), int(b.value), int(c.value)
+
+    def decode(self, triples, text):
+        tr = np.ascontiguousarray(triples, np.uint32)
+        out = np.zeros(text.size, np.uint8)
+        rc = self.lib.tdcoracle_lzss_decode(_P(tr), ctypes.c_uint64(len(tr)), _P(text), ctypes.c_uint32(text.size), _P(out))
+        assert rc == 0
+        return out
+
+
+class Reference:
+    """tests-only binding of oracle/_ref/libtdcref.so (the unmodified reference compiled by oracle/Makefile)."""
+
+    def __init__(self):
+        path = os.path.join(ROOT, "oracle", "_ref", "libtdcref.so")
+        if not os.path.exists(path):
+            pytest.skip("oracle/_ref/libtdcref.so not built (needs /root/reference; run `make -C oracle ref`)")
+        self.lib = ctypes.CDLL(path)
+        for f in ("tdcref_lzss_lcp_factors", "tdcref_lzss_lcp_compress", "tdcref_lzss_lcp_decompress", "tdcref_escape",
+                  "tdcref_bwt_compress"):
+            getattr(self.lib, f).restype = ctypes.c_int64
+        self.lib.tdcref_last_error.restype = ctypes.c_char_p
+
+    def textds(self, t):
+        n = t.size
+        sa, isa, lcp, phi, plcp = (np.zeros(n, np.uint32) for _ in range(5))
+        mx = ctypes.c_uint32()
+        rc = self.lib.tdcref_textds(_P(t), ctypes.c_uint64(n), _P(sa), _P(isa), _P(lcp), _P(phi), _P(plcp), ctypes.byref(mx))
+        assert rc == 0, self.lib.tdcref_last_error()
+        return dict(sa=sa, isa=isa, lcp=lcp, phi=phi, plcp=plcp, max_lcp=int(mx.value))
+
+    def bwt(self, t):
+        out = np.zeros(t.size, np.uint8)
+        assert self.lib.tdcref_bwt(_P(t), ctypes.c_uint64(t.size), _P(out)) == 0
+        return out
+
+    def factors(self, t, threshold):
+        out = np.zeros((max(t.size, 1), 3), np.uint32)
+        hdr = np.zeros(3, np.uint64)
+        z = self.lib.tdcref_lzss_lcp_factors(_P(t), ctypes.c_uint64(t.size), ctypes.c_uint32(threshold), _P(out),
+                                             ctypes.c_uint64(max(t.size, 1)), _P(hdr))
+        assert z >= 0, self.lib.tdcref_last_error()
+        return out[:z].copy(), tuple(int(x) for x in hdr)
+
+    def compress(self, t, threshold, coder):
+        cap = 16 * t.size + 65536
+        out = np.zeros(cap, np.uint8)
+        secs = ctypes.c_double()
+        m = self.lib.tdcref_lzss_lcp_compress(_P(t), ctypes.c_uint64(t.size), ctypes.c_uint32(threshold), coder, _P(out),
+                                              ctypes.c_uint64(cap), ctypes.byref(secs))
+        assert 0 <= m <= cap, self.lib.tdcref_last_error()
+        return out[:m].copy(), secs.value
+
+    def decompress(self, arc, coder, n):
+        out = np.zeros(n + 16, np.uint8)
+        m = self.lib.tdcref_lzss_lcp_decompress(_P(arc), ctypes.c_uint64(arc.size), coder, _P(out), ctypes.c_uint64(out.size))
+        assert m >= 0, self.lib.tdcref_last_error()
+        return out[:m].copy()
+
+    def escape(self, raw: bytes):
+        a = np.frombuffer(raw, np.uint8).copy() if raw else np.zeros(0, np.uint8)
+        out = np.zeros(2 * a.size + 16, np.uint8)
+        m = self.lib.tdcref_escape(_P(a) if a.size else None, ctypes.c_uint64(a.size), _P(out), ctypes.c_uint64(out.size))
+        assert m >= 0
+        return out[:m].copy()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    return Oracle()
+
+
+@pytest.fixture(scope="session")
+def reference():
+    return Reference()

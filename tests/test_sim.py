@@ -1,0 +1,58 @@
+"""CPU tests: the CUDA kernels' LOGIC, executed by the test-only interpreter tests/sim/cusim.h, against the oracle.
+This is how kernels are debugged without a GPU in the build container; it proves nothing about the real device
+(memory ordering, occupancy), which the `-m gpu` tests cover."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from inputs import generator_strings, roundtrip_batch, small_synthetic
+from tudocomp_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SIM = os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so")
+
+pytestmark = pytest.mark.sim
+
+
+@pytest.fixture(scope="module")
+def simlib():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    return _abi.TdcGpuLib(SIM)
+
+
+def _check(simlib, oracle, name, t, thresholds=(3,)):
+    ds = oracle.textds(t)
+    with _abi.Context(simlib) as c:
+        c.set_text(t)
+        c.build(_abi.SA | _abi.ISA | _abi.LCP | _abi.PHI | _abi.PLCP | _abi.BWT)
+        for k, fl in (("sa", _abi.SA), ("isa", _abi.ISA), ("lcp", _abi.LCP), ("phi", _abi.PHI), ("plcp", _abi.PLCP)):
+            assert np.array_equal(c.get(fl), ds[k]), (name, k)
+        assert c.max_lcp() == ds["max_lcp"], name
+        assert np.array_equal(c.get(_abi.BWT), oracle.bwt(t, ds["sa"])), name
+        for thr in thresholds:
+            z, mn, mx = c.factorize(thr)
+            f = c.factors(z)
+            want = oracle.factorize(ds, t.size, thr)
+            got = np.stack([f["pos"], f["src"], f["len"]], 1) if z else np.zeros((0, 3), np.uint32)
+            assert np.array_equal(got, want), (name, thr)
+            wmn, wmx, _ = oracle.factor_stats(want, t.size)
+            assert (mn, mx) == (wmn, wmx), (name, thr)
+
+
+def test_sim_reference_test_strings(simlib, oracle):
+    for name, t in roundtrip_batch():
+        _check(simlib, oracle, name, t, thresholds=(1, 2, 3))
+
+
+def test_sim_generator_strings(simlib, oracle):
+    for name, t in generator_strings(9):
+        _check(simlib, oracle, name, t, thresholds=(2, 3))
+
+
+def test_sim_synthetic_multi_tile(simlib, oracle):
+    for name, t in small_synthetic():
+        if t.size > 21000:
+            continue  # keep the CPU suite short; the larger cases run on the GPU
+        _check(simlib, oracle, name, t, thresholds=(3, 5))

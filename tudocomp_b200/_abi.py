@@ -1,0 +1,153 @@
+"""ctypes binding of the C ABI declared in include/tdcgpu.h.
+
+`TdcGpuLib(path)` binds one shared object.  The package (`tudocomp_b200/__init__.py`) only ever binds
+`tudocomp_b200/libtdcgpu.so` — the nvcc-built CUDA library — and raises if it is missing: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+SA, ISA, LCP, PHI, PLCP, BWT = 0x01, 0x02, 0x04, 0x08, 0x10, 0x100
+
+EXPORTS = [
+    "tdcgpu_last_error", "tdcgpu_device_count", "tdcgpu_create", "tdcgpu_destroy", "tdcgpu_set_text",
+    "tdcgpu_textds_build", "tdcgpu_textds_get", "tdcgpu_textds_device_ptr", "tdcgpu_textds_max_lcp",
+    "tdcgpu_lzss_lcp_factorize", "tdcgpu_lzss_lcp_get_factors", "tdcgpu_textds_build_host", "tdcgpu_bwt_host",
+    "tdcgpu_phase_count", "tdcgpu_phase_name", "tdcgpu_phase_ms", "tdcgpu_sa_stats", "tdcgpu_sync",
+]
+
+FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
+
+
+class TdcGpuError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"tdcgpu error {code}: {msg}")
+        self.code = code
+
+
+class TdcGpuLib:
+    def __init__(self, path: str):
+        self.path = path
+        self.lib = C.CDLL(path)
+        L = self.lib
+        L.tdcgpu_last_error.restype = C.c_char_p
+        L.tdcgpu_device_count.restype = C.c_int
+        L.tdcgpu_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.tdcgpu_destroy.argtypes = [C.c_void_p]
+        L.tdcgpu_destroy.restype = None
+        L.tdcgpu_set_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.tdcgpu_textds_build.argtypes = [C.c_void_p, C.c_uint32]
+        L.tdcgpu_textds_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.tdcgpu_textds_device_ptr.argtypes = [C.c_void_p, C.c_uint32]
+        L.tdcgpu_textds_device_ptr.restype = C.c_void_p
+        L.tdcgpu_textds_max_lcp.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+        L.tdcgpu_lzss_lcp_factorize.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
+                                                C.POINTER(C.c_uint32)]
+        L.tdcgpu_lzss_lcp_get_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.tdcgpu_textds_build_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5 + [C.POINTER(C.c_uint32)]
+        L.tdcgpu_bwt_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.tdcgpu_phase_count.argtypes = [C.c_void_p]
+        L.tdcgpu_phase_name.argtypes = [C.c_void_p, C.c_int]
+        L.tdcgpu_phase_name.restype = C.c_char_p
+        L.tdcgpu_phase_ms.argtypes = [C.c_void_p, C.c_int]
+        L.tdcgpu_phase_ms.restype = C.c_float
+        L.tdcgpu_sa_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.tdcgpu_sync.argtypes = [C.c_void_p]
+
+    def check(self, rc: int) -> None:
+        if rc < 0:
+            raise TdcGpuError(rc, (self.lib.tdcgpu_last_error() or b"").decode(errors="replace"))
+
+    def device_count(self) -> int:
+        return int(self.lib.tdcgpu_device_count())
+
+
+def _host_ptr(a: np.ndarray) -> C.c_void_p:
+    assert a.flags["C_CONTIGUOUS"]
+    return C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One device context: resident text, index arrays and factor list (tdcgpu_ctx)."""
+
+    def __init__(self, lib: TdcGpuLib, device: int = 0):
+        self.lib = lib
+        self._h = C.c_void_p()
+        lib.check(lib.lib.tdcgpu_create(device, C.byref(self._h)))
+        self.n = 0
+
+    def close(self) -> None:
+        if self._h:
+            self.lib.lib.tdcgpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- text ------------------------------------------------------------------------------------------------------
+    def set_text(self, text: np.ndarray) -> None:
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        self.lib.check(self.lib.lib.tdcgpu_set_text(self._h, _host_ptr(text), text.size, 0))
+        self.n = int(text.size)
+
+    def set_text_device(self, dev_ptr: int, n: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_set_text(self._h, C.c_void_p(dev_ptr), n, 1))
+        self.n = int(n)
+
+    # -- text DS ---------------------------------------------------------------------------------------------------
+    def build(self, flags: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_textds_build(self._h, flags))
+
+    def get(self, which: int) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.uint8 if which == BWT else np.uint32)
+        self.lib.check(self.lib.lib.tdcgpu_textds_get(self._h, which, _host_ptr(out), 0))
+        return out
+
+    def get_into_device(self, which: int, dev_ptr: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_textds_get(self._h, which, C.c_void_p(dev_ptr), 1))
+
+    def device_ptr(self, which: int) -> Optional[int]:
+        return self.lib.lib.tdcgpu_textds_device_ptr(self._h, which)
+
+    def max_lcp(self) -> int:
+        v = C.c_uint32()
+        self.lib.check(self.lib.lib.tdcgpu_textds_max_lcp(self._h, C.byref(v)))
+        return int(v.value)
+
+    # -- lzss_lcp --------------------------------------------------------------------------------------------------
+    def factorize(self, threshold: int = 3):
+        cnt, mn, mx = C.c_uint64(), C.c_uint32(), C.c_uint32()
+        self.lib.check(self.lib.lib.tdcgpu_lzss_lcp_factorize(self._h, threshold, C.byref(cnt), C.byref(mn), C.byref(mx)))
+        return int(cnt.value), int(mn.value), int(mx.value)
+
+    def factors(self, count: int) -> np.ndarray:
+        out = np.empty(count, dtype=FACTOR_DTYPE)
+        self.lib.check(self.lib.lib.tdcgpu_lzss_lcp_get_factors(self._h, _host_ptr(out), count, 0))
+        return out
+
+    # -- stats -----------------------------------------------------------------------------------------------------
+    def phases(self):
+        L = self.lib.lib
+        return [(L.tdcgpu_phase_name(self._h, i).decode(), float(L.tdcgpu_phase_ms(self._h, i)))
+                for i in range(L.tdcgpu_phase_count(self._h))]
+
+    def sa_stats(self) -> dict:
+        buf = (C.c_uint64 * 6)()
+        self.lib.check(self.lib.lib.tdcgpu_sa_stats(self._h, buf))
+        keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key"]
+        return dict(zip(keys, [int(x) for x in buf]))
+
+    def sync(self) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_sync(self._h))

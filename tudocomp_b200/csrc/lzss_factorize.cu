@@ -1,0 +1,421 @@
+// lzss_lcp factorisation on the GPU (sm_100a): emits exactly the factor list of the loop in
+// /root/reference/include/tudocomp/compressors/LZSSLCPCompressor.hpp:60-115.
+//
+// What the reference does per visited text position i (rank p = ISA[i]):
+//   PSV side (:71-77): walk up from p while SA[q] > i, l_up  = min LCP[q+1..p]  (q = nearest rank above with SA[q] < i)
+//   NSV side (:82-96): walk down to the first SA[q] < i,   l_dn = min LCP[p+1..q]  (0 if there is none)
+//   len = max(l_up, l_dn); if len >= threshold emit (i, SA[l_up == len ? psv : nsv], len) and i += len, else i += 1.
+// The naive walks are unbounded.  Here:
+//   1. min-trees (fan-out 32) over SA and LCP;
+//   2. every rank p finds PSV/NSV and the range minima in one up/down tree walk (abandoned as soon as the running
+//      minimum drops below the threshold, because such a side can never produce a factor) and scatters
+//      (len << 1 | side) to text order;
+//   3. the greedy chain i -> i + max(1, len) from 0: per tile of text positions a shared-memory pointer-jumping
+//      computes where each position leaves the tile; a scalar walk over tile exits finds each tile's entry; a second
+//      shared-memory pointer doubling marks the positions actually visited;
+//   4. visited positions with len > 0 are compacted, in position order, to (pos, src, len) records
+//      (lzss::Factor, compressors/lzss/LZSSFactors.hpp:13-20); src is recovered by repeating the winning side's walk.
+//      PSV wins ties (:101).
+#include "tdc_ctx.h"
+
+namespace tdc {
+
+static const int MT_MAX_LEVELS = 8;
+struct MinTree {
+    const u32* a[MT_MAX_LEVELS];  // level 0 = SA
+    const u32* l[MT_MAX_LEVELS];  // level 0 = LCP
+    u32 sz[MT_MAX_LEVELS];
+    int nlev;
+};
+
+// one warp per output element: min over 32 inputs
+__global__ void __launch_bounds__(256)
+mintree_level_kernel(const u32* __restrict__ a_in, const u32* __restrict__ l_in, u32 sz_in, u32* __restrict__ a_out,
+                     u32* __restrict__ l_out, u32 sz_out) {
+    const u32 o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (o >= sz_out) return;  // whole warps leave together (sz_out is tested per warp)
+    const u64 i = u64(o) * 32 + lane_id();
+    u32 av = i < sz_in ? a_in[i] : 0xffffffffu;
+    u32 lv = i < sz_in ? l_in[i] : 0xffffffffu;
+    av = warp_min(av);
+    lv = warp_min(lv);
+    if (lane_id() == 0) { a_out[o] = av; l_out[o] = lv; }
+}
+
+// nearest rank q < p with SA[q] < v; m (in: LCP[p]) becomes min LCP[q+1..p].  false: none, or the minimum fell below thr.
+__device__ __forceinline__ bool walk_psv(const MinTree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
+    if (m < thr) return false;
+    u32 idx = p, q = 0;
+    int lvl = 0;
+    bool found = false;
+    while (!found) {
+        const u32 bs = idx & ~31u;
+        const u32* __restrict__ A = T.a[lvl];
+        const u32* __restrict__ L = T.l[lvl];
+        for (q = idx; q-- > bs;) {
+            if (A[q] < v) { found = true; break; }
+            m = min(m, L[q]);
+            if (m < thr) return false;
+        }
+        if (found) break;
+        if (lvl == T.nlev - 1) return false;
+        idx >>= 5;
+        lvl++;
+    }
+    while (lvl > 0) {
+        const u32* __restrict__ A = T.a[lvl - 1];
+        const u32* __restrict__ L = T.l[lvl - 1];
+        const u32 lo = q * 32u;
+        u32 c = min(lo + 32u, T.sz[lvl - 1]);
+        while (c-- > lo) {
+            if (A[c] < v) break;
+            m = min(m, L[c]);
+            if (m < thr) return false;
+        }
+        q = c;
+        lvl--;
+    }
+    q_out = q;
+    return true;
+}
+
+// nearest rank q > p with SA[q] < v; m becomes min LCP[p+1..q].
+__device__ __forceinline__ bool walk_nsv(const MinTree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
+    m = 0xffffffffu;
+    u32 idx = p, q = 0;
+    int lvl = 0;
+    bool found = false;
+    while (!found) {
+        const u32 be = min((idx | 31u) + 1u, T.sz[lvl]);
+        const u32* __restrict__ A = T.a[lvl];
+        const u32* __restrict__ L = T.l[lvl];
+        for (q = idx + 1; q < be; q++) {
+            if (A[q] < v) { found = true; break; }
+            m = min(m, L[q]);
+            if (m < thr) return false;
+        }
+        if (found) break;
+        if (lvl == T.nlev - 1) return false;
+        idx >>= 5;
+        lvl++;
+    }
+    while (lvl > 0) {
+        const u32* __restrict__ A = T.a[lvl - 1];
+        const u32* __restrict__ L = T.l[lvl - 1];
+        u32 c = q * 32u;
+        while (true) {
+            if (A[c] < v) break;
+            m = min(m, L[c]);
+            if (m < thr) return false;
+            c++;
+        }
+        q = c;
+        lvl--;
+    }
+    m = min(m, T.l[0][q]);
+    if (m < thr) return false;
+    q_out = q;
+    return true;
+}
+
+// per rank: longest previous factor length and winning side, scattered to text order
+__global__ void __launch_bounds__(256)
+lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lenside) {
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const u32 v = T.a[0][p];
+    u32 q;
+    u32 mu = T.l[0][p];
+    const u32 lu = walk_psv(T, p, v, thr, mu, q) ? mu : 0u;
+    u32 md;
+    const u32 ld = walk_nsv(T, p, v, thr, md, q) ? md : 0u;
+    const u32 len = max(lu, ld);
+    lenside[v] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// greedy chain
+// ---------------------------------------------------------------------------------------------------------------
+static const int CH_THREADS = 512;
+static const int CH_IPT = 16;
+static const int CH_TILE = CH_THREADS * CH_IPT;  // text positions per tile
+static const u32 CH_NONE = 0xffffffffu;
+
+__device__ __forceinline__ u32 next_of(u32 i, u32 ls) {
+    const u32 len = ls >> 1;
+    return i + (len ? len : 1u);
+}
+
+// where does each position leave its tile?  nodes are positions < n-1; anything >= n-1 is terminal.
+__global__ void __launch_bounds__(CH_THREADS)
+chain_exit_kernel(const u32* __restrict__ lenside, u32 n, u32* __restrict__ exitp) {
+    __shared__ u32 J[CH_TILE];
+    __shared__ u32 changed;
+    const u32 base = blockIdx.x * CH_TILE;
+    const u32 tile_end = min(base + u32(CH_TILE), n - 1);
+    for (u32 j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
+        const u32 i = base + j;
+        J[j] = i < tile_end ? next_of(i, lenside[i]) : CH_NONE;
+    }
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        bool any = false;
+        for (u32 j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
+            const u32 t = J[j];
+            if (t < tile_end) {  // still inside: hop through the target's current pointer (always a node on j's path)
+                J[j] = J[t - base];
+                any = true;
+            }
+        }
+        if (any) changed = 1;
+        __syncthreads();
+        const bool again = changed != 0;
+        __syncthreads();
+        if (!again) break;
+    }
+    for (u32 j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
+        const u32 i = base + j;
+        if (i < tile_end) exitp[i] = J[j];
+    }
+}
+
+// scalar walk over tile exits: the first visited position of every tile the chain touches
+__global__ void chain_entries_kernel(const u32* __restrict__ exitp, u32 n, u32* __restrict__ entry) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u32 x = 0;
+    while (x < n - 1) {
+        entry[x / CH_TILE] = x;
+        x = exitp[x];
+    }
+}
+
+// mark the visited positions of a tile by pointer doubling; output one bit per position that starts a factor
+__global__ void __launch_bounds__(CH_THREADS)
+chain_mark_kernel(const u32* __restrict__ lenside, u32 n, const u32* __restrict__ entry, u32* __restrict__ fmask,
+                  u32* __restrict__ tile_count) {
+    __shared__ u32 J[CH_TILE];
+    __shared__ u32 mark[CH_TILE / 32];
+    __shared__ u32 isfac[CH_TILE / 32];
+    __shared__ u32 flag;
+    __shared__ u32 s_cnt[CH_THREADS / 32];
+    const u32 base = blockIdx.x * CH_TILE;
+    const u32 tile_end = min(base + u32(CH_TILE), n - 1);
+    const u32 e = entry[blockIdx.x];
+    u32* out = fmask + u64(blockIdx.x) * (CH_TILE / 32);
+    if (e == CH_NONE) {  // chain jumps over this tile
+        for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) out[w] = 0;
+        if (threadIdx.x == 0) tile_count[blockIdx.x] = 0;
+        return;
+    }
+    for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) { mark[w] = 0; isfac[w] = 0; }
+    __syncthreads();
+    // thread owns CH_IPT consecutive positions = half of one 32-bit flag word
+    const u32 j0 = threadIdx.x * CH_IPT;
+    u32 fbits = 0;
+#pragma unroll
+    for (int q = 0; q < CH_IPT; q++) {
+        const u32 i = base + j0 + q;
+        u32 ls = 0;
+        if (i < tile_end) { ls = lenside[i]; J[j0 + q] = next_of(i, ls); } else J[j0 + q] = CH_NONE;
+        if (ls) fbits |= 1u << q;
+    }
+    if (fbits) atomicOr(&isfac[j0 >> 5], fbits << (j0 & 31));
+    if (threadIdx.x == 0) mark[(e - base) >> 5] = 1u << ((e - base) & 31);
+    __syncthreads();
+    while (true) {
+        if (threadIdx.x == 0) flag = 0;
+        __syncthreads();
+        // A: marked nodes mark their current jump target (every target is a true chain node)
+        const u32 mw = (mark[j0 >> 5] >> (j0 & 31)) & 0xffffu;
+        bool prop = false;
+        if (mw) {
+#pragma unroll
+            for (int q = 0; q < CH_IPT; q++) {
+                if ((mw >> q) & 1u) {
+                    const u32 t = J[j0 + q];
+                    if (t < tile_end) {
+                        atomicOr(&mark[(t - base) >> 5], 1u << ((t - base) & 31));
+                        prop = true;
+                    }
+                }
+            }
+        }
+        if (prop) flag = 1;
+        __syncthreads();
+        const bool again = flag != 0;
+        // B: J <- J o J with all reads before all writes, so every pointer keeps the same power of `next`
+        u32 nj[CH_IPT];
+#pragma unroll
+        for (int q = 0; q < CH_IPT; q++) {
+            const u32 t = J[j0 + q];
+            nj[q] = t < tile_end ? J[t - base] : t;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < CH_IPT; q++) J[j0 + q] = nj[q];
+        __syncthreads();
+        if (!again) break;
+    }
+    u32 cnt = 0;
+    for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) {
+        const u32 f = mark[w] & isfac[w];
+        out[w] = f;
+        cnt += __popc(f);
+    }
+    cnt = warp_sum<u32>(cnt);
+    if (lane_id() == 0) s_cnt[warp_id()] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 s = 0;
+        for (int w = 0; w < CH_THREADS / 32; w++) s += s_cnt[w];
+        tile_count[blockIdx.x] = s;
+    }
+}
+
+// single CTA: exclusive scan of per-tile counts; *total = sum
+__global__ void __launch_bounds__(1024) scan_counts_kernel(u32* __restrict__ cnt, u32 ntiles, u32* __restrict__ total) {
+    __shared__ u32 scratch[33];
+    u32 carry = 0;
+    for (u32 b = 0; b < ntiles; b += 1024) {
+        const u32 i = b + threadIdx.x;
+        const u32 c = i < ntiles ? cnt[i] : 0;
+        u32 tot;
+        const u32 ex = block_exclusive_sum<u32>(c, scratch, &tot);
+        if (i < ntiles) cnt[i] = carry + ex;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+// emit (pos, src, len) in position order; one thread per 32-bit mask word
+__global__ void __launch_bounds__(CH_TILE / 32)
+emit_factors_kernel(MinTree T, const u32* __restrict__ isa, const u32* __restrict__ lenside, const u32* __restrict__ fmask,
+                    const u32* __restrict__ tile_off, u32 thr, Factor* __restrict__ out, u32* __restrict__ minmax) {
+    __shared__ u32 scratch[33];
+    __shared__ u32 s_min[CH_TILE / 32 / 32], s_max[CH_TILE / 32 / 32];
+    const u32 base = blockIdx.x * CH_TILE;
+    u32 word = fmask[u64(blockIdx.x) * (CH_TILE / 32) + threadIdx.x];
+    u32 tot;
+    u32 o = tile_off[blockIdx.x] + block_exclusive_sum<u32>(u32(__popc(word)), scratch, &tot);
+    u32 mn = 0xffffffffu, mx = 0;
+    while (word) {
+        const u32 b = __ffs(int(word)) - 1;
+        word &= word - 1;
+        const u32 i = base + threadIdx.x * 32 + b;
+        const u32 ls = lenside[i];
+        const u32 len = ls >> 1;
+        const u32 p = isa[i];
+        u32 q = 0, m;
+        if (ls & 1u) {
+            walk_nsv(T, p, i, thr, m, q);
+        } else {
+            m = T.l[0][p];
+            walk_psv(T, p, i, thr, m, q);
+        }
+        Factor f;
+        f.pos = i;
+        f.src = T.a[0][q];
+        f.len = len;
+        out[o++] = f;
+        mn = min(mn, len);
+        mx = max(mx, len);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane_id() == 0) { s_min[warp_id()] = mn; s_max[warp_id()] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (u32 w = 0; w < CH_TILE / 32 / 32; w++) { mn = min(mn, s_min[w]); mx = max(mx, s_max[w]); }
+        if (mx) { atomicMin(&minmax[0], mn); atomicMax(&minmax[1], mx); }
+    }
+}
+
+__global__ void fill_u32_kernel(u32* p, u64 count, u32 v) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < count) p[i] = v;
+}
+
+int factorize_lzss_lcp(Ctx& c, u32 threshold) {
+    if (threshold < 1) { set_error("lzss_lcp: threshold must be >= 1"); return -5; }
+    if ((c.have & (DS_SA | DS_ISA | DS_LCP)) != (DS_SA | DS_ISA | DS_LCP)) {
+        set_error("lzss_lcp: SA, ISA and LCP must be built first");
+        return -6;
+    }
+    const u32 n = u32(c.n);
+    cudaStream_t st = c.stream;
+    c.num_factors = 0;
+    c.flen_min = 0xffffffffu;
+    c.flen_max = 0;
+    if (n <= 1) return 0;
+
+    c.arena.reset();
+    // ---- 1. min-trees ----
+    MinTree T;
+    T.a[0] = c.d_sa;
+    T.l[0] = c.d_lcp;
+    T.sz[0] = n;
+    T.nlev = 1;
+    while (T.sz[T.nlev - 1] > 32) {
+        if (T.nlev >= MT_MAX_LEVELS) { set_error("min-tree too deep"); return -7; }
+        const u32 szi = T.sz[T.nlev - 1], szo = u32(div_up(szi, 32));
+        u32* a = c.arena.take<u32>(szo);
+        u32* l = c.arena.take<u32>(szo);
+        if (!a || !l) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+        TDC_LAUNCH(mintree_level_kernel, u32(div_up(u64(szo) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
+        T.a[T.nlev] = a;
+        T.l[T.nlev] = l;
+        T.sz[T.nlev] = szo;
+        T.nlev++;
+    }
+    for (int i = T.nlev; i < MT_MAX_LEVELS; i++) { T.a[i] = nullptr; T.l[i] = nullptr; T.sz[i] = 0; }
+    TDC_KCHECK();
+
+    const u32 ntiles = u32(div_up(u64(n), CH_TILE));
+    u32* lenside = c.arena.take<u32>(n);
+    u32* exitp = c.arena.take<u32>(n);
+    u32* entry = c.arena.take<u32>(ntiles);
+    u32* fmask = c.arena.take<u32>(u64(ntiles) * (CH_TILE / 32));
+    u32* tile_cnt = c.arena.take<u32>(ntiles);
+    if (!lenside || !exitp || !entry || !fmask || !tile_cnt) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+
+    // ---- 2. LPF per rank ----
+    TDC_LAUNCH(lpf_kernel, u32(div_up(u64(n), 256)), 256, 0, st, T, n, threshold, lenside);
+    // ---- 3. chain ----
+    TDC_LAUNCH(chain_exit_kernel, ntiles, CH_THREADS, 0, st, lenside, n, exitp);
+    TDC_LAUNCH(fill_u32_kernel, u32(div_up(u64(ntiles), 256)), 256, 0, st, entry, u64(ntiles), CH_NONE);
+    TDC_LAUNCH(chain_entries_kernel, 1, 32, 0, st, exitp, n, entry);
+    TDC_LAUNCH(chain_mark_kernel, ntiles, CH_THREADS, 0, st, lenside, n, entry, fmask, tile_cnt);
+    u32* d_total = c.d_scalars + 0;
+    u32* d_minmax = c.d_scalars + 2;
+    TDC_LAUNCH(scan_counts_kernel, 1, 1024, 0, st, tile_cnt, ntiles, d_total);
+    TDC_KCHECK();
+    c.h_scalars[2] = 0xffffffffu;
+    c.h_scalars[3] = 0;
+    TDC_CUDA(cudaMemcpyAsync(d_minmax, c.h_scalars + 2, 2 * sizeof(u32), cudaMemcpyHostToDevice, st));
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, d_total, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    const u64 z = c.h_scalars[0];
+    if (z > c.factors_cap) {
+        if (c.d_factors) TDC_CUDA(cudaFree(c.d_factors));
+        c.d_factors = nullptr;
+        c.factors_cap = 0;
+        const u64 cap = z + z / 8 + 1024;
+        TDC_CUDA(cudaMalloc(&c.d_factors, cap * sizeof(Factor)));
+        c.factors_cap = cap;
+    }
+    // ---- 4. emit ----
+    if (z > 0) {
+        TDC_LAUNCH(emit_factors_kernel, ntiles, CH_TILE / 32, 0, st, T, c.d_isa, lenside, fmask, tile_cnt, threshold, c.d_factors, d_minmax);
+        TDC_KCHECK();
+    }
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 2, d_minmax, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    c.num_factors = z;
+    c.flen_min = c.h_scalars[2];
+    c.flen_max = c.h_scalars[3];
+    return 0;
+}
+
+}  // namespace tdc

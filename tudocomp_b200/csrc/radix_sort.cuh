@@ -1,0 +1,301 @@
+// Hand-written LSD radix sort of (key, u32 value) pairs for sm_100a — the sorting engine of the prefix-doubling
+// suffix-array builder (replaces sssort/trsort of the reference's divsufsort,
+// /root/reference/include/tudocomp/util/divsufsort/divsufsort_ssort.hpp:691, divsufsort_trsort.hpp:506).
+//
+// Structure ("onesweep"): ONE histogram kernel counts every digit position of the key range in a single read; each
+// digit pass is then ONE kernel that reads a tile, ranks it with warp-level match/ballot, stages the tile in shared
+// memory in digit order and writes each digit's run coalesced.  The tile's global offsets come from a decoupled
+// look-back over per-tile digit counts (one 64-bit descriptor per (tile, digit) carrying epoch|status|count in a single
+// word, so a reader never sees a count without its flag).  Per pass: keys and values are read once and written once.
+#pragma once
+#include "tdc_common.cuh"
+
+namespace tdc {
+
+static const int RS_THREADS = 512;
+static const int RS_WARPS = RS_THREADS / 32;
+static const int RS_RADIX = 256;
+static const int RS_MAX_PASSES = 8;
+
+struct PassPlan {
+    int npass;
+    u32 shift[RS_MAX_PASSES];
+    u32 mask[RS_MAX_PASSES];
+};
+
+struct SortWorkspace {
+    u32* hist = nullptr;          // device [RS_MAX_PASSES][256]: digit counts, then exclusive bucket starts
+    u32* uniform = nullptr;       // device [RS_MAX_PASSES]: 1 if one bin holds every key (pass can be skipped)
+    u32* tile_counter = nullptr;  // device [RS_MAX_PASSES]: dynamic tile ids (look-back needs start order == id order)
+    ull* desc = nullptr;          // device [max_tiles][256] look-back descriptors
+    u32* h_uniform = nullptr;     // pinned host mirror of `uniform`
+    u64 max_tiles = 0;
+    u32 epoch = 0;                // bumped once per executed pass; stale descriptors never match
+    int sm_count = 148;
+    // statistics for the work model: executed passes and elements moved
+    u64 stat_passes = 0, stat_elems = 0;
+};
+
+template <class K> struct RsCfg;
+template <> struct RsCfg<u64> { static const int IPT = 12; };
+template <> struct RsCfg<u32> { static const int IPT = 16; };
+
+static const ull RS_STATUS_AGG = 1, RS_STATUS_PREFIX = 2;
+
+__device__ __forceinline__ void desc_store(ull* p, ull v) {
+#ifdef TDC_CUSIM
+    *p = v;
+#else
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ ull desc_load(const ull* p) {
+#ifdef TDC_CUSIM
+    return *p;
+#else
+    ull v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// all digit histograms in one read of the keys
+// ---------------------------------------------------------------------------------------------------------------
+template <class K>
+__global__ void __launch_bounds__(512) rs_histogram_kernel(const K* __restrict__ keys, u64 m, PassPlan plan,
+                                                           u32* __restrict__ ghist) {
+    __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
+    for (u32 i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const u64 m_round = (m + 31) & ~u64(31);
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < m_round; i += stride) {
+        const bool valid = i < m;
+        const K k = valid ? keys[i] : K(0);
+#pragma unroll
+        for (int p = 0; p < RS_MAX_PASSES; p++) {
+            if (p < plan.npass) {
+                const u32 d = u32(k >> plan.shift[p]) & plan.mask[p];
+                // warp-uniform digit (constant high bits, runs): one shared atomic instead of a 32-way conflict
+                const u32 d0 = __shfl_sync(kFull, d, 0);
+                if (__all_sync(kFull, valid && d == d0)) {
+                    if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d0], 32u);
+                } else if (valid) {
+                    atomicAdd(&sh[p * RS_RADIX + d], 1u);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < u32(plan.npass) * RS_RADIX; i += blockDim.x)
+        if (sh[i]) atomicAdd(&ghist[i], sh[i]);
+}
+
+// one CTA of 256 threads per pass: counts -> exclusive bucket starts; flag single-bin passes
+static __global__ void __launch_bounds__(256) rs_scan_kernel(u32* __restrict__ ghist, u32* __restrict__ uniform, u64 m) {
+    __shared__ u32 scratch[33];
+    u32* h = ghist + blockIdx.x * RS_RADIX;
+    const u32 c = h[threadIdx.x];
+    u32 total;
+    const u32 ex = block_exclusive_sum<u32>(c, scratch, &total);
+    h[threadIdx.x] = ex;
+    if (u64(c) == m) uniform[blockIdx.x] = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// one digit pass
+// ---------------------------------------------------------------------------------------------------------------
+template <class K, bool IOTA>
+__global__ void __launch_bounds__(RS_THREADS)
+rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* __restrict__ vin, u32* __restrict__ vout,
+                   u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc,
+                   u32* __restrict__ tile_counter, u32 epoch) {
+    constexpr int IPT = RsCfg<K>::IPT;
+    constexpr int TILE = RS_THREADS * IPT;
+    TDC_DYN_SMEM(smem_raw);
+    K* skeys = reinterpret_cast<K*>(smem_raw);                                  // TILE keys
+    u32* svals = reinterpret_cast<u32*>(smem_raw + sizeof(K) * TILE);           // TILE values
+    u32* warp_cnt = svals + TILE;                                               // [RS_WARPS][256]
+    u32* digit_start = warp_cnt + RS_WARPS * RS_RADIX;                          // [256]
+    u32* gbase = digit_start + RS_RADIX;                                        // [256]
+    u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch + tile id
+
+    const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
+    if (tid == 0) misc[34] = atomicAdd(tile_counter, 1u);
+    u32* my_cnt = warp_cnt + w * RS_RADIX;
+#pragma unroll
+    for (int j = 0; j < RS_RADIX / 32; j++) my_cnt[j * 32 + lane] = 0;
+    __syncthreads();
+    const u32 tile = misc[34];
+    const u64 tile_base = u64(tile) * TILE;
+    const u32 count = u32(min(u64(TILE), m - tile_base));
+
+    // ---- load (warp-striped: coalesced, and index order == (k, lane) order inside a warp) ----
+    K key[IPT];
+    u32 rank[IPT];
+    const u64 wbase = tile_base + u64(w) * (32 * IPT);
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u64 idx = wbase + u32(k) * 32 + lane;
+        key[k] = idx < m ? kin[idx] : ~K(0);
+    }
+    // ---- stable rank inside the warp ----
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u32 d = u32(key[k] >> shift) & mask;
+        const u32 peers = __match_any_sync(kFull, d);
+        const u32 before = __popc(peers & lanemask_lt());
+        const u32 c = my_cnt[d];
+        __syncwarp();
+        if (before == 0) my_cnt[d] = c + __popc(peers);
+        __syncwarp();
+        rank[k] = c + before;
+    }
+    __syncthreads();
+
+    // ---- per-digit totals, warp offsets, tile-local digit starts ----
+    u32 total = 0;
+    if (tid < RS_RADIX) {
+        u32 run = 0;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            const u32 t = warp_cnt[ww * RS_RADIX + tid];
+            warp_cnt[ww * RS_RADIX + tid] = run;
+            run += t;
+        }
+        total = run;
+    }
+    u32 blk_total;
+    const u32 ex = block_exclusive_sum<u32>(total, misc, &blk_total);  // threads >= 256 contribute 0
+    if (tid < RS_RADIX) {
+        digit_start[tid] = ex;
+        // padding keys (~0) of a partial tile were counted in the top bin; they sort last and are never written
+        u32 pub = total;
+        if (tid == mask) pub -= (u32(TILE) - count);
+        // ---- decoupled look-back for digit `tid` ----
+        const ull tag = ull(epoch) << 34;
+        ull* my_desc = desc + u64(tile) * RS_RADIX + tid;
+        u32 exclusive = 0;
+        if (tile == 0) {
+            desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | pub);
+        } else {
+            desc_store(my_desc, tag | (RS_STATUS_AGG << 32) | pub);
+            const ull* look = my_desc - RS_RADIX;
+            while (true) {
+                const ull v = desc_load(look);
+                if ((v >> 34) != ull(epoch) || ((v >> 32) & 3) == 0) continue;  // predecessor not published yet
+                exclusive += u32(v);
+                if (((v >> 32) & 3) == RS_STATUS_PREFIX) break;
+                look -= RS_RADIX;
+            }
+            desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
+        }
+        gbase[tid] = bucket_start[tid] + exclusive - ex;
+    }
+    __syncthreads();
+
+    // ---- stage in shared memory in digit order ----
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u32 d = u32(key[k] >> shift) & mask;
+        const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
+        const u64 idx = wbase + u32(k) * 32 + lane;
+        skeys[p] = key[k];
+        if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];
+    }
+    __syncthreads();
+
+    // ---- coalesced runs out ----
+    for (u32 j = tid; j < count; j += RS_THREADS) {
+        const K kk = skeys[j];
+        const u32 d = u32(kk >> shift) & mask;
+        const u64 o = u64(gbase[d] + j);
+        kout[o] = kk;
+        vout[o] = svals[j];
+    }
+}
+
+static __global__ void rs_iota_kernel(u32* v, u64 m) {
+    u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < m) v[i] = u32(i);
+}
+
+template <class K>
+static inline size_t rs_smem_bytes() {
+    constexpr int TILE = RS_THREADS * RsCfg<K>::IPT;
+    return sizeof(K) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
+}
+template <class K>
+static inline u64 rs_tiles(u64 m) {
+    return div_up(m, u64(RS_THREADS) * RsCfg<K>::IPT);
+}
+
+int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count);
+void sort_workspace_free(SortWorkspace& ws);
+
+// Sorts m pairs by key bits [begin_bit, end_bit).  Buffers ping-pong between (k[0], v[0]) and (k[1], v[1]); the input
+// is in slot 0 and *result receives the slot holding the output.  With iota=true the input values are implicitly
+// 0..m-1 (v[0] is not read).  Stable.
+template <class K>
+int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64 m, int begin_bit, int end_bit,
+                     bool iota, int* result) {
+    *result = 0;
+    if (m == 0) return 0;
+    const int bits = end_bit - begin_bit;
+    PassPlan plan;
+    plan.npass = bits <= 0 ? 0 : (bits + 7) / 8;
+    if (plan.npass > RS_MAX_PASSES) { set_error("radix_sort_pairs: %d bits need more than %d passes", bits, RS_MAX_PASSES); return -1; }
+    if (rs_tiles<K>(m) > ws.max_tiles) { set_error("radix_sort_pairs: workspace too small"); return -1; }
+    {
+        int base = plan.npass ? bits / plan.npass : 0, extra = plan.npass ? bits % plan.npass : 0, sh = begin_bit;
+        for (int p = 0; p < plan.npass; p++) {
+            int wd = base + (p < extra ? 1 : 0);
+            plan.shift[p] = u32(sh);
+            plan.mask[p] = (1u << wd) - 1u;
+            sh += wd;
+        }
+    }
+    int cur = 0;
+    bool need_iota = iota;
+    if (plan.npass > 0) {
+        TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
+        TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
+        TDC_CUDA(cudaMemsetAsync(ws.tile_counter, 0, sizeof(u32) * RS_MAX_PASSES, st));
+        const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
+        auto hk = rs_histogram_kernel<K>;
+        TDC_LAUNCH(hk, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
+        TDC_LAUNCH(rs_scan_kernel, plan.npass, 256, 0, st, ws.hist, ws.uniform, m);
+        TDC_KCHECK();
+        TDC_CUDA(cudaMemcpyAsync(ws.h_uniform, ws.uniform, sizeof(u32) * RS_MAX_PASSES, cudaMemcpyDeviceToHost, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        const u32 grid = u32(rs_tiles<K>(m));
+        const size_t smem = rs_smem_bytes<K>();
+        for (int p = 0; p < plan.npass; p++) {
+            if (ws.h_uniform[p]) continue;  // every key has the same digit here: the pass would be the identity
+            ws.epoch++;
+            if (need_iota) {
+                auto kern = rs_onesweep_kernel<K, true>;
+                TDC_LAUNCH(kern, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m, plan.shift[p],
+                           plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+            } else {
+                auto kern = rs_onesweep_kernel<K, false>;
+                TDC_LAUNCH(kern, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m, plan.shift[p],
+                           plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+            }
+            TDC_KCHECK();
+            need_iota = false;
+            cur ^= 1;
+            ws.stat_passes++;
+            ws.stat_elems += m;
+        }
+    }
+    if (need_iota) {
+        TDC_LAUNCH(rs_iota_kernel, u32(div_up(m, 256)), 256, 0, st, v[cur], m);
+        TDC_KCHECK();
+    }
+    *result = cur;
+    return 0;
+}
+
+}  // namespace tdc

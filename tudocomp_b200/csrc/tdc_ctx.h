@@ -1,0 +1,93 @@
+// Host-side context shared by the tdcgpu translation units.  One context = one device + one stream + one text.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "radix_sort.cuh"
+#include "tdc_common.cuh"
+
+namespace tdc {
+
+// bit flags as in /root/reference/include/tudocomp/ds/TextDSFlags.hpp:10-15
+enum : u32 { DS_SA = 0x01, DS_ISA = 0x02, DS_LCP = 0x04, DS_PHI = 0x08, DS_PLCP = 0x10, DS_BWT = 0x100 };
+
+struct Factor {  // lzss::Factor, /root/reference/include/tudocomp/compressors/lzss/LZSSFactors.hpp:13-20 (packed 3 x u32)
+    u32 pos, src, len;
+};
+
+struct PhaseTime {
+    std::string name;
+    float ms;
+};
+
+// A bump allocator over one device allocation.  SA construction, LCP construction and factorisation run one after the
+// other and each re-carves the same scratch bytes.
+struct Arena {
+    uint8_t* base = nullptr;
+    size_t cap = 0, off = 0;
+    void reset() { off = 0; }
+    template <class T>
+    T* take(size_t count) {
+        size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+        if (off + bytes > cap) return nullptr;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += bytes;
+        return p;
+    }
+};
+
+struct Ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = 0;
+
+    // text (device), padded with zero bytes up to a multiple of 16 plus 64
+    u64 n = 0;
+    u64 cap_n = 0;  // capacity the buffers below were sized for
+    uint8_t* d_text = nullptr;
+
+    // results (device, persistent until the next load)
+    u32 *d_sa = nullptr, *d_isa = nullptr, *d_lcp = nullptr, *d_phi = nullptr, *d_plcp = nullptr;
+    uint8_t* d_bwt = nullptr;
+    u32 have = 0;  // DS_* bits that are valid
+    u32 max_lcp = 0;
+
+    // factor list
+    Factor* d_factors = nullptr;
+    u64 factors_cap = 0, num_factors = 0;
+    u32 flen_min = 0xffffffffu, flen_max = 0;
+
+    // scratch
+    Arena arena;
+    SortWorkspace sortws;
+    u32* d_scalars = nullptr;  // small device scratch (256 u32)
+    u32* h_scalars = nullptr;  // pinned mirror
+
+    // pinned staging for host<->device copies of caller buffers
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_cap = 0;
+
+    // stats
+    std::vector<PhaseTime> phases;
+    u32 sa_rounds = 0;
+    u64 sa_active_sum = 0;
+    u32 alphabet = 0, symbols_per_key = 0;
+};
+
+// suffix_array.cu
+int build_suffix_array(Ctx& c);  // fills d_sa and d_isa
+// lcp.cu
+int build_phi_bwt(Ctx& c, bool want_phi, bool want_bwt);
+int build_plcp_lcp(Ctx& c, bool want_lcp);
+// lzss_factorize.cu
+int factorize_lzss_lcp(Ctx& c, u32 threshold);
+
+struct PhaseTimer {  // CUDA-event timing of one phase on the context's stream
+    Ctx& c;
+    const char* name;
+    cudaEvent_t a, b;
+    PhaseTimer(Ctx& c_, const char* name_);
+    ~PhaseTimer();
+};
+
+}  // namespace tdc

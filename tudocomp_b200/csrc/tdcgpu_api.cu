@@ -1,0 +1,314 @@
+// C ABI of libtdcgpu (see include/tdcgpu.h for the contract and the reference interfaces each entry replaces).
+#include <cstdarg>
+#include <cstring>
+#include <new>
+
+#include "../../include/tdcgpu.h"
+#include "tdc_ctx.h"
+
+namespace tdc {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+PhaseTimer::PhaseTimer(Ctx& c_, const char* name_) : c(c_), name(name_), a(nullptr), b(nullptr) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, c.stream);
+}
+PhaseTimer::~PhaseTimer() {
+    cudaEventRecord(b, c.stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    c.phases.push_back(PhaseTime{name, ms});
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+}
+
+static const u64 TEXT_PAD = 1024;  // zero bytes readable past the text (8-byte LCE loads, warp-wide look-ahead)
+
+static void free_arrays(Ctx& c) {
+    void* ps[] = {c.d_text, c.d_sa, c.d_isa, c.d_lcp, c.d_phi, c.d_plcp, c.d_bwt, c.arena.base};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    c.d_text = nullptr;
+    c.d_sa = c.d_isa = c.d_lcp = c.d_phi = c.d_plcp = nullptr;
+    c.d_bwt = nullptr;
+    c.arena = Arena();
+    c.cap_n = 0;
+    c.have = 0;
+}
+
+static int ensure_capacity(Ctx& c, u64 n) {
+    if (n <= c.cap_n) return 0;
+    free_arrays(c);
+    TDC_CUDA(cudaMalloc(&c.d_text, n + TEXT_PAD + 16));
+    TDC_CUDA(cudaMalloc(&c.d_sa, sizeof(u32) * n));
+    TDC_CUDA(cudaMalloc(&c.d_isa, sizeof(u32) * n));
+    // scratch: SA construction is the high-water mark: 2 x u64 keys, 2 x u32 values, 2 x u32 slots, u32 group ids
+    const size_t arena_bytes = size_t(36) * n + n / 8 + (size_t(4) << 20);
+    TDC_CUDA(cudaMalloc(&c.arena.base, arena_bytes));
+    c.arena.cap = arena_bytes;
+    c.arena.off = 0;
+    TDC_TRY(sort_workspace_init(c.sortws, n, c.sm_count));
+    c.cap_n = n;
+    return 0;
+}
+
+template <class T>
+static int lazy_alloc(T** p, u64 count) {
+    if (*p) return 0;
+    TDC_CUDA(cudaMalloc(p, sizeof(T) * count));
+    return 0;
+}
+
+static int do_build(Ctx& c, u32 flags) {
+    if (c.n == 0) { set_error("no text loaded"); return TDCGPU_ERR_STATE; }
+    u32 need = flags;
+    if (need & DS_LCP) need |= DS_PLCP | DS_SA;
+    if (need & DS_PLCP) need |= DS_PHI | DS_SA;
+    if (need & (DS_PHI | DS_ISA | DS_BWT)) need |= DS_SA;
+    need |= (need & DS_SA) ? DS_ISA : 0;  // the doubling builder always produces both
+    need &= ~c.have;
+    if (!need) return 0;
+    if (need & DS_SA) {
+        PhaseTimer t(c, "Construct SA");  // also yields ISA ("Construct ISA" is free on this path)
+        TDC_TRY(build_suffix_array(c));
+        c.have |= DS_SA | DS_ISA;
+    }
+    if (need & (DS_PHI | DS_BWT)) {
+        PhaseTimer t(c, (need & DS_PHI) ? "Construct Phi Array" : "Construct BWT");
+        if (need & DS_PHI) TDC_TRY(lazy_alloc(&c.d_phi, c.cap_n));
+        if (need & DS_BWT) TDC_TRY(lazy_alloc(&c.d_bwt, c.cap_n));
+        TDC_TRY(build_phi_bwt(c, (need & DS_PHI) != 0, (need & DS_BWT) != 0));
+        c.have |= need & (DS_PHI | DS_BWT);
+    }
+    if (need & DS_PLCP) {
+        PhaseTimer t(c, (need & DS_LCP) ? "Construct PLCP+LCP Array" : "Construct PLCP Array");
+        TDC_TRY(lazy_alloc(&c.d_plcp, c.cap_n));
+        if (need & DS_LCP) TDC_TRY(lazy_alloc(&c.d_lcp, c.cap_n));
+        TDC_TRY(build_plcp_lcp(c, (need & DS_LCP) != 0));
+        c.have |= need & (DS_PLCP | DS_LCP);
+    }
+    return 0;
+}
+
+static void* array_ptr(Ctx& c, u32 which, size_t* elem) {
+    *elem = 4;
+    switch (which) {
+        case DS_SA: return c.d_sa;
+        case DS_ISA: return c.d_isa;
+        case DS_LCP: return c.d_lcp;
+        case DS_PHI: return c.d_phi;
+        case DS_PLCP: return c.d_plcp;
+        case DS_BWT: *elem = 1; return c.d_bwt;
+    }
+    return nullptr;
+}
+
+}  // namespace tdc
+
+using namespace tdc;
+
+struct tdcgpu_ctx {
+    Ctx c;
+};
+
+#define API_GUARD(ctx)                                         \
+    if (!(ctx)) { set_error("null context"); return TDCGPU_ERR_ARG; } \
+    Ctx& c = (ctx)->c;                                         \
+    if (cudaSetDevice(c.device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", c.device); return TDCGPU_ERR_CUDA; }
+
+extern "C" {
+
+const char* tdcgpu_last_error(void) { return g_err; }
+
+int tdcgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int tdcgpu_create(int device, tdcgpu_ctx** out) {
+    if (!out) { set_error("null out pointer"); return TDCGPU_ERR_ARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available (tdcgpu has no CPU fallback)");
+        return TDCGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return TDCGPU_ERR_ARG; }
+    TDC_CUDA(cudaSetDevice(device));
+    tdcgpu_ctx* h = new (std::nothrow) tdcgpu_ctx();
+    if (!h) { set_error("out of host memory"); return TDCGPU_ERR_NOMEM; }
+    Ctx& c = h->c;
+    c.device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c.d_scalars, 512 * sizeof(u32)) != cudaSuccess ||
+        cudaMallocHost(&c.h_scalars, 512 * sizeof(u32)) != cudaSuccess) {
+        set_error("context allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        delete h;
+        return TDCGPU_ERR_CUDA;
+    }
+    *out = h;
+    return 0;
+}
+
+void tdcgpu_destroy(tdcgpu_ctx* ctx) {
+    if (!ctx) return;
+    Ctx& c = ctx->c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    free_arrays(c);
+    sort_workspace_free(c.sortws);
+    if (c.d_factors) cudaFree(c.d_factors);
+    if (c.d_scalars) cudaFree(c.d_scalars);
+    if (c.h_scalars) cudaFreeHost(c.h_scalars);
+    cudaStreamDestroy(c.stream);
+    delete ctx;
+}
+
+int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_device) {
+    API_GUARD(ctx);
+    if (!text || n == 0) { set_error("empty text (the path always sees at least the sentinel)"); return TDCGPU_ERR_ARG; }
+    if (n >= (uint64_t(1) << 31)) { set_error("n = %llu: indices are 32-bit, n must be < 2^31", (unsigned long long)n); return TDCGPU_ERR_ARG; }
+    TDC_TRY(ensure_capacity(c, n));
+    c.n = n;
+    c.have = 0;
+    c.max_lcp = 0;
+    c.num_factors = 0;
+    c.phases.clear();
+    TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+    TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, TEXT_PAD + 16, c.stream));
+    if (!on_device) TDC_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its buffer
+    return 0;
+}
+
+int tdcgpu_textds_build(tdcgpu_ctx* ctx, uint32_t flags) {
+    API_GUARD(ctx);
+    c.phases.clear();
+    return do_build(c, flags);
+}
+
+int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device) {
+    API_GUARD(ctx);
+    size_t elem;
+    void* src = array_ptr(c, which, &elem);
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
+    TDC_CUDA(cudaMemcpyAsync(dst, src, elem * c.n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+const void* tdcgpu_textds_device_ptr(tdcgpu_ctx* ctx, uint32_t which) {
+    if (!ctx) return nullptr;
+    size_t elem;
+    void* p = array_ptr(ctx->c, which, &elem);
+    return (ctx->c.have & which) ? p : nullptr;
+}
+
+int tdcgpu_textds_max_lcp(tdcgpu_ctx* ctx, uint32_t* max_lcp) {
+    API_GUARD(ctx);
+    if (!(c.have & DS_PLCP)) { set_error("PLCP has not been built"); return TDCGPU_ERR_STATE; }
+    if (max_lcp) *max_lcp = c.max_lcp;
+    return 0;
+}
+
+int tdcgpu_lzss_lcp_factorize(tdcgpu_ctx* ctx, uint32_t threshold, uint64_t* count, uint32_t* min_len, uint32_t* max_len) {
+    API_GUARD(ctx);
+    c.phases.clear();
+    if (threshold < 1) { set_error("lzss_lcp: threshold must be >= 1"); return TDCGPU_ERR_ARG; }
+    TDC_TRY(do_build(c, DS_SA | DS_ISA | DS_LCP));
+    {
+        PhaseTimer t(c, "Factorize");
+        TDC_TRY(factorize_lzss_lcp(c, threshold));
+    }
+    if (count) *count = c.num_factors;
+    if (min_len) *min_len = c.flen_min;
+    if (max_len) *max_len = c.flen_max;
+    return 0;
+}
+
+int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t cap, int to_device) {
+    API_GUARD(ctx);
+    if (c.num_factors > cap) { set_error("factor buffer too small: %llu > %llu", (unsigned long long)c.num_factors, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
+    if (c.num_factors == 0) return 0;
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors,
+                             to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_textds_build_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp,
+                             uint32_t* phi, uint32_t* plcp, uint32_t* max_lcp) {
+    tdcgpu_ctx* h = nullptr;
+    int rc = tdcgpu_create(device, &h);
+    if (rc < 0) return rc;
+    uint32_t flags = 0;
+    if (sa) flags |= DS_SA;
+    if (isa) flags |= DS_ISA;
+    if (lcp) flags |= DS_LCP;
+    if (phi) flags |= DS_PHI;
+    if (plcp || max_lcp) flags |= DS_PLCP;
+    rc = tdcgpu_set_text(h, text, n, 0);
+    if (rc == 0) rc = tdcgpu_textds_build(h, flags);
+    if (rc == 0 && sa) rc = tdcgpu_textds_get(h, DS_SA, sa, 0);
+    if (rc == 0 && isa) rc = tdcgpu_textds_get(h, DS_ISA, isa, 0);
+    if (rc == 0 && lcp) rc = tdcgpu_textds_get(h, DS_LCP, lcp, 0);
+    if (rc == 0 && phi) rc = tdcgpu_textds_get(h, DS_PHI, phi, 0);
+    if (rc == 0 && plcp) rc = tdcgpu_textds_get(h, DS_PLCP, plcp, 0);
+    if (rc == 0 && max_lcp) rc = tdcgpu_textds_max_lcp(h, max_lcp);
+    tdcgpu_destroy(h);
+    return rc;
+}
+
+int tdcgpu_bwt_host(int device, const uint8_t* text, uint64_t n, uint8_t* out) {
+    tdcgpu_ctx* h = nullptr;
+    int rc = tdcgpu_create(device, &h);
+    if (rc < 0) return rc;
+    rc = tdcgpu_set_text(h, text, n, 0);
+    if (rc == 0) rc = tdcgpu_textds_build(h, DS_SA | DS_BWT);
+    if (rc == 0) rc = tdcgpu_textds_get(h, DS_BWT, out, 0);
+    tdcgpu_destroy(h);
+    return rc;
+}
+
+int tdcgpu_phase_count(tdcgpu_ctx* ctx) { return ctx ? int(ctx->c.phases.size()) : 0; }
+const char* tdcgpu_phase_name(tdcgpu_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= int(ctx->c.phases.size())) return nullptr;
+    return ctx->c.phases[i].name.c_str();
+}
+float tdcgpu_phase_ms(tdcgpu_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= int(ctx->c.phases.size())) return -1.f;
+    return ctx->c.phases[i].ms;
+}
+
+int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]) {
+    API_GUARD(ctx);
+    out[0] = c.sa_rounds;
+    out[1] = c.sa_active_sum;
+    out[2] = c.sortws.stat_passes;
+    out[3] = c.sortws.stat_elems;
+    out[4] = c.alphabet;
+    out[5] = c.symbols_per_key;
+    return 0;
+}
+
+int tdcgpu_sync(tdcgpu_ctx* ctx) {
+    API_GUARD(ctx);
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+}  // extern "C"
