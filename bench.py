@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: SA + ISA + LCP construction and lzss_lcp factorisation (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload dna|markov|repetitive]
+                    [--log2-bytes L]
+
+A "step" is one pass of the hot path over one synthetic text: set text -> TextDS(SA|ISA|LCP) -> Factorize(threshold 3).
+  value   input MB/s with the text already resident in HBM (device->device hand-over), CUDA events on the library's
+          stream around exactly K steps, max over ranks.
+  e2e     the same through the plugin-facing C-ABI call sequence with HOST buffers: pinned host text in (H2D inside the
+          timed region), factor list out to pinned host memory (D2H inside the timed region).
+  N > 1   block mode: every rank owns one GPU and an independent text of the same size (different seed), no data-path
+          collective ("scaling": "weak"); NCCL is used only for the barrier and the max over ranks.
+  --impl reference   times the reference's own CPU implementation (oracle/_ref, the unmodified tudocomp headers) on a
+          bounded sample of the same workload, rank 0 only.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "input MB/s for SA+LCP+lzss_lcp factorization"
+THRESHOLD = 3
+CPU_SAMPLE_LOG2 = 24  # 16 MiB of the same text: ~13 s of single-core reference work
+
+
+def gen_text(workload: str, n_body: int, seed: int) -> np.ndarray:
+    from tudocomp_b200 import synth
+
+    if workload == "dna":
+        return synth.dna(n_body, seed)
+    if workload == "markov":
+        return synth.markov_text(n_body, seed)
+    if workload == "repetitive":
+        return synth.repetitive(n_body, seed)
+    raise SystemExit(f"unknown workload {workload}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.samples, self.proc, self.thread = gpu_index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for p in self.samples:
+            try:
+                sm.append(float(p[0]))
+                mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the unmodified reference (oracle/_ref) on a bounded sample.  The only place bench.py executes oracle/.
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(sample: np.ndarray, steps: int):
+    path = os.path.join(ROOT, "oracle", "_ref", "libtdcref.so")
+    kind = "reference"
+    if os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        lib.tdcref_lzss_lcp_factors.restype = ctypes.c_int64
+
+        def one():
+            hdr = (ctypes.c_uint64 * 3)()
+            z = lib.tdcref_lzss_lcp_factors(sample.ctypes.data_as(ctypes.c_void_p), ctypes.c_uint64(sample.size),
+                                            ctypes.c_uint32(THRESHOLD), None, ctypes.c_uint64(0), hdr)
+            assert z >= 0
+            return z
+    else:  # the reference did not travel: fall back to the C restatement (kind "port")
+        kind = "port"
+        opath = os.path.join(ROOT, "oracle", "libtdcoracle.so")
+        if not os.path.exists(opath):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "libtdcoracle.so"])
+        lib = ctypes.CDLL(opath)
+        lib.tdcoracle_lzss_lcp_factorize.restype = ctypes.c_int64
+        n = sample.size
+        sa, isa, lcp = (np.zeros(n, np.uint32) for _ in range(3))
+        out = np.zeros((n, 3), np.uint32)
+        P = lambda a: a.ctypes.data_as(ctypes.c_void_p)  # noqa: E731
+
+        def one():
+            assert lib.tdcoracle_textds(P(sample), ctypes.c_uint32(n), P(sa), P(isa), P(lcp), None, None, None) == 0
+            return lib.tdcoracle_lzss_lcp_factorize(P(sa), P(isa), P(lcp), ctypes.c_uint32(n), ctypes.c_uint32(THRESHOLD), P(out), ctypes.c_uint64(n))
+
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+    return kind, times
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dna", choices=["dna", "markov", "repetitive"])
+    ap.add_argument("--log2-bytes", type=int, default=30, help="text body size per GPU = 2^L bytes (default 1 GiB)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_body = 1 << args.log2_bytes
+    seed_of = {"dna": 2, "markov": 1, "repetitive": 3}[args.workload]
+    workload_name = f"{args.workload}_2^{args.log2_bytes}B_per_gpu: TextDS SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD}) factorize"
+    config = {"workload": workload_name, "text_bytes_per_gpu": n_body + 1, "threshold": THRESHOLD, "index_bits": 32,
+              "l2_policy": "inputs (>= 1 GiB text, 4 GiB arrays) are far larger than the 126 MB L2; no flush needed",
+              "parallelism": f"block mode, {max(world, args.gpus)} independent texts, no collective"}
+
+    # ------------------------------------------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        sample_body = min(n_body, 1 << CPU_SAMPLE_LOG2)
+        sample = gen_text(args.workload, sample_body, seed_of)  # same generator and seed as rank 0's text
+        kind, times = cpu_reference_run(sample, args.warmup + args.steps)
+        times = times[args.warmup:]
+        mbps = sample_body / 1e6 / (sum(times) / len(times))
+        line = {"impl": "reference", "metric": METRIC, "value": mbps, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": 1, "kind": kind,
+                                 "sample": f"first 2^{int(np.log2(sample_body))} B of the workload text + sentinel; the reference is single-threaded"},
+                "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------ our arm
+    import torch
+
+    import tudocomp_b200 as tdc
+
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    lib = tdc.load()  # raises if the CUDA library is missing: no fallback
+    ctx = tdc.Context(lib, dev)
+
+    text = gen_text(args.workload, n_body, seed_of + 1000 * rank)
+    n = int(text.size)
+    h_text = torch.from_numpy(text).pin_memory()
+    d_text = h_text.to(f"cuda:{dev}", non_blocking=False)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.set_text_device(d_text.data_ptr(), n)
+        ctx.build(tdc.SA | tdc.ISA | tdc.LCP)
+        return ctx.factorize(THRESHOLD)
+
+    # factor buffer on the host for the e2e arm (pinned), sized after the first step
+    z0, _, _ = step_resident()
+    h_factors = torch.empty(int(z0 * 1.05) + 1024, 3, dtype=torch.int32).pin_memory()
+
+    def step_e2e():
+        ctx.set_text_host_ptr(h_text.data_ptr(), n)
+        ctx.build(tdc.SA | tdc.ISA | tdc.LCP)
+        z, mn, mx = ctx.factorize(THRESHOLD)
+        ctx.get_factors_into(h_factors.data_ptr(), h_factors.shape[0])
+        return z, mn, mx
+
+    for _ in range(args.warmup):
+        z, mn, mx = step_resident()
+
+    # ---- timed: resident ----
+    sampler = ClockSampler(dev)
+    sampler.start()
+    lib.profile_reset()
+    lib.profile_enable(True)
+    barrier()
+    launches0 = lib.launch_count()
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        z, mn, mx = step_resident()
+    ctx.event_record(1)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    launches = lib.launch_count() - launches0
+    lib.profile_enable(False)
+    prof = lib.profile()
+    stats = ctx.sa_stats()
+    phases = ctx.phases()
+
+    # ---- timed: end to end with host buffers ----
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    barrier()
+    ctx.event_record(2)
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        ze, _, _ = step_e2e()
+    ctx.event_record(3)
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+    dev_ms_e2e = max(ctx.event_elapsed_ms(2, 3), 1e3 * wall_e2e)  # host-inclusive, take the larger
+    clocks = sampler.stop()
+
+    ms_step = dev_ms / args.steps
+    ms_step_e2e = dev_ms_e2e / args.steps
+    if world > 1:
+        tt = torch.tensor([ms_step, ms_step_e2e], device=f"cuda:{dev}", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, ms_step_e2e = float(tt[0]), float(tt[1])
+    total_bytes = n_body * world
+    value = total_bytes / 1e6 / (ms_step / 1e3)
+    e2e_value = total_bytes / 1e6 / (ms_step_e2e / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+        # dominant kernel: the radix-sort digit pass
+        dom_name = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+        roof = None
+        if dom_name:
+            d = prof[dom_name]
+            per_launch_bytes = d["bytes"] / max(d["launches"], 1)
+            per_launch_ms = d["ms"] / max(d["launches"], 1)
+            achieved = per_launch_bytes / 1e9 / (per_launch_ms / 1e3) if d["bytes"] else None
+            roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "launches": d["launches"], "avg_launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
+                    "share_of_step": d["ms"] / dev_ms}
+        pipeline_bytes = (25.0 * n + 12.0 * z)  # compulsory traffic of SA+ISA+LCP+factorisation
+        pipeline = {"algorithmic_bytes": pipeline_bytes, "achieved_GBps": pipeline_bytes / 1e9 / (ms_step / 1e3),
+                    "frac_of_peak": pipeline_bytes / 1e9 / (ms_step / 1e3) / peak}
+        line = {"metric": METRIC, "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+                "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(12 * ze),
+                        "ms_per_step": ms_step_e2e},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "pipeline_roofline": pipeline,
+                "factors": int(z), "factor_len": [int(mn), int(mx)], "sa_stats": stats,
+                "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "last_step_phases_ms": {k: round(v, 3) for k, v in phases}, "wall_s_timed": wall}
+        if not args.no_cpu_baseline:
+            sample_body = min(n_body, 1 << CPU_SAMPLE_LOG2)
+            sample = text[: sample_body + 1].copy()
+            sample[-1] = 0
+            kind, times = cpu_reference_run(sample, 1)
+            line["cpu_baseline"] = {"value": sample_body / 1e6 / times[0], "unit": "MB/s", "cores": 1, "kind": kind,
+                                    "host_cores_available": os.cpu_count(),
+                                    "sample": f"first 2^{int(np.log2(sample_body))} B of rank 0's text + sentinel, one run; the reference is single-threaded"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -103,6 +103,19 @@ int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]);
 /* Block until all work queued on the context's stream is done. */
 int tdcgpu_sync(tdcgpu_ctx* ctx);
 
+/* ---- measurement hooks (no reference counterpart; the reference times phases with StatPhase on the host) ---- */
+/* CUDA events on the context's stream: record into slot 0..7, elapsed time between two recorded slots. */
+int tdcgpu_event_record(tdcgpu_ctx* ctx, int slot);
+int tdcgpu_event_elapsed_ms(tdcgpu_ctx* ctx, int slot_a, int slot_b, float* ms);
+/* Number of CUDA kernels this library has launched in this process. */
+uint64_t tdcgpu_launch_count(void);
+/* Optional per-kernel timing: every launch is bracketed by CUDA events on its stream and aggregated by kernel name
+ * (launch count, device ms, algorithmic bytes where the host knows them). */
+void tdcgpu_profile_enable(int on);
+void tdcgpu_profile_reset(void);
+int tdcgpu_profile_count(void);
+int tdcgpu_profile_entry(int i, const char** name, uint64_t* launches, double* ms, double* bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -404,3 +404,4 @@ template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute,
 #define TDC_LAUNCH(kernel, grid, block, smem, stream, ...) \
     cusim::launch(dim3(grid), dim3(block), (smem), [&]() { kernel(__VA_ARGS__); })
 #define TDC_DYN_SMEM(name) unsigned char* name = cusim::S().dyn_smem
+namespace tdc { inline void prof_add_bytes(const char*, double) {} }

@@ -17,6 +17,8 @@ EXPORTS = [
     "tdcgpu_textds_build", "tdcgpu_textds_get", "tdcgpu_textds_device_ptr", "tdcgpu_textds_max_lcp",
     "tdcgpu_lzss_lcp_factorize", "tdcgpu_lzss_lcp_get_factors", "tdcgpu_textds_build_host", "tdcgpu_bwt_host",
     "tdcgpu_phase_count", "tdcgpu_phase_name", "tdcgpu_phase_ms", "tdcgpu_sa_stats", "tdcgpu_sync",
+    "tdcgpu_event_record", "tdcgpu_event_elapsed_ms", "tdcgpu_launch_count", "tdcgpu_profile_enable",
+    "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -56,6 +58,14 @@ class TdcGpuLib:
         L.tdcgpu_phase_ms.restype = C.c_float
         L.tdcgpu_sa_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.tdcgpu_sync.argtypes = [C.c_void_p]
+        L.tdcgpu_event_record.argtypes = [C.c_void_p, C.c_int]
+        L.tdcgpu_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        L.tdcgpu_launch_count.restype = C.c_uint64
+        L.tdcgpu_profile_enable.argtypes = [C.c_int]
+        L.tdcgpu_profile_enable.restype = None
+        L.tdcgpu_profile_reset.restype = None
+        L.tdcgpu_profile_entry.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_double)]
 
     def check(self, rc: int) -> None:
         if rc < 0:
@@ -63,6 +73,24 @@ class TdcGpuLib:
 
     def device_count(self) -> int:
         return int(self.lib.tdcgpu_device_count())
+
+    def launch_count(self) -> int:
+        return int(self.lib.tdcgpu_launch_count())
+
+    def profile_enable(self, on: bool) -> None:
+        self.lib.tdcgpu_profile_enable(1 if on else 0)
+
+    def profile_reset(self) -> None:
+        self.lib.tdcgpu_profile_reset()
+
+    def profile(self) -> dict:
+        """kernel name -> dict(launches, ms, bytes) aggregated since the last reset (resolves pending events)."""
+        out = {}
+        for i in range(self.lib.tdcgpu_profile_count()):
+            name, n, ms, by = C.c_char_p(), C.c_uint64(), C.c_double(), C.c_double()
+            self.check(self.lib.tdcgpu_profile_entry(i, C.byref(name), C.byref(n), C.byref(ms), C.byref(by)))
+            out[name.value.decode()] = dict(launches=int(n.value), ms=float(ms.value), bytes=float(by.value))
+        return out
 
 
 def _host_ptr(a: np.ndarray) -> C.c_void_p:
@@ -151,3 +179,18 @@ class Context:
 
     def sync(self) -> None:
         self.lib.check(self.lib.lib.tdcgpu_sync(self._h))
+
+    def event_record(self, slot: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self.lib.check(self.lib.lib.tdcgpu_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return float(ms.value)
+
+    def get_factors_into(self, host_ptr: int, cap: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_lzss_lcp_get_factors(self._h, C.c_void_p(host_ptr), cap, 0))
+
+    def set_text_host_ptr(self, host_ptr: int, n: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_set_text(self._h, C.c_void_p(host_ptr), n, 0))
+        self.n = int(n)

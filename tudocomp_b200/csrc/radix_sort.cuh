@@ -263,8 +263,9 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
         TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
         TDC_CUDA(cudaMemsetAsync(ws.tile_counter, 0, sizeof(u32) * RS_MAX_PASSES, st));
         const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
-        auto hk = rs_histogram_kernel<K>;
-        TDC_LAUNCH(hk, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
+        auto rs_histogram = rs_histogram_kernel<K>;
+        TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
+        prof_add_bytes("rs_histogram", double(m) * sizeof(K));
         TDC_LAUNCH(rs_scan_kernel, plan.npass, 256, 0, st, ws.hist, ws.uniform, m);
         TDC_KCHECK();
         TDC_CUDA(cudaMemcpyAsync(ws.h_uniform, ws.uniform, sizeof(u32) * RS_MAX_PASSES, cudaMemcpyDeviceToHost, st));
@@ -274,14 +275,17 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
         for (int p = 0; p < plan.npass; p++) {
             if (ws.h_uniform[p]) continue;  // every key has the same digit here: the pass would be the identity
             ws.epoch++;
+            // algorithmic bytes of one pass: keys and values read once, written once
             if (need_iota) {
-                auto kern = rs_onesweep_kernel<K, true>;
-                TDC_LAUNCH(kern, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m, plan.shift[p],
-                           plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                auto rs_onesweep_iota = rs_onesweep_kernel<K, true>;
+                TDC_LAUNCH(rs_onesweep_iota, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m,
+                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                prof_add_bytes("rs_onesweep_iota", double(m) * (2 * sizeof(K) + 4));
             } else {
-                auto kern = rs_onesweep_kernel<K, false>;
-                TDC_LAUNCH(kern, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m, plan.shift[p],
-                           plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                auto rs_onesweep = rs_onesweep_kernel<K, false>;
+                TDC_LAUNCH(rs_onesweep, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m,
+                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                prof_add_bytes("rs_onesweep", double(m) * (2 * sizeof(K) + 8));
             }
             TDC_KCHECK();
             need_iota = false;

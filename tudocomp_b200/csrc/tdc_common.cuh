@@ -5,7 +5,13 @@
 
 #ifndef TDC_CUSIM
 #include <cuda_runtime.h>
-#define TDC_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+// every kernel launch goes through this macro: it counts launches and, when profiling is on, brackets the launch with
+// CUDA events on the launching stream (tdcgpu_profile_* in include/tdcgpu.h)
+#define TDC_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+    do {                                                                   \
+        tdc::LaunchScope ls__(#kernel, (stream));                          \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);        \
+    } while (0)
 #define TDC_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
@@ -17,6 +23,19 @@ typedef unsigned long long ull;
 
 static const u32 kWarp = 32;
 static const u32 kFull = 0xffffffffu;
+
+// ----------------------------------------------------------------------------------------------------------------
+// launch accounting / optional per-kernel event timing (tdcgpu_api.cu)
+// ----------------------------------------------------------------------------------------------------------------
+#ifndef TDC_CUSIM
+struct LaunchScope {
+    int slot;
+    cudaStream_t st;
+    LaunchScope(const char* name, cudaStream_t stream);
+    ~LaunchScope();
+};
+#endif
+void prof_add_bytes(const char* name, double bytes);  // algorithmic bytes of the launch just issued under `name`
 
 // ----------------------------------------------------------------------------------------------------------------
 // error plumbing: kernels never abort; host wrappers return negative codes and stash a message (tdcgpu_last_error)

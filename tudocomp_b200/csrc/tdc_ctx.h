@@ -67,6 +67,8 @@ struct Ctx {
     uint8_t* h_stage = nullptr;
     size_t h_stage_cap = 0;
 
+    cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+
     // stats
     std::vector<PhaseTime> phases;
     u32 sa_rounds = 0;

@@ -17,6 +17,73 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// ---- launch accounting + optional per-kernel event timing -------------------------------------------------------
+struct ProfEntry {
+    std::string name;
+    u64 launches = 0;
+    double ms = 0, bytes = 0;
+};
+struct PendingLaunch {
+    int entry;
+    cudaEvent_t a, b;
+};
+static u64 g_launches = 0;
+static bool g_prof_on = false;
+static std::vector<ProfEntry> g_prof;
+static std::vector<PendingLaunch> g_pending;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static int prof_entry(const char* name) {
+    for (size_t i = 0; i < g_prof.size(); i++)
+        if (g_prof[i].name == name) return int(i);
+    ProfEntry e;
+    e.name = name;
+    g_prof.push_back(e);
+    return int(g_prof.size()) - 1;
+}
+static cudaEvent_t take_event() {
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+#ifndef TDC_CUSIM
+LaunchScope::LaunchScope(const char* name, cudaStream_t stream) : slot(-1), st(stream) {
+    g_launches++;
+    if (!g_prof_on) return;
+    PendingLaunch p;
+    p.entry = prof_entry(name);
+    p.a = take_event();
+    p.b = take_event();
+    cudaEventRecord(p.a, st);
+    g_pending.push_back(p);
+    slot = int(g_pending.size()) - 1;
+}
+LaunchScope::~LaunchScope() {
+    if (slot >= 0) cudaEventRecord(g_pending[slot].b, st);
+}
+void prof_add_bytes(const char* name, double bytes) {
+    if (!g_prof_on) return;
+    g_prof[prof_entry(name)].bytes += bytes;
+}
+#endif
+static void prof_resolve() {  // call after the stream has been synchronised
+    for (auto& p : g_pending) {
+        float ms = 0;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            g_prof[p.entry].ms += ms;
+            g_prof[p.entry].launches++;
+        }
+        g_event_pool.push_back(p.a);
+        g_event_pool.push_back(p.b);
+    }
+    g_pending.clear();
+}
+
 PhaseTimer::PhaseTimer(Ctx& c_, const char* name_) : c(c_), name(name_), a(nullptr), b(nullptr) {
     cudaEventCreate(&a);
     cudaEventCreate(&b);
@@ -173,6 +240,8 @@ void tdcgpu_destroy(tdcgpu_ctx* ctx) {
     if (c.d_factors) cudaFree(c.d_factors);
     if (c.d_scalars) cudaFree(c.d_scalars);
     if (c.h_scalars) cudaFreeHost(c.h_scalars);
+    for (auto& e : c.user_events)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
     delete ctx;
 }
@@ -308,6 +377,48 @@ int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]) {
 int tdcgpu_sync(tdcgpu_ctx* ctx) {
     API_GUARD(ctx);
     TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_event_record(tdcgpu_ctx* ctx, int slot) {
+    API_GUARD(ctx);
+    if (slot < 0 || slot >= 8) { set_error("event slot out of range"); return TDCGPU_ERR_ARG; }
+    if (!c.user_events[slot]) TDC_CUDA(cudaEventCreate(&c.user_events[slot]));
+    TDC_CUDA(cudaEventRecord(c.user_events[slot], c.stream));
+    return 0;
+}
+
+int tdcgpu_event_elapsed_ms(tdcgpu_ctx* ctx, int slot_a, int slot_b, float* ms) {
+    API_GUARD(ctx);
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !c.user_events[slot_a] || !c.user_events[slot_b] || !ms) {
+        set_error("bad event slots");
+        return TDCGPU_ERR_ARG;
+    }
+    TDC_CUDA(cudaEventSynchronize(c.user_events[slot_b]));
+    TDC_CUDA(cudaEventElapsedTime(ms, c.user_events[slot_a], c.user_events[slot_b]));
+    return 0;
+}
+
+uint64_t tdcgpu_launch_count(void) { return g_launches; }
+
+void tdcgpu_profile_enable(int on) { g_prof_on = on != 0; }
+
+void tdcgpu_profile_reset(void) {
+    prof_resolve();
+    g_prof.clear();
+}
+
+int tdcgpu_profile_count(void) {
+    prof_resolve();
+    return int(g_prof.size());
+}
+
+int tdcgpu_profile_entry(int i, const char** name, uint64_t* launches, double* ms, double* bytes) {
+    if (i < 0 || i >= int(g_prof.size())) { set_error("profile index out of range"); return TDCGPU_ERR_ARG; }
+    if (name) *name = g_prof[i].name.c_str();
+    if (launches) *launches = g_prof[i].launches;
+    if (ms) *ms = g_prof[i].ms;
+    if (bytes) *bytes = g_prof[i].bytes;
     return 0;
 }
 
