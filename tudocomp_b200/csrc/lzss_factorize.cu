@@ -137,7 +137,11 @@ lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lenside) {
 // greedy chain
 // ---------------------------------------------------------------------------------------------------------------
 static const int CH_THREADS = 512;
+#ifdef TDC_CUSIM
+static const int CH_IPT = 2;  // small tiles so that the CPU tests cross many tile/region boundaries
+#else
 static const int CH_IPT = 16;
+#endif
 static const int CH_TILE = CH_THREADS * CH_IPT;  // text positions per tile
 static const u32 CH_NONE = 0xffffffffu;
 
@@ -181,14 +185,46 @@ chain_exit_kernel(const u32* __restrict__ lenside, u32 n, u32* __restrict__ exit
     }
 }
 
-// scalar walk over tile exits: the first visited position of every tile the chain touches
-__global__ void chain_entries_kernel(const u32* __restrict__ exitp, u32 n, u32* __restrict__ entry) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    u32 x = 0;
-    while (x < n - 1) {
-        entry[x / CH_TILE] = x;
+// The first visited position ("entry") of every tile the chain touches.  The chain is a dependent pointer walk over
+// tile exits, so it is split: `regions` walkers start speculatively at their region's first position (as if it were
+// visited) and record the entries of their own path; a scalar stitcher then follows the TRUE chain and, in each
+// region, only walks until it lands on a node the region's walker also visited — from there on the two paths are
+// identical, so the walker's remaining entries are already right and the stitcher jumps to the walker's exit.
+// Entries the stitcher skips over (speculative but not on the true chain) are erased.
+__global__ void __launch_bounds__(128)
+chain_entries_spec_kernel(const u32* __restrict__ exitp, u32 n, u32 tiles_per_region, u32 regions,
+                          u32* __restrict__ entry, u32* __restrict__ region_exit) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= regions) return;
+    const u64 start = u64(r) * tiles_per_region * CH_TILE;
+    const u64 end = min(start + u64(tiles_per_region) * CH_TILE, u64(n - 1));
+    u64 x = start;
+    while (x < end) {
+        entry[x / CH_TILE] = u32(x);
         x = exitp[x];
     }
+    region_exit[r] = u32(min(x, u64(0xffffffffu)));
+}
+
+__global__ void chain_entries_stitch_kernel(const u32* __restrict__ exitp, u32 n, u32 tiles_per_region,
+                                            u32* __restrict__ entry, const u32* __restrict__ region_exit) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    u32 x = 0, clear_from = 0;
+    while (x < n - 1) {
+        const u32 t = x / CH_TILE;
+        for (u32 tt = clear_from; tt < t; tt++) entry[tt] = CH_NONE;
+        if (entry[t] == x) {  // merged with the region walker's path
+            const u32 r = t / tiles_per_region;
+            x = region_exit[r];
+            clear_from = (r + 1) * tiles_per_region;
+        } else {
+            entry[t] = x;
+            x = exitp[x];
+            clear_from = t + 1;
+        }
+    }
+    const u32 ntiles = (n + CH_TILE - 1) / CH_TILE;
+    for (u32 tt = clear_from; tt < ntiles; tt++) entry[tt] = CH_NONE;
 }
 
 // mark the visited positions of a tile by pointer doubling; output one bit per position that starts a factor
@@ -228,7 +264,7 @@ chain_mark_kernel(const u32* __restrict__ lenside, u32 n, const u32* __restrict_
         if (threadIdx.x == 0) flag = 0;
         __syncthreads();
         // A: marked nodes mark their current jump target (every target is a true chain node)
-        const u32 mw = (mark[j0 >> 5] >> (j0 & 31)) & 0xffffu;
+        const u32 mw = (mark[j0 >> 5] >> (j0 & 31)) & u32((1ull << CH_IPT) - 1ull);
         bool prop = false;
         if (mw) {
 #pragma unroll
@@ -385,7 +421,17 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
     // ---- 3. chain ----
     TDC_LAUNCH(chain_exit_kernel, ntiles, CH_THREADS, 0, st, lenside, n, exitp);
     TDC_LAUNCH(fill_u32_kernel, u32(div_up(u64(ntiles), 256)), 256, 0, st, entry, u64(ntiles), CH_NONE);
-    TDC_LAUNCH(chain_entries_kernel, 1, 32, 0, st, exitp, n, entry);
+    {
+        // regions ~ sqrt(ntiles / 2): the walkers' hops (tiles per region) balance the stitcher's hops (~2 per region)
+        u32 regions = 1;
+        while (u64(regions) * regions * 2 < ntiles) regions *= 2;
+        const u32 tiles_per_region = u32(div_up(u64(ntiles), regions));
+        regions = u32(div_up(u64(ntiles), tiles_per_region));
+        u32* region_exit = c.arena.take<u32>(regions);
+        if (!region_exit) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+        TDC_LAUNCH(chain_entries_spec_kernel, u32(div_up(u64(regions), 128)), 128, 0, st, exitp, n, tiles_per_region, regions, entry, region_exit);
+        TDC_LAUNCH(chain_entries_stitch_kernel, 1, 32, 0, st, exitp, n, tiles_per_region, entry, region_exit);
+    }
     TDC_LAUNCH(chain_mark_kernel, ntiles, CH_THREADS, 0, st, lenside, n, entry, fmask, tile_cnt);
     u32* d_total = c.d_scalars + 0;
     u32* d_minmax = c.d_scalars + 2;

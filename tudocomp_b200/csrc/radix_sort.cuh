@@ -12,7 +12,17 @@
 
 namespace tdc {
 
-static const int RS_THREADS = 512;
+#ifndef RS_THREADS_CFG
+#define RS_THREADS_CFG 256
+#endif
+#ifndef RS_IPT64_CFG
+#define RS_IPT64_CFG 12
+#endif
+#ifndef RS_MIN_CTAS_CFG
+#define RS_MIN_CTAS_CFG 4
+#endif
+static const int RS_THREADS = RS_THREADS_CFG;  // >= 256: one thread per digit in the look-back
+static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
 static const int RS_WARPS = RS_THREADS / 32;
 static const int RS_RADIX = 256;
 static const int RS_MAX_PASSES = 8;
@@ -26,7 +36,6 @@ struct PassPlan {
 struct SortWorkspace {
     u32* hist = nullptr;          // device [RS_MAX_PASSES][256]: digit counts, then exclusive bucket starts
     u32* uniform = nullptr;       // device [RS_MAX_PASSES]: 1 if one bin holds every key (pass can be skipped)
-    u32* tile_counter = nullptr;  // device [RS_MAX_PASSES]: dynamic tile ids (look-back needs start order == id order)
     ull* desc = nullptr;          // device [max_tiles][256] look-back descriptors
     u32* h_uniform = nullptr;     // pinned host mirror of `uniform`
     u64 max_tiles = 0;
@@ -37,7 +46,7 @@ struct SortWorkspace {
 };
 
 template <class K> struct RsCfg;
-template <> struct RsCfg<u64> { static const int IPT = 12; };
+template <> struct RsCfg<u64> { static const int IPT = RS_IPT64_CFG; };
 template <> struct RsCfg<u32> { static const int IPT = 16; };
 
 static const ull RS_STATUS_AGG = 1, RS_STATUS_PREFIX = 2;
@@ -106,11 +115,26 @@ static __global__ void __launch_bounds__(256) rs_scan_kernel(u32* __restrict__ g
 // ---------------------------------------------------------------------------------------------------------------
 // one digit pass
 // ---------------------------------------------------------------------------------------------------------------
+// peers of this lane = lanes holding the same digit.  Eight ballots instead of match.any: MATCH is a slow-path
+// instruction on sm_100 (ncu: 43 % of the kernel's stall samples sat on its result), VOTE is full rate.
+__device__ __forceinline__ u32 match_digit(u32 d, u32 nbits_mask) {
+    u32 peers = kFull;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if ((nbits_mask >> b) & 1u) {  // warp-uniform: digits of the last pass may be narrower than 8 bits
+            const u32 bal = __ballot_sync(kFull, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? bal : ~bal;
+        }
+    }
+    return peers;
+}
+
+// Tile ids are blockIdx.x: CTAs of a 1-D grid are dispatched in index order, so every predecessor a tile looks back
+// at is resident or finished (the same assumption CUB's decoupled look-back scan makes).
 template <class K, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
 rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* __restrict__ vin, u32* __restrict__ vout,
-                   u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc,
-                   u32* __restrict__ tile_counter, u32 epoch) {
+                   u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc, u32 epoch) {
     constexpr int IPT = RsCfg<K>::IPT;
     constexpr int TILE = RS_THREADS * IPT;
     TDC_DYN_SMEM(smem_raw);
@@ -119,15 +143,10 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     u32* warp_cnt = svals + TILE;                                               // [RS_WARPS][256]
     u32* digit_start = warp_cnt + RS_WARPS * RS_RADIX;                          // [256]
     u32* gbase = digit_start + RS_RADIX;                                        // [256]
-    u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch + tile id
+    u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
-    if (tid == 0) misc[34] = atomicAdd(tile_counter, 1u);
-    u32* my_cnt = warp_cnt + w * RS_RADIX;
-#pragma unroll
-    for (int j = 0; j < RS_RADIX / 32; j++) my_cnt[j * 32 + lane] = 0;
-    __syncthreads();
-    const u32 tile = misc[34];
+    const u32 tile = blockIdx.x;
     const u64 tile_base = u64(tile) * TILE;
     const u32 count = u32(min(u64(TILE), m - tile_base));
 
@@ -140,11 +159,15 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u64 idx = wbase + u32(k) * 32 + lane;
         key[k] = idx < m ? kin[idx] : ~K(0);
     }
+    u32* my_cnt = warp_cnt + w * RS_RADIX;
+#pragma unroll
+    for (int j = 0; j < RS_RADIX / 32; j++) my_cnt[j * 32 + lane] = 0;
+    __syncwarp();
     // ---- stable rank inside the warp ----
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const u32 d = u32(key[k] >> shift) & mask;
-        const u32 peers = __match_any_sync(kFull, d);
+        const u32 peers = match_digit(d, mask);
         const u32 before = __popc(peers & lanemask_lt());
         const u32 c = my_cnt[d];
         __syncwarp();
@@ -165,22 +188,22 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
             run += t;
         }
         total = run;
+        // publish the tile's count of this digit as early as possible (successors are waiting on it)
+        u32 pub = total;
+        if (tid == mask) pub -= (u32(TILE) - count);  // padding keys (~0) sit in the top bin and are never written
+        if (tile != 0) desc_store(desc + u64(tile) * RS_RADIX + tid, (ull(epoch) << 34) | (RS_STATUS_AGG << 32) | pub);
     }
     u32 blk_total;
     const u32 ex = block_exclusive_sum<u32>(total, misc, &blk_total);  // threads >= 256 contribute 0
     if (tid < RS_RADIX) {
         digit_start[tid] = ex;
-        // padding keys (~0) of a partial tile were counted in the top bin; they sort last and are never written
         u32 pub = total;
         if (tid == mask) pub -= (u32(TILE) - count);
         // ---- decoupled look-back for digit `tid` ----
         const ull tag = ull(epoch) << 34;
         ull* my_desc = desc + u64(tile) * RS_RADIX + tid;
         u32 exclusive = 0;
-        if (tile == 0) {
-            desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | pub);
-        } else {
-            desc_store(my_desc, tag | (RS_STATUS_AGG << 32) | pub);
+        if (tile != 0) {
             const ull* look = my_desc - RS_RADIX;
             while (true) {
                 const ull v = desc_load(look);
@@ -189,8 +212,8 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
                 if (((v >> 32) & 3) == RS_STATUS_PREFIX) break;
                 look -= RS_RADIX;
             }
-            desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
         }
+        desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
         gbase[tid] = bucket_start[tid] + exclusive - ex;
     }
     __syncthreads();
@@ -261,7 +284,6 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
     if (plan.npass > 0) {
         TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
         TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
-        TDC_CUDA(cudaMemsetAsync(ws.tile_counter, 0, sizeof(u32) * RS_MAX_PASSES, st));
         const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
         auto rs_histogram = rs_histogram_kernel<K>;
         TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
@@ -279,12 +301,12 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
             if (need_iota) {
                 auto rs_onesweep_iota = rs_onesweep_kernel<K, true>;
                 TDC_LAUNCH(rs_onesweep_iota, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m,
-                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.epoch);
                 prof_add_bytes("rs_onesweep_iota", double(m) * (2 * sizeof(K) + 4));
             } else {
                 auto rs_onesweep = rs_onesweep_kernel<K, false>;
                 TDC_LAUNCH(rs_onesweep, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], v[cur], v[cur ^ 1], m,
-                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.tile_counter + p, ws.epoch);
+                           plan.shift[p], plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.epoch);
                 prof_add_bytes("rs_onesweep", double(m) * (2 * sizeof(K) + 8));
             }
             TDC_KCHECK();

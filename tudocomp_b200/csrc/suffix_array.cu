@@ -257,7 +257,6 @@ int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count) {
     ws.max_tiles = (t64 > t32 ? t64 : t32) + 1;
     TDC_CUDA(cudaMalloc(&ws.hist, sizeof(u32) * RS_MAX_PASSES * RS_RADIX));
     TDC_CUDA(cudaMalloc(&ws.uniform, sizeof(u32) * RS_MAX_PASSES));
-    TDC_CUDA(cudaMalloc(&ws.tile_counter, sizeof(u32) * RS_MAX_PASSES));
     TDC_CUDA(cudaMalloc(&ws.desc, sizeof(ull) * ws.max_tiles * RS_RADIX));
     TDC_CUDA(cudaMemset(ws.desc, 0, sizeof(ull) * ws.max_tiles * RS_RADIX));
     TDC_CUDA(cudaMallocHost(&ws.h_uniform, sizeof(u32) * RS_MAX_PASSES));
@@ -274,10 +273,8 @@ int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count) {
 void sort_workspace_free(SortWorkspace& ws) {
     if (ws.hist) cudaFree(ws.hist);
     if (ws.uniform) cudaFree(ws.uniform);
-    if (ws.tile_counter) cudaFree(ws.tile_counter);
     if (ws.desc) cudaFree(ws.desc);
     if (ws.h_uniform) cudaFreeHost(ws.h_uniform);
-    ws.hist = ws.uniform = ws.tile_counter = nullptr;
     ws.desc = nullptr;
     ws.h_uniform = nullptr;
     ws.max_tiles = 0;
