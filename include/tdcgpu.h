@@ -69,7 +69,7 @@ int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device)
 /* Device pointer of a built structure (valid until the next set_text/destroy); NULL if not built. */
 const void* tdcgpu_textds_device_ptr(tdcgpu_ctx* ctx, uint32_t which);
 
-/* max over PLCP[0..n-2] — PLCPFromPhi::max_lcp(), ds/PLCPFromPhi.hpp:40,55-57 */
+/* max over PLCP[0..n-2] (= max LCP) — PLCPFromPhi::max_lcp(), ds/PLCPFromPhi.hpp:40,55-57; needs PLCP or LCP built */
 int tdcgpu_textds_max_lcp(tdcgpu_ctx* ctx, uint32_t* max_lcp);
 
 /* Greedy lzss_lcp factorisation — the "Factorize" phase of LZSSLCPCompressor::compress
@@ -97,8 +97,9 @@ float tdcgpu_phase_ms(tdcgpu_ctx* ctx, int i);
 
 /* Work-model counters of the last SA build: [0] doubling rounds incl. the initial sort, [1] sum of
  * active suffixes over rounds, [2] radix passes executed, [3] elements moved by those passes, [4] alphabet size,
- * [5] symbols per initial key. */
-int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]);
+ * [5] symbols per initial key, [6] LCP route of the last LCP build (1 = direct comparison in SA order, 2 = Phi/PLCP as
+ * in the reference), [7] sum over rounds of active suffixes x known common prefix (the route's LCP-sum estimate). */
+int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[8]);
 
 /* Block until all work queued on the context's stream is done. */
 int tdcgpu_sync(tdcgpu_ctx* ctx);

@@ -56,3 +56,25 @@ def test_sim_synthetic_multi_tile(simlib, oracle):
         if t.size > 21000:
             continue  # keep the CPU suite short; the larger cases run on the GPU
         _check(simlib, oracle, name, t, thresholds=(3, 5))
+
+
+def test_sim_lcp_only_routes(simlib, oracle):
+    """LCP without Phi/PLCP: short-prefix texts take the direct comparison route, repetitive ones the Phi route."""
+    from tudocomp_b200 import synth
+    cases = [("dna", synth.dna(12000, 3), 1), ("markov", synth.markov_text(9000, 4), 1),
+             ("repetitive", synth.repetitive(12000, 5, block=300, p=0.005), 2),
+             ("run_a", synth.with_sentinel(np.full(3000, 97, np.uint8)), 2),
+             ("long_repeat_in_random", synth.with_sentinel(np.concatenate([np.random.default_rng(1).integers(97, 101, 4000, dtype=np.uint8)] * 2 + [np.random.default_rng(2).integers(97, 101, 9000, dtype=np.uint8)])), None)]
+    for name, t, route in cases:
+        ds = oracle.textds(t)
+        with _abi.Context(simlib) as c:
+            c.set_text(t)
+            c.build(_abi.SA | _abi.ISA | _abi.LCP)
+            assert np.array_equal(c.get(_abi.LCP), ds["lcp"]), name
+            assert c.max_lcp() == ds["max_lcp"], name
+            if route is not None:
+                assert c.sa_stats()["lcp_route"] == route, (name, c.sa_stats())
+            z, mn, mx = c.factorize(3)
+            f = c.factors(z)
+            got = np.stack([f["pos"], f["src"], f["len"]], 1) if z else np.zeros((0, 3), np.uint32)
+            assert np.array_equal(got, oracle.factorize(ds, t.size, 3)), name

@@ -172,9 +172,9 @@ class Context:
                 for i in range(L.tdcgpu_phase_count(self._h))]
 
     def sa_stats(self) -> dict:
-        buf = (C.c_uint64 * 6)()
+        buf = (C.c_uint64 * 8)()
         self.lib.check(self.lib.lib.tdcgpu_sa_stats(self._h, buf))
-        keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key"]
+        keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key", "lcp_route", "prefix_work"]
         return dict(zip(keys, [int(x) for x in buf]))
 
     def sync(self) -> None:

@@ -13,13 +13,14 @@
 
 namespace tdc {
 
+// Phi[SA[j]] = SA[j-1] is emitted as (index, value) pairs for the partitioned scatter; BWT is a gather
 __global__ void __launch_bounds__(256)
-phi_bwt_kernel(const u32* __restrict__ sa, const uint8_t* __restrict__ text, u64 n, u32* __restrict__ phi,
-               uint8_t* __restrict__ bwt) {
+phi_bwt_kernel(const u32* __restrict__ sa, const uint8_t* __restrict__ text, u64 n, u32* __restrict__ phi_idx,
+               u32* __restrict__ phi_val, uint8_t* __restrict__ bwt) {
     const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const u32 s = sa[j];
-    if (phi) phi[s] = sa[j ? j - 1 : n - 1];
+    if (phi_idx) { phi_idx[j] = s; phi_val[j] = sa[j ? j - 1 : n - 1]; }
     if (bwt) bwt[j] = s ? text[s - 1] : text[n - 1];
 }
 
@@ -187,11 +188,107 @@ lcp_gather_kernel(const u32* __restrict__ sa, const u32* __restrict__ plcp, u64 
     lcp[j] = j ? plcp[sa[j]] : 0u;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Direct route (LCP only, texts whose suffixes separate early): LCP[j] = lce(SA[j-1], SA[j]) by character comparison
+// in SA order.  Each lane loads the first 32 bytes of its own suffix once and receives its predecessor's from the
+// neighbouring lane, so the common case costs one random text access per suffix instead of the Phi scatter, the PLCP
+// pass and the LCP gather of the reference's data flow.  Identical values by definition (LCPFromPLCP.hpp:43-47).
+// ---------------------------------------------------------------------------------------------------------------
+static const u32 LCPD_THREAD_LIMIT = 256;  // bytes compared by one thread before the pair is queued for a whole warp
+
+__global__ void __launch_bounds__(256)
+lcp_direct_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u64 n, u32* __restrict__ lcp,
+                  u32* __restrict__ queue, u32* __restrict__ queue_len, u32* __restrict__ max_lcp) {
+    __shared__ u32 s_max[256 / 32];
+    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool valid = j < n;
+    const u32 own = valid ? sa[j] : 0u;
+    u64 w[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) w[k] = valid ? load_text8(text, u64(own) + 8u * k) : 0ull;
+    u32 prev = __shfl_up_sync(kFull, own, 1);
+    u64 pw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) pw[k] = __shfl_up_sync(kFull, w[k], 1);
+    if (lane_id() == 0 && valid && j > 0) {
+        prev = sa[j - 1];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pw[k] = load_text8(text, u64(prev) + 8u * k);
+    }
+    u32 l = 0;
+    if (valid && j > 0) {
+        bool found = false;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!found) {
+                const u64 x = w[k] ^ pw[k];
+                if (x) { l = 8u * k + ((__ffsll((long long)x) - 1) >> 3); found = true; }
+            }
+        }
+        if (!found) {
+            bool done;
+            l = lce_thread(text, own, prev, 32, LCPD_THREAD_LIMIT, &done);
+            if (!done) queue[atomicAdd(queue_len, 1u)] = u32(j);
+        }
+        lcp[j] = l;
+    } else if (valid) {
+        lcp[0] = 0;
+    }
+    u32 mx = warp_max(l);
+    if (lane_id() == 0) s_max[warp_id()] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 256 / 32; q++) mx = max(mx, s_max[q]);
+        if (mx) atomicMax(max_lcp, mx);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lcp_direct_long_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u32* __restrict__ lcp,
+                       const u32* __restrict__ queue, const u32* __restrict__ queue_len, u32* __restrict__ max_lcp) {
+    const u32 nq = *queue_len;
+    const u32 warps = (gridDim.x * blockDim.x) >> 5;
+    for (u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+        const u32 j = queue[q];
+        const u32 l = lce_warp(text, sa[j], sa[j - 1], lcp[j]);
+        __syncwarp();
+        if (lane_id() == 0) { lcp[j] = l; atomicMax(max_lcp, l); }
+    }
+}
+
+// needs d_sa; fills d_lcp and max_lcp without materialising Phi/PLCP
+int build_lcp_direct(Ctx& c) {
+    const u64 n = c.n;
+    cudaStream_t st = c.stream;
+    c.arena.reset();
+    u32* queue = c.arena.take<u32>(n);
+    if (!queue) { set_error("lcp: scratch arena too small"); return -2; }
+    u32* d_qlen = c.d_scalars + 0;
+    u32* d_max = c.d_scalars + 1;
+    TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
+    TDC_LAUNCH(lcp_direct_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, queue, d_qlen, d_max);
+    TDC_LAUNCH(lcp_direct_long_kernel, u32(c.sm_count * 4), 256, 0, st, c.d_text, c.d_sa, c.d_lcp, queue, d_qlen, d_max);
+    TDC_KCHECK();
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    c.max_lcp = c.h_scalars[1];
+    return 0;
+}
+
 int build_phi_bwt(Ctx& c, bool want_phi, bool want_bwt) {
     if (!want_phi && !want_bwt) return 0;
-    TDC_LAUNCH(phi_bwt_kernel, u32(div_up(c.n, 256)), 256, 0, c.stream, c.d_sa, c.d_text, c.n, want_phi ? c.d_phi : nullptr,
+    const u64 n = c.n;
+    c.arena.reset();
+    u32* sc_idx[2] = {nullptr, nullptr};
+    u32* sc_val[2] = {nullptr, nullptr};
+    if (want_phi) {
+        for (int q = 0; q < 2; q++) { sc_idx[q] = c.arena.take<u32>(n); sc_val[q] = c.arena.take<u32>(n); }
+        if (!sc_idx[0] || !sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("phi: scratch arena too small"); return -2; }
+    }
+    TDC_LAUNCH(phi_bwt_kernel, u32(div_up(n, 256)), 256, 0, c.stream, c.d_sa, c.d_text, n, sc_idx[0], sc_val[0],
                want_bwt ? c.d_bwt : nullptr);
     TDC_KCHECK();
+    if (want_phi) TDC_TRY(partitioned_scatter(c.sortws, c.stream, sc_idx, sc_val, n, c.d_phi, n));
     return 0;
 }
 

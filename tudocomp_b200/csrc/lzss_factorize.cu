@@ -11,8 +11,8 @@
 //      minimum drops below the threshold, because such a side can never produce a factor) and scatters
 //      (len << 1 | side) to text order;
 //   3. the greedy chain i -> i + max(1, len) from 0: per tile of text positions a shared-memory pointer-jumping
-//      computes where each position leaves the tile; a scalar walk over tile exits finds each tile's entry; a second
-//      shared-memory pointer doubling marks the positions actually visited;
+//      computes where each position leaves the tile; speculative per-region walkers plus a short scalar stitch over
+//      tile exits find each tile's entry; then one thread per tile walks its part of the chain and marks it;
 //   4. visited positions with len > 0 are compacted, in position order, to (pos, src, len) records
 //      (lzss::Factor, compressors/lzss/LZSSFactors.hpp:13-20); src is recovered by repeating the winning side's walk.
 //      PSV wins ties (:101).
@@ -120,7 +120,7 @@ __device__ __forceinline__ bool walk_nsv(const MinTree& T, u32 p, u32 v, u32 thr
 
 // per rank: longest previous factor length and winning side, scattered to text order
 __global__ void __launch_bounds__(256)
-lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lenside) {
+lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_pos, u32* __restrict__ out_lenside) {
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const u32 v = T.a[0][p];
@@ -130,7 +130,9 @@ lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lenside) {
     u32 md;
     const u32 ld = walk_nsv(T, p, v, thr, md, q) ? md : 0u;
     const u32 len = max(lu, ld);
-    lenside[v] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+    // lenside[v] = ..., applied by the partitioned scatter that follows (text order is random with respect to ranks)
+    out_pos[p] = v;
+    out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -227,87 +229,32 @@ __global__ void chain_entries_stitch_kernel(const u32* __restrict__ exitp, u32 n
     for (u32 tt = clear_from; tt < ntiles; tt++) entry[tt] = CH_NONE;
 }
 
-// mark the visited positions of a tile by pointer doubling; output one bit per position that starts a factor
-__global__ void __launch_bounds__(CH_THREADS)
-chain_mark_kernel(const u32* __restrict__ lenside, u32 n, const u32* __restrict__ entry, u32* __restrict__ fmask,
-                  u32* __restrict__ tile_count) {
-    __shared__ u32 J[CH_TILE];
-    __shared__ u32 mark[CH_TILE / 32];
-    __shared__ u32 isfac[CH_TILE / 32];
-    __shared__ u32 flag;
-    __shared__ u32 s_cnt[CH_THREADS / 32];
-    const u32 base = blockIdx.x * CH_TILE;
-    const u32 tile_end = min(base + u32(CH_TILE), n - 1);
-    const u32 e = entry[blockIdx.x];
-    u32* out = fmask + u64(blockIdx.x) * (CH_TILE / 32);
-    if (e == CH_NONE) {  // chain jumps over this tile
-        for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) out[w] = 0;
-        if (threadIdx.x == 0) tile_count[blockIdx.x] = 0;
-        return;
-    }
-    for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) { mark[w] = 0; isfac[w] = 0; }
-    __syncthreads();
-    // thread owns CH_IPT consecutive positions = half of one 32-bit flag word
-    const u32 j0 = threadIdx.x * CH_IPT;
-    u32 fbits = 0;
-#pragma unroll
-    for (int q = 0; q < CH_IPT; q++) {
-        const u32 i = base + j0 + q;
-        u32 ls = 0;
-        if (i < tile_end) { ls = lenside[i]; J[j0 + q] = next_of(i, ls); } else J[j0 + q] = CH_NONE;
-        if (ls) fbits |= 1u << q;
-    }
-    if (fbits) atomicOr(&isfac[j0 >> 5], fbits << (j0 & 31));
-    if (threadIdx.x == 0) mark[(e - base) >> 5] = 1u << ((e - base) & 31);
-    __syncthreads();
-    while (true) {
-        if (threadIdx.x == 0) flag = 0;
-        __syncthreads();
-        // A: marked nodes mark their current jump target (every target is a true chain node)
-        const u32 mw = (mark[j0 >> 5] >> (j0 & 31)) & u32((1ull << CH_IPT) - 1ull);
-        bool prop = false;
-        if (mw) {
-#pragma unroll
-            for (int q = 0; q < CH_IPT; q++) {
-                if ((mw >> q) & 1u) {
-                    const u32 t = J[j0 + q];
-                    if (t < tile_end) {
-                        atomicOr(&mark[(t - base) >> 5], 1u << ((t - base) & 31));
-                        prop = true;
-                    }
-                }
+// Mark the visited positions of every tile: with the tile entries known the tiles are independent, so ONE THREAD walks
+// one tile's chain (a few hundred dependent, mostly L1-resident loads) while hundreds of thousands of tiles are in
+// flight.  Output: one bit per position that starts a factor (fmask is pre-zeroed) and the per-tile factor count.
+__global__ void __launch_bounds__(128)
+chain_mark_kernel(const u32* __restrict__ lenside, u32 n, u32 ntiles, const u32* __restrict__ entry,
+                  u32* __restrict__ fmask, u32* __restrict__ tile_count) {
+    const u32 tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= ntiles) return;
+    u32 x = entry[tile];
+    u32 cnt = 0;
+    if (x != CH_NONE) {
+        const u32 tile_end = u32(min(u64(tile) * CH_TILE + CH_TILE, u64(n - 1)));
+        u32 word = x >> 5, bits = 0;
+        while (x < tile_end) {
+            const u32 ls = lenside[x];
+            if (ls) { bits |= 1u << (x & 31); cnt++; }
+            x = next_of(x, ls);
+            if ((x >> 5) != word) {
+                if (bits) fmask[word] = bits;
+                word = x >> 5;
+                bits = 0;
             }
         }
-        if (prop) flag = 1;
-        __syncthreads();
-        const bool again = flag != 0;
-        // B: J <- J o J with all reads before all writes, so every pointer keeps the same power of `next`
-        u32 nj[CH_IPT];
-#pragma unroll
-        for (int q = 0; q < CH_IPT; q++) {
-            const u32 t = J[j0 + q];
-            nj[q] = t < tile_end ? J[t - base] : t;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int q = 0; q < CH_IPT; q++) J[j0 + q] = nj[q];
-        __syncthreads();
-        if (!again) break;
+        if (bits) fmask[word] = bits;  // unreachable (the word changes when x leaves it); kept for clarity
     }
-    u32 cnt = 0;
-    for (u32 w = threadIdx.x; w < CH_TILE / 32; w += CH_THREADS) {
-        const u32 f = mark[w] & isfac[w];
-        out[w] = f;
-        cnt += __popc(f);
-    }
-    cnt = warp_sum<u32>(cnt);
-    if (lane_id() == 0) s_cnt[warp_id()] = cnt;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 s = 0;
-        for (int w = 0; w < CH_THREADS / 32; w++) s += s_cnt[w];
-        tile_count[blockIdx.x] = s;
-    }
+    tile_count[tile] = cnt;
 }
 
 // single CTA: exclusive scan of per-tile counts; *total = sum
@@ -417,7 +364,14 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
     if (!lenside || !exitp || !entry || !fmask || !tile_cnt) { set_error("lzss_lcp: scratch arena too small"); return -2; }
 
     // ---- 2. LPF per rank ----
-    TDC_LAUNCH(lpf_kernel, u32(div_up(u64(n), 256)), 256, 0, st, T, n, threshold, lenside);
+    {
+        u32* sc_idx[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
+        u32* sc_val[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
+        if (!sc_idx[0] || !sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+        TDC_LAUNCH(lpf_kernel, u32(div_up(u64(n), 256)), 256, 0, st, T, n, threshold, sc_idx[0], sc_val[0]);
+        TDC_KCHECK();
+        TDC_TRY(partitioned_scatter(c.sortws, st, sc_idx, sc_val, n, lenside, n));
+    }
     // ---- 3. chain ----
     TDC_LAUNCH(chain_exit_kernel, ntiles, CH_THREADS, 0, st, lenside, n, exitp);
     TDC_LAUNCH(fill_u32_kernel, u32(div_up(u64(ntiles), 256)), 256, 0, st, entry, u64(ntiles), CH_NONE);
@@ -432,7 +386,8 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         TDC_LAUNCH(chain_entries_spec_kernel, u32(div_up(u64(regions), 128)), 128, 0, st, exitp, n, tiles_per_region, regions, entry, region_exit);
         TDC_LAUNCH(chain_entries_stitch_kernel, 1, 32, 0, st, exitp, n, tiles_per_region, entry, region_exit);
     }
-    TDC_LAUNCH(chain_mark_kernel, ntiles, CH_THREADS, 0, st, lenside, n, entry, fmask, tile_cnt);
+    TDC_CUDA(cudaMemsetAsync(fmask, 0, sizeof(u32) * u64(ntiles) * (CH_TILE / 32), st));
+    TDC_LAUNCH(chain_mark_kernel, u32(div_up(u64(ntiles), 128)), 128, 0, st, lenside, n, ntiles, entry, fmask, tile_cnt);
     u32* d_total = c.d_scalars + 0;
     u32* d_minmax = c.d_scalars + 2;
     TDC_LAUNCH(scan_counts_kernel, 1, 1024, 0, st, tile_cnt, ntiles, d_total);

@@ -324,4 +324,41 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// partitioned scatter: dst[idx[t]] = val[t] for distinct idx
+// ---------------------------------------------------------------------------------------------------------------
+// A 4-byte store to a random address costs DRAM a 32 B sector read plus a 32 B sector write (ncu: 64-80 B/element for
+// the ISA / Phi / LPF scatters).  Instead: one radix pass partitions the (idx, val) pairs by the top bits of idx into
+// <= 256 destination windows (each far smaller than the 126 MB L2), then the pairs are scattered window by window:
+// every store of a window lands in L2, sectors are completed there and written back once.
+static __global__ void __launch_bounds__(256)
+scatter_pairs_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 m, u32* __restrict__ dst) {
+    const u64 stride = u64(gridDim.x) * blockDim.x;
+    for (u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x; t < m; t += stride) dst[idx[t]] = val[t];
+}
+
+#ifdef TDC_CUSIM
+static const u64 PS_DIRECT_BELOW = 1000;  // tiny thresholds so that the CPU tests exercise the partition pass
+static const int PS_WINDOW_BITS = 8;
+#else
+static const u64 PS_DIRECT_BELOW = u64(1) << 22;  // small batches stay L2-resident anyway
+static const int PS_WINDOW_BITS = 22;             // window = 2^22 elements = 16 MiB
+#endif
+
+// idx[0]/val[0] hold the pairs; idx[1]/val[1] are scratch of the same size.  n_dst = size of dst (bounds the idx bits).
+static inline int partitioned_scatter(SortWorkspace& ws, cudaStream_t st, u32* idx[2], u32* val[2], u64 m, u32* dst, u64 n_dst) {
+    if (m == 0) return 0;
+    int res = 0;
+    const int bits = int(bits_for_host(n_dst > 1 ? n_dst - 1 : 1));
+    if (m >= PS_DIRECT_BELOW && bits > PS_WINDOW_BITS) {
+        const int wbits = bits - PS_WINDOW_BITS > 8 ? 8 : bits - PS_WINDOW_BITS;  // at most 256 windows
+        TDC_TRY(radix_sort_pairs<u32>(ws, st, idx, val, m, bits - wbits, bits, false, &res));
+    }
+    const u32 grid = u32(min(u64(ws.sm_count) * 16, div_up(m, 256)));
+    TDC_LAUNCH(scatter_pairs_kernel, grid, 256, 0, st, idx[res], val[res], m, dst);
+    prof_add_bytes("scatter_pairs_kernel", double(m) * 12);
+    TDC_KCHECK();
+    return 0;
+}
+
 }  // namespace tdc

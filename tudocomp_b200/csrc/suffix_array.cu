@@ -189,8 +189,8 @@ template <class K>
 __global__ void __launch_bounds__(RR_THREADS)
 rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ pos_in, u64 m,
                     const u32* __restrict__ pre_lasthead, const ull* __restrict__ pre_cnt, u32* __restrict__ sa,
-                    u32* __restrict__ rank, u32* __restrict__ pos_out, u32* __restrict__ idx_out,
-                    u32* __restrict__ gid_out) {
+                    u32* __restrict__ rank_idx, u32* __restrict__ rank_val, u32* __restrict__ pos_out,
+                    u32* __restrict__ idx_out, u32* __restrict__ gid_out) {
     __shared__ ull scratch_s[33];
     __shared__ u32 scratch_m[33];
     const u64 t0 = u64(blockIdx.x) * RR_TILE + u64(threadIdx.x) * RR_IPT;
@@ -221,7 +221,8 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
         const u32 slot = pos_in ? pos_in[t] : u32(t);
         const u32 headslot = pos_in ? pos_in[hidx] : hidx;
         const u32 sfx = vals[t];
-        rank[sfx] = headslot;
+        rank_idx[t] = sfx;  // rank[sfx] = headslot, applied by the partitioned scatter that follows
+        rank_val[t] = headslot;
         if (ns) {
             if (h) run_s += ull(1) << 32;
             const u32 o = u32(run_s);
@@ -266,6 +267,10 @@ int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count) {
         auto k2 = rs_onesweep_kernel<u64, false>;
         TDC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<u64>())));
         TDC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<u64>())));
+        auto k3 = rs_onesweep_kernel<u32, true>;
+        auto k4 = rs_onesweep_kernel<u32, false>;
+        TDC_CUDA(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<u32>())));
+        TDC_CUDA(cudaFuncSetAttribute(k4, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<u32>())));
     }
     return 0;
 }
@@ -285,15 +290,17 @@ void sort_workspace_free(SortWorkspace& ws) {
 // ---------------------------------------------------------------------------------------------------------------
 template <class K>
 static int rerank(Ctx& c, const K* keys, const u32* vals, const u32* pos_in, u64 m, u32* agg_lasthead, ull* agg_cnt,
-                  u32* pos_out, u32* idx_out, u32* gid_out, u64* m_out, u64* g_out) {
+                  u32* pos_out, u32* idx_out, u32* gid_out, u32* sc_idx[2], u32* sc_val[2], u64* m_out, u64* g_out) {
     const u32 ntiles = u32(div_up(m, RR_TILE));
-    auto k1 = rerank_reduce_kernel<K>;
-    TDC_LAUNCH(k1, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt);
+    auto rerank_reduce = rerank_reduce_kernel<K>;
+    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt);
     TDC_LAUNCH(rerank_scan_kernel, 1, 1024, 0, c.stream, agg_lasthead, agg_cnt, ntiles, c.d_scalars);
     auto k3 = rerank_apply_kernel<K>;
-    TDC_LAUNCH(k3, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, c.d_sa, c.d_isa, pos_out,
-               idx_out, gid_out);
+    auto rerank_apply = k3;
+    TDC_LAUNCH(rerank_apply, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, c.d_sa, sc_idx[0],
+               sc_val[0], pos_out, idx_out, gid_out);
     TDC_KCHECK();
+    TDC_TRY(partitioned_scatter(c.sortws, c.stream, sc_idx, sc_val, m, c.d_isa, c.n));
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     *m_out = c.h_scalars[0];
@@ -306,6 +313,7 @@ int build_suffix_array(Ctx& c) {
     cudaStream_t st = c.stream;
     c.sa_rounds = 0;
     c.sa_active_sum = 0;
+    c.sa_prefix_work = 0;
     c.sortws.stat_passes = 0;
     c.sortws.stat_elems = 0;
     if (n == 1) {  // text == "\0"
@@ -367,11 +375,13 @@ int build_suffix_array(Ctx& c) {
     u32* vals[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
     u32* pos[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
     u32* gid = c.arena.take<u32>(n);
+    u32* sc_a = c.arena.take<u32>(n);  // second buffer pair of the partitioned ISA scatter
+    u32* sc_b = c.arena.take<u32>(n);
     const u64 rr_tiles = div_up(n, RR_TILE);
     u32* agg_lasthead = c.arena.take<u32>(rr_tiles);
     ull* agg_cnt = c.arena.take<ull>(rr_tiles);
     uint8_t* d_code_map = c.arena.take<uint8_t>(256);
-    if (!keys[0] || !keys[1] || !vals[0] || !vals[1] || !pos[0] || !pos[1] || !gid || !agg_lasthead || !agg_cnt || !d_code_map) {
+    if (!keys[0] || !keys[1] || !vals[0] || !vals[1] || !pos[0] || !pos[1] || !gid || !sc_a || !sc_b || !agg_lasthead || !agg_cnt || !d_code_map) {
         set_error("suffix array: scratch arena too small");
         return -2;
     }
@@ -385,7 +395,12 @@ int build_suffix_array(Ctx& c) {
     u64 m = 0, g = 0;
     int pcur = 0;
     // the sorted (key, suffix) pairs are in slot `res`; compacted survivors go to the other slot's value buffer
-    TDC_TRY(rerank<u64>(c, keys[res], vals[res], nullptr, n, agg_lasthead, agg_cnt, pos[pcur], vals[res ^ 1], gid, &m, &g));
+    {
+        // the key buffer that does not hold the sorted keys is free: it carries the first (idx, val) pair buffer
+        u32* sc_idx[2] = {reinterpret_cast<u32*>(keys[res ^ 1]), sc_a};
+        u32* sc_val[2] = {reinterpret_cast<u32*>(keys[res ^ 1]) + n, sc_b};
+        TDC_TRY(rerank<u64>(c, keys[res], vals[res], nullptr, n, agg_lasthead, agg_cnt, pos[pcur], vals[res ^ 1], gid, sc_idx, sc_val, &m, &g));
+    }
     c.sa_rounds = 1;
     c.sa_active_sum = n;
 
@@ -402,9 +417,12 @@ int build_suffix_array(Ctx& c) {
         TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, k2, v2, m, 0, int(rbits) + gbits, false, &r2));
         c.sa_rounds++;
         c.sa_active_sum += m;
+        c.sa_prefix_work += double(m) * double(h);
         u64 m_new = 0, g_new = 0;
         // survivors are written to the value buffer that does not hold the sorted input
-        TDC_TRY(rerank<u64>(c, k2[r2], v2[r2], pos[pcur], m, agg_lasthead, agg_cnt, pos[pcur ^ 1], v2[r2 ^ 1], gid, &m_new, &g_new));
+        u32* sc_idx[2] = {reinterpret_cast<u32*>(k2[r2 ^ 1]), sc_a};
+        u32* sc_val[2] = {reinterpret_cast<u32*>(k2[r2 ^ 1]) + n, sc_b};
+        TDC_TRY(rerank<u64>(c, k2[r2], v2[r2], pos[pcur], m, agg_lasthead, agg_cnt, pos[pcur ^ 1], v2[r2 ^ 1], gid, sc_idx, sc_val, &m_new, &g_new));
         // re-point: next round's suffix list lives in v2[r2 ^ 1]
         if (v2[r2 ^ 1] == vals[res ^ 1]) {
             // already where the loop expects it

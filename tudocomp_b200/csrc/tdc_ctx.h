@@ -74,6 +74,8 @@ struct Ctx {
     u32 sa_rounds = 0;
     u64 sa_active_sum = 0;
     u32 alphabet = 0, symbols_per_key = 0;
+    double sa_prefix_work = 0;  // sum over doubling rounds of (active suffixes x already-known common prefix): LCP-sum estimate
+    u32 lcp_route = 0;          // 1 = direct comparison in SA order, 2 = Phi/PLCP route
 };
 
 // suffix_array.cu
@@ -81,6 +83,7 @@ int build_suffix_array(Ctx& c);  // fills d_sa and d_isa
 // lcp.cu
 int build_phi_bwt(Ctx& c, bool want_phi, bool want_bwt);
 int build_plcp_lcp(Ctx& c, bool want_lcp);
+int build_lcp_direct(Ctx& c);  // LCP without Phi/PLCP (texts with short common prefixes)
 // lzss_factorize.cu
 int factorize_lzss_lcp(Ctx& c, u32 threshold);
 

@@ -119,8 +119,9 @@ static int ensure_capacity(Ctx& c, u64 n) {
     TDC_CUDA(cudaMalloc(&c.d_text, n + TEXT_PAD + 16));
     TDC_CUDA(cudaMalloc(&c.d_sa, sizeof(u32) * n));
     TDC_CUDA(cudaMalloc(&c.d_isa, sizeof(u32) * n));
-    // scratch: SA construction is the high-water mark: 2 x u64 keys, 2 x u32 values, 2 x u32 slots, u32 group ids
-    const size_t arena_bytes = size_t(36) * n + n / 8 + (size_t(4) << 20);
+    // scratch: SA construction is the high-water mark: 2 x u64 keys, 2 x u32 values, 2 x u32 slots, u32 group ids,
+    // 2 x u32 scatter buffers
+    const size_t arena_bytes = size_t(44) * n + n / 8 + (size_t(4) << 20);
     TDC_CUDA(cudaMalloc(&c.arena.base, arena_bytes));
     c.arena.cap = arena_bytes;
     c.arena.off = 0;
@@ -139,6 +140,25 @@ static int lazy_alloc(T** p, u64 count) {
 static int do_build(Ctx& c, u32 flags) {
     if (c.n == 0) { set_error("no text loaded"); return TDCGPU_ERR_STATE; }
     u32 need = flags;
+    // LCP alone on a text whose suffixes separate early (estimated mean LCP small): compare characters directly in SA
+    // order.  Otherwise (or when Phi/PLCP are wanted anyway) follow the reference's Phi -> PLCP -> LCP data flow.
+    bool lcp_direct = false;
+    if ((need & DS_LCP) && !(c.have & DS_LCP) && !((need | c.have) & (DS_PHI | DS_PLCP))) {
+        if (!(c.have & DS_SA)) {
+            PhaseTimer t(c, "Construct SA");
+            TDC_TRY(build_suffix_array(c));
+            c.have |= DS_SA | DS_ISA;
+        }
+        lcp_direct = c.sa_prefix_work / double(c.n) <= 48.0;
+    }
+    if (lcp_direct) {
+        PhaseTimer t(c, "Construct LCP Array");
+        TDC_TRY(lazy_alloc(&c.d_lcp, c.cap_n));
+        TDC_TRY(build_lcp_direct(c));
+        c.have |= DS_LCP;
+        c.lcp_route = 1;
+        need &= ~DS_LCP;
+    }
     if (need & DS_LCP) need |= DS_PLCP | DS_SA;
     if (need & DS_PLCP) need |= DS_PHI | DS_SA;
     if (need & (DS_PHI | DS_ISA | DS_BWT)) need |= DS_SA;
@@ -163,6 +183,7 @@ static int do_build(Ctx& c, u32 flags) {
         if (need & DS_LCP) TDC_TRY(lazy_alloc(&c.d_lcp, c.cap_n));
         TDC_TRY(build_plcp_lcp(c, (need & DS_LCP) != 0));
         c.have |= need & (DS_PLCP | DS_LCP);
+        if (need & DS_LCP) c.lcp_route = 2;
     }
     return 0;
 }
@@ -288,7 +309,7 @@ const void* tdcgpu_textds_device_ptr(tdcgpu_ctx* ctx, uint32_t which) {
 
 int tdcgpu_textds_max_lcp(tdcgpu_ctx* ctx, uint32_t* max_lcp) {
     API_GUARD(ctx);
-    if (!(c.have & DS_PLCP)) { set_error("PLCP has not been built"); return TDCGPU_ERR_STATE; }
+    if (!(c.have & (DS_PLCP | DS_LCP))) { set_error("neither PLCP nor LCP has been built"); return TDCGPU_ERR_STATE; }
     if (max_lcp) *max_lcp = c.max_lcp;
     return 0;
 }
@@ -363,7 +384,7 @@ float tdcgpu_phase_ms(tdcgpu_ctx* ctx, int i) {
     return ctx->c.phases[i].ms;
 }
 
-int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]) {
+int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[8]) {
     API_GUARD(ctx);
     out[0] = c.sa_rounds;
     out[1] = c.sa_active_sum;
@@ -371,6 +392,8 @@ int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[6]) {
     out[3] = c.sortws.stat_elems;
     out[4] = c.alphabet;
     out[5] = c.symbols_per_key;
+    out[6] = c.lcp_route;
+    out[7] = uint64_t(c.sa_prefix_work);
     return 0;
 }
 
