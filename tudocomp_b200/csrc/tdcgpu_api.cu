@@ -139,7 +139,8 @@ static int lazy_alloc(T** p, u64 count) {
 
 static int do_build(Ctx& c, u32 flags) {
     if (c.n == 0) { set_error("no text loaded"); return TDCGPU_ERR_STATE; }
-    u32 need = flags;
+    u32 need = flags & ~c.have;  // dependencies below are only pulled in for structures that are actually missing
+    if (!need) return 0;
     // LCP alone on a text whose suffixes separate early (estimated mean LCP small): compare characters directly in SA
     // order.  Otherwise (or when Phi/PLCP are wanted anyway) follow the reference's Phi -> PLCP -> LCP data flow.
     bool lcp_direct = false;
