@@ -1,0 +1,115 @@
+"""The reference-side boundary: the stock `tdc` driver built with the GPU text index plugged into its registry
+(tudocomp_b200/plugin).  CPU tests check that the binaries exist, list the GPU provider and fail loudly without a
+device; GPU tests check byte-identical archives against the unmodified reference driver and round trips."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tudocomp_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF, GPU, GPU_ONLY = (os.path.join(ROOT, "build", b) for b in ("tdc_ref", "tdc_gpu", "tdc_gpu_only"))
+
+
+def _need_bins():
+    if not all(os.path.exists(p) for p in (REF, GPU, GPU_ONLY)):
+        pytest.skip("tdc drivers not built (bash tudocomp_b200/plugin/build_tdc.sh; needs /root/reference)")
+
+
+def _run(binary, algo, src, dst, extra=()):
+    return subprocess.run([binary, "-a", algo, src, "-o", dst, "--force", *extra], capture_output=True, text=True)
+
+
+def test_registry_lists_gpu_textds():
+    _need_bins()
+    out = subprocess.run([GPU, "--list"], capture_output=True, text=True).stdout
+    assert "gpu(compress" in out and "Text index built on the GPU" in out
+    assert "lzss_lcp(coder, textds" in out and "bwt(textds" in out
+    only = subprocess.run([GPU_ONLY, "--list"], capture_output=True, text=True).stdout
+    assert "textds = gpu(" in only  # the GPU index is the default of lzss_lcp / bwt in the GPU-only registry
+
+
+def test_gpu_driver_fails_loudly_without_device(tmp_path):
+    _need_bins()
+    import tudocomp_b200 as tdc
+    if tdc.load().device_count() > 0:
+        pytest.skip("a GPU is present")
+    src = tmp_path / "in.txt"
+    src.write_bytes(b"hello hello hello world world")
+    r = _run(GPU, "lzss_lcp(ascii, gpu)", str(src), str(tmp_path / "o.tdc"))
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+    # the CPU providers of the same binary still work: the plugin is an addition, not a replacement
+    r = _run(GPU, "lzss_lcp(coder=ascii)", str(src), str(tmp_path / "o.tdc"))
+    assert r.returncode == 0
+    assert (tmp_path / "o.tdc").read_bytes().startswith(b"lzss_lcp(coder=ascii)%31:6:12:6:16:hello ")
+
+
+def _inputs(tmp_path):
+    cases = {
+        "markov": synth.markov_text(300000, 5)[:-1].tobytes(),
+        "dna": synth.dna(300000, 6)[:-1].tobytes(),
+        "repetitive": synth.repetitive(200000, 7, block=3000, p=0.01)[:-1].tobytes(),
+        "binary_with_escapes": bytes(np.random.default_rng(3).integers(0, 256, 50000, dtype=np.uint8)),
+        "empty": b"",
+        "one": b"a",
+    }
+    out = {}
+    for k, v in cases.items():
+        p = tmp_path / f"{k}.bin"
+        p.write_bytes(v)
+        out[k] = str(p)
+    return out
+
+
+@pytest.mark.gpu
+def test_archives_byte_identical_to_reference_driver(tmp_path):
+    _need_bins()
+    for name, src in _inputs(tmp_path).items():
+        for coder in ("bit", "huff", "ascii"):
+            for thr in (3, 5):
+                a, b, c = (str(tmp_path / f"{name}.{coder}.{thr}.{x}") for x in ("ref", "gpu", "only"))
+                cpu_algo = f"lzss_lcp(coder={coder},threshold={thr})"
+                assert _run(REF, cpu_algo, src, a, ["--raw"]).returncode == 0
+                r = _run(GPU, f"lzss_lcp(coder={coder},textds=gpu,threshold={thr})", src, b, ["--raw"])
+                assert r.returncode == 0, r.stderr
+                assert open(a, "rb").read() == open(b, "rb").read(), (name, coder, thr)
+                # GPU-only registry: identical -a string, so the archive INCLUDING the driver header is identical
+                assert _run(REF, cpu_algo, src, a).returncode == 0
+                r = _run(GPU_ONLY, cpu_algo, src, c)
+                assert r.returncode == 0, r.stderr
+                assert open(a, "rb").read() == open(c, "rb").read(), (name, coder, thr, "with header")
+        # decompress the GPU-built archive with the unmodified reference driver
+        back = str(tmp_path / f"{name}.back")
+        r = subprocess.run([REF, "-d", c, "-o", back, "--force"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(back, "rb").read() == open(src, "rb").read(), name
+
+
+@pytest.mark.gpu
+def test_bwt_chain_byte_identical(tmp_path):
+    _need_bins()
+    for name, src in _inputs(tmp_path).items():
+        a, b = str(tmp_path / f"{name}.bwt.ref"), str(tmp_path / f"{name}.bwt.gpu")
+        algo = "bwt:mtf:rle:encode(huff)"
+        assert _run(REF, algo, src, a).returncode == 0
+        r = _run(GPU_ONLY, algo, src, b)
+        assert r.returncode == 0, r.stderr
+        assert open(a, "rb").read() == open(b, "rb").read(), name
+        back = str(tmp_path / f"{name}.bwt.back")
+        assert subprocess.run([REF, "-d", b, "-o", back, "--force"], capture_output=True).returncode == 0
+        assert open(back, "rb").read() == open(src, "rb").read(), name
+
+
+@pytest.mark.gpu
+def test_gpu_textds_arrays_through_stats(tmp_path):
+    """The GPU provider logs the same phase titles / bit widths the reference providers log."""
+    _need_bins()
+    src = tmp_path / "m.txt"
+    src.write_bytes(synth.markov_text(100000, 8)[:-1].tobytes())
+    r = subprocess.run([GPU_ONLY, "-a", "lzss_lcp(coder=bit)", str(src), "-o", str(tmp_path / "o"), "--force", "--stats"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for title in ("Construct Text DS", "Factorize", "Encode", "factors", "threshold"):
+        assert title in r.stdout, title

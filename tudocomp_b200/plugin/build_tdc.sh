@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# Builds the reference's `tdc` driver offline in three flavours (see registry_gpu.py):
+#   build/tdc_ref        unmodified reference subset (CPU)            — byte-identity checker
+#   build/tdc_gpu        reference registry + GpuTextDS ("mixed")     — -a "lzss_lcp(huff, gpu)"
+#   build/tdc_gpu_only   GPU text index as the default ("only")       — same -a strings as the reference
+# The reference sources are compiled where they lie under $REF (nothing is copied); the two missing third-party headers
+# come from oracle/ref_build/shim.  Needs $REF, so it only runs in the build container; the binaries travel in build/.
+set -euo pipefail
+ROOT="$(cd "$(dirname "$0")/../.." && pwd)"
+REF="${REF:-/root/reference}"
+OUT="$ROOT/build/tdc"
+JOBS="${JOBS:-8}"
+[ -d "$REF/include/tudocomp" ] || { echo "build_tdc.sh: $REF absent, keeping prebuilt binaries"; exit 0; }
+[ -f "$ROOT/tudocomp_b200/libtdcgpu.so" ] || make -s -C "$ROOT/tudocomp_b200/csrc"
+CXXFLAGS="-std=gnu++14 -O2 -DNDEBUG -w -I$ROOT/oracle/ref_build/shim -I$ROOT/tudocomp_b200/plugin/include -I$ROOT/include -I$REF/include"
+for mode in none mixed only; do
+  case $mode in none) bin=tdc_ref;; mixed) bin=tdc_gpu;; only) bin=tdc_gpu_only;; esac
+  gen="$OUT/gen_$mode"; rm -rf "$gen"; mkdir -p "$gen/tudocomp"
+  # generated headers the reference's CMake would configure
+  printf '#pragma once\n' > "$gen/tudocomp/config.h"
+  printf '#pragma once\n#include <string>\nnamespace tdc { const std::string VERSION = "tdc-b200 offline build (%s)"; }\n' "$mode" > "$gen/tudocomp/version.hpp"
+  TDC_GPU_MODE=$mode python3 "$REF/etc/genregistry.py" "$ROOT/tudocomp_b200/plugin/registry_gpu.py" "$gen/tudocomp/config.h" "$gen" --generate_files >/dev/null
+  extra=""; [ "$mode" = only ] && extra="-DTDC_GPU_DEFAULT_TEXTDS"
+  srcs=$(ls "$gen"/*.cpp)
+  all="$srcs $REF/src/tudocomp_driver/tudocomp_driver.cpp $REF/src/tudocomp_stat/StatPhase.cpp $REF/src/tudocomp_stat/malloc.cpp"
+  objs=""
+  for s in $all; do objs="$objs $gen/$(basename "${s%.cpp}").o"; done
+  for s in $all; do
+    echo "g++ $CXXFLAGS $extra -I$gen -c $s -o $gen/$(basename "${s%.cpp}").o"
+  done | xargs -P "$JOBS" -I{} sh -c '{}'
+  if [ "$mode" != none ]; then
+    g++ -o "$ROOT/build/$bin" $objs -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+  else
+    g++ -o "$ROOT/build/$bin" $objs -ldl
+  fi
+  echo "built build/$bin"
+done

@@ -1,0 +1,281 @@
+// GPU-backed drop-ins for tudocomp's text index and lzss_lcp / bwt compressors.
+//
+// This header is compiled AGAINST the reference's headers (it is the host side "in the reference's own language") and
+// talks to the device only through the C ABI in include/tdcgpu.h.  It adds, without touching any reference file:
+//
+//   GpuTextDS                                  a whole replacement `text_t` (legal template argument of
+//                                              LZSSLCPCompressor<coder_t, text_t> / BWTCompressor<text_t>,
+//                                              compressors/LZSSLCPCompressor.hpp:23, BWTCompressor.hpp:13) with the
+//                                              TextDS surface the consumers use: require_sa/isa/lcp/phi/plcp, require(),
+//                                              size(), operator[], text(), SA/ISA/LCP/PHI/PLCP flags,
+//                                              common_restrictions(), meta()            (ds/TextDS.hpp:23-346)
+//   LZSSLCPCompressor<coder_t, GpuTextDS>      partial specialisation whose "Factorize" phase is the device factoriser;
+//                                              same Meta("compressor","lzss_lcp"), same options (coder, textds, threshold),
+//                                              same phases, the reference's own encode_text / decode_text
+//   BWTCompressor<GpuTextDS>                   partial specialisation writing the device-side BWT gather
+//
+// Arrays handed back to callers are tdc::DynamicIntVector at width 32 — byte-identical to uint32_t[n]
+// (ds/BitPackingVector.hpp:259-271) — and honour the `compress` option like the reference providers do
+// (ds/SADivSufSort.hpp:53-63 etc.): "delayed"/"compressed" narrow to bits_for(n) / bits_for(max_lcp) after filling.
+//
+// Errors: C-ABI failures become std::runtime_error (caught by the driver's main like any Env::error,
+// src/tudocomp_driver/tudocomp_driver.cpp:392-395); a text without sentinel throws the same std::logic_error as
+// TextDS (ds/TextDS.hpp:132-138).  Single-threaded like the reference; StatPhase is only touched from the caller.
+#pragma once
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+
+#include <tudocomp/Algorithm.hpp>
+#include <tudocomp/compressors/BWTCompressor.hpp>
+#include <tudocomp/compressors/LZSSLCPCompressor.hpp>
+#include <tudocomp/ds/ArrayDS.hpp>
+#include <tudocomp/ds/CompressMode.hpp>
+#include <tudocomp/ds/IntVector.hpp>
+#include <tudocomp/ds/TextDS.hpp>
+#include <tudocomp/ds/TextDSFlags.hpp>
+#include <tudocomp_stat/StatPhase.hpp>
+
+#include <tdcgpu.h>
+
+namespace tdc {
+
+namespace gpu_detail {
+inline void check(int rc, const char* what) {
+    if (rc < 0) throw std::runtime_error(std::string("tdcgpu: ") + what + ": " + tdcgpu_last_error());
+}
+inline int device_from_env() {
+    const char* e = std::getenv("TDCGPU_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+// log the device-side phase times under the current StatPhase (tudocomp_stat/StatPhase.hpp:217-220)
+inline void log_phases(tdcgpu_ctx* ctx) {
+    for (int i = 0; i < tdcgpu_phase_count(ctx); i++) {
+        StatPhase::log((std::string("gpu_ms:") + tdcgpu_phase_name(ctx, i)).c_str(), tdcgpu_phase_ms(ctx, i));
+    }
+}
+}  // namespace gpu_detail
+
+/// One array of the GPU text index, fetched on demand into a DynamicIntVector (what ArrayDS providers expose).
+class GpuArray : public DynamicIntVector {
+    len_t m_max_lcp = 0;
+
+public:
+    using data_type = DynamicIntVector;
+    inline GpuArray() {}
+    inline GpuArray(DynamicIntVector&& iv, len_t max_lcp) : DynamicIntVector(std::move(iv)), m_max_lcp(max_lcp) {}
+    inline len_t max_lcp() const { return m_max_lcp; }
+    inline DynamicIntVector relinquish() { return std::move(static_cast<DynamicIntVector&>(*this)); }
+    inline DynamicIntVector copy() const { return DynamicIntVector(*this); }
+};
+
+class GpuTextDS : public Algorithm {
+public:
+    using dsflags_t = ds::dsflags_t;
+    static const dsflags_t SA = ds::SA;
+    static const dsflags_t ISA = ds::ISA;
+    static const dsflags_t LCP = ds::LCP;
+    static const dsflags_t PHI = ds::PHI;
+    static const dsflags_t PLCP = ds::PLCP;
+    using value_type = uliteral_t;
+    using sa_type = GpuArray;
+    using phi_type = GpuArray;
+    using plcp_type = GpuArray;
+    using lcp_type = GpuArray;
+    using isa_type = GpuArray;
+
+    inline static ds::InputRestrictions common_restrictions(dsflags_t) {
+        // same as SADivSufSort::restrictions(): escape 0, null-terminate (ds/SADivSufSort.hpp:21-26)
+        return ds::InputRestrictions{{0}, true};
+    }
+
+    inline static Meta meta() {
+        Meta m("textds", "gpu", "Text index built on the GPU (tdcgpu, sm_100a)");
+        m.option("compress").dynamic("delayed");
+        return m;
+    }
+
+private:
+    struct CtxDeleter {
+        void operator()(tdcgpu_ctx* c) const { tdcgpu_destroy(c); }
+    };
+    View m_text;
+    std::unique_ptr<tdcgpu_ctx, CtxDeleter> m_ctx;
+    std::unique_ptr<GpuArray> m_sa, m_isa, m_lcp, m_phi, m_plcp;
+    CompressMode m_cm;
+
+    inline const GpuArray& fetch(std::unique_ptr<GpuArray>& slot, uint32_t which, const char* title, bool lcp_width) {
+        if (!slot) {
+            StatPhase::wrap(title, [&] {
+                const size_t n = m_text.size();
+                gpu_detail::check(tdcgpu_textds_build(m_ctx.get(), which), title);
+                gpu_detail::log_phases(m_ctx.get());
+                DynamicIntVector iv(n, 0, INDEX_FAST_BITS);
+                static_assert(INDEX_FAST_BITS == 32, "the C ABI hands back 32-bit indices (default build, def.hpp:103,128)");
+                gpu_detail::check(tdcgpu_textds_get(m_ctx.get(), which, iv.data(), 0), title);
+                uint32_t mx = 0;
+                if (lcp_width) gpu_detail::check(tdcgpu_textds_max_lcp(m_ctx.get(), &mx), title);
+                if (m_cm != CompressMode::plain) {  // "delayed" and "compressed" end in the same narrowed state
+                    iv.width(lcp_width ? bits_for(mx) : bits_for(n));
+                    iv.shrink_to_fit();
+                }
+                StatPhase::log("bit_width", size_t(iv.width()));
+                StatPhase::log("size", iv.bit_size() / 8);
+                slot = std::make_unique<GpuArray>(std::move(iv), len_t(mx));
+            });
+        }
+        return *slot;
+    }
+
+public:
+    inline GpuTextDS(Env&& env, const View& text) : Algorithm(std::move(env)), m_text(text) {
+        if (!m_text.ends_with(uint8_t(0))) {
+            throw std::logic_error(
+                "Input has no sentinel! Please make sure you declare "
+                "the compressor calling this with "
+                "`m.needs_sentinel_terminator()` in its `meta()` function.");
+        }
+        auto& cm_str = this->env().option("compress").as_string();
+        m_cm = cm_str == "delayed" ? CompressMode::delayed : (cm_str == "compressed" ? CompressMode::compressed : CompressMode::plain);
+        tdcgpu_ctx* raw = nullptr;
+        gpu_detail::check(tdcgpu_create(gpu_detail::device_from_env(), &raw), "create");
+        m_ctx.reset(raw);
+        gpu_detail::check(tdcgpu_set_text(m_ctx.get(), reinterpret_cast<const uint8_t*>(m_text.data()), m_text.size(), 0), "set_text");
+    }
+
+    inline GpuTextDS(Env&& env, const View& text, dsflags_t flags, CompressMode = CompressMode::select)
+        : GpuTextDS(std::move(env), text) {
+        require(flags);
+    }
+
+    /// Builds on the device; nothing is copied to the host until a require_*() asks for it.
+    inline void require(dsflags_t flags, CompressMode = CompressMode::select) {
+        gpu_detail::check(tdcgpu_textds_build(m_ctx.get(), flags), "require");
+        gpu_detail::log_phases(m_ctx.get());
+    }
+
+    inline const GpuArray& require_sa(CompressMode = CompressMode::select) { return fetch(m_sa, TDCGPU_SA, "Construct SA", false); }
+    inline const GpuArray& require_isa(CompressMode = CompressMode::select) { return fetch(m_isa, TDCGPU_ISA, "Construct ISA", false); }
+    inline const GpuArray& require_phi(CompressMode = CompressMode::select) { return fetch(m_phi, TDCGPU_PHI, "Construct Phi Array", false); }
+    inline const GpuArray& require_plcp(CompressMode = CompressMode::select) { return fetch(m_plcp, TDCGPU_PLCP, "Construct PLCP Array", true); }
+    inline const GpuArray& require_lcp(CompressMode = CompressMode::select) { return fetch(m_lcp, TDCGPU_LCP, "Construct LCP Array", true); }
+
+    inline GpuArray release_sa() { require_sa(); return std::move(*m_sa); }
+    inline GpuArray release_isa() { require_isa(); return std::move(*m_isa); }
+    inline GpuArray release_phi() { require_phi(); return std::move(*m_phi); }
+    inline GpuArray release_plcp() { require_plcp(); return std::move(*m_plcp); }
+    inline GpuArray release_lcp() { require_lcp(); return std::move(*m_lcp); }
+
+    inline value_type operator[](size_t i) const { return m_text[i]; }
+    inline const value_type* text() const { return m_text.data(); }
+    inline size_t size() const { return m_text.size(); }
+
+    /// Device handle for the GPU-side consumers below.
+    inline tdcgpu_ctx* device() const { return m_ctx.get(); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// lzss_lcp with the device factoriser.  Mirrors LZSSLCPCompressor::compress (compressors/LZSSLCPCompressor.hpp:42-124)
+// phase by phase; only the body of "Factorize" differs.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef TDC_GPU_DEFAULT_TEXTDS
+#define TDCGPU_DEFAULT_TEXT_T GpuTextDS  /* GPU-only registry: `lzss_lcp(...)` / `bwt` select the GPU text index */
+#else
+#define TDCGPU_DEFAULT_TEXT_T TextDS<>   /* mixed registry: defaults must equal the reference's (Meta.hpp:303-316) */
+#endif
+
+template <typename coder_t>
+class LZSSLCPCompressor<coder_t, GpuTextDS> : public Compressor {
+    using text_t = GpuTextDS;
+
+public:
+    inline static Meta meta() {
+        Meta m("compressor", "lzss_lcp", "LZSS Factorization using LCP");
+        m.option("coder").templated<coder_t>("coder");
+        m.option("textds").templated<text_t, TDCGPU_DEFAULT_TEXT_T>("textds");
+        m.option("threshold").dynamic(3);
+        m.uses_textds<text_t>(text_t::SA | text_t::ISA | text_t::LCP);
+        return m;
+    }
+
+    inline LZSSLCPCompressor() = delete;
+    inline LZSSLCPCompressor(Env&& env) : Compressor(std::move(env)) {}
+
+    inline virtual void compress(Input& input, Output& output) override {
+        auto view = input.as_view();
+        DCHECK(view.ends_with(uint8_t(0)));
+
+        text_t text = StatPhase::wrap("Construct Text DS", [&] {
+            return text_t(env().env_for_option("textds"), view, text_t::SA | text_t::ISA | text_t::LCP);
+        });
+
+        lzss::FactorBuffer factors;
+        StatPhase::wrap("Factorize", [&] {
+            const len_t threshold = env().option("threshold").as_integer();
+            if (threshold < 1) throw std::runtime_error("lzss_lcp: threshold must be >= 1");
+            uint64_t z = 0;
+            uint32_t mn = 0, mx = 0;
+            gpu_detail::check(tdcgpu_lzss_lcp_factorize(text.device(), threshold, &z, &mn, &mx), "factorize");
+            gpu_detail::log_phases(text.device());
+            std::unique_ptr<tdcgpu_factor[]> buf(new tdcgpu_factor[z ? z : 1]);
+            gpu_detail::check(tdcgpu_lzss_lcp_get_factors(text.device(), buf.get(), z, 0), "get_factors");
+            for (uint64_t k = 0; k < z; k++) factors.emplace_back(buf[k].pos, buf[k].src, buf[k].len);
+            StatPhase::log("threshold", threshold);
+            StatPhase::log("factors", factors.size());
+        });
+
+        StatPhase::wrap("Encode", [&] {
+            typename coder_t::Encoder coder(env().env_for_option("coder"), output, lzss::TextLiterals<text_t>(text, factors));
+            lzss::encode_text(coder, text, factors);
+        });
+    }
+
+    inline virtual void decompress(Input& input, Output& output) override {
+        typename coder_t::Decoder decoder(env().env_for_option("coder"), input);
+        auto outs = output.as_stream();
+        lzss::decode_text<typename coder_t::Decoder, lzss::DecodeBackBuffer>(decoder, outs);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// bwt with the device gather (compressors/BWTCompressor.hpp:29-47).  decompress is the reference's.
+// ---------------------------------------------------------------------------------------------------------------------
+template <>
+class BWTCompressor<GpuTextDS> : public Compressor {
+    using text_t = GpuTextDS;
+
+public:
+    inline static Meta meta() {
+        Meta m("compressor", "bwt", "BWT Compressor");
+        m.option("textds").templated<text_t, TDCGPU_DEFAULT_TEXT_T>("textds");
+        m.uses_textds<text_t>(ds::SA);
+        return m;
+    }
+
+    using Compressor::Compressor;
+
+    inline virtual void compress(Input& input, Output& output) override {
+        auto ostream = output.as_stream();
+        auto in = input.as_view();
+        DCHECK(in.ends_with(uint8_t(0)));
+        text_t t(env().env_for_option("textds"), in);
+        std::string bwt(t.size(), 0);
+        StatPhase::wrap("Construct Text DS", [&] {
+            gpu_detail::check(tdcgpu_textds_build(t.device(), TDCGPU_SA | TDCGPU_BWT), "bwt");
+            gpu_detail::log_phases(t.device());
+            gpu_detail::check(tdcgpu_textds_get(t.device(), TDCGPU_BWT, &bwt[0], 0), "bwt");
+        });
+        ostream.write(bwt.data(), bwt.size());
+    }
+
+    inline virtual void decompress(Input& input, Output& output) override {
+        auto in = input.as_view();
+        auto ostream = output.as_stream();
+        auto decoded_string = StatPhase::wrap("Decode BWT", [&] { return bwt::decode_bwt(in); });
+        if (tdc_unlikely(decoded_string.empty())) return;
+        StatPhase::wrap("Output Text", [&] { ostream << decoded_string << '\0'; });
+    }
+};
+
+}  // namespace tdc
