@@ -255,15 +255,14 @@ def main():
     dev_ms_e2e = max(ctx.event_elapsed_ms(2, 3), 1e3 * wall_e2e)  # host-inclusive, take the larger
     clocks = sampler.stop()
 
-    ms_step = dev_ms / args.steps
-    ms_step_e2e = dev_ms_e2e / args.steps
-    if world > 1:
-        tt = torch.tensor([ms_step, ms_step_e2e], device=f"cuda:{dev}", dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms_step, ms_step_e2e = float(tt[0]), float(tt[1])
+    from tudocomp_b200 import blockmode
+
+    # whole-job step time = max over ranks (block mode: no other communication)
+    ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist if world > 1 else None)
+    ms_step_e2e = blockmode.reduce_step_time(dev_ms_e2e / args.steps, dist if world > 1 else None)
     total_bytes = n_body * world
-    value = total_bytes / 1e6 / (ms_step / 1e3)
-    e2e_value = total_bytes / 1e6 / (ms_step_e2e / 1e3)
+    value = blockmode.job_throughput_mb_s(total_bytes, ms_step)
+    e2e_value = blockmode.job_throughput_mb_s(total_bytes, ms_step_e2e)
 
     if rank == 0:
         peaks = {}
