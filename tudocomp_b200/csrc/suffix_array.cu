@@ -15,6 +15,9 @@
 //   3. doubling round with offset h: key = (group id << rbits) | rank[suffix + h]; sort the active list; rerank; h *= 2.
 //      Active suffixes always satisfy suffix + h <= n-1 (a suffix whose h-prefix reaches the sentinel is unique).
 //   When the active list is empty, sa[] is the suffix array and rank[] is the inverse suffix array.
+#include <cmath>
+#include <cstdlib>
+
 #include "tdc_ctx.h"
 
 namespace tdc {
@@ -62,6 +65,7 @@ static const int PK_THREADS = 256;
 static const int PK_IPT = 8;
 static const int PK_TILE = PK_THREADS * PK_IPT;
 static const int PK_HALO = 64;  // k <= 64 (sigma >= 2)
+static const int SA_RESIDUE_LOG2 = 10;  // initial sort aims to leave ~n / 2^10 suffixes to the doubling rounds
 
 __global__ void __launch_bounds__(PK_THREADS)
 pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restrict__ code_map, PackParams pp,
@@ -355,6 +359,35 @@ int build_suffix_array(Ctx& c) {
             pw *= sigma;
             pp.top *= sigma;
             pp.k++;
+        }
+    }
+    // Fewer symbols per key = fewer radix passes over all n suffixes; the price is a larger active set in the doubling
+    // rounds.  For a memoryless source a k-symbol prefix is shared with another suffix with probability about
+    // n * 2^(-H0 k) (H0 = empirical order-0 entropy from the byte histogram), so k is chosen to leave ~2^-10 of the
+    // suffixes unresolved, then rounded up to the most symbols that fit the same number of 8-bit passes.  A wrong guess
+    // (text with memory) only moves work into the doubling rounds; the result is the same.
+    {
+        double h0 = 0;
+        for (int b = 0; b < 256; b++)
+            if (hist[b]) { const double pr = double(hist[b]) / double(n); h0 -= pr * log2(pr); }
+        u32 k_need = pp.k;
+        if (h0 > 1e-6) {
+            const double want = ceil((log2(double(n)) + double(SA_RESIDUE_LOG2)) / h0);
+            if (want < double(pp.k)) k_need = u32(want < 1 ? 1 : want);
+        }
+        if (const char* e = getenv("TDCGPU_SA_SYMBOLS")) {  // tuning/debug override
+            const long v = atol(e);
+            if (v >= 1 && v <= long(pp.k)) k_need = u32(v);
+            else k_need = pp.k;
+        } else {
+            const double l2s = log2(double(sigma));
+            const u32 passes = u32(ceil(ceil(k_need * l2s) / 8.0));
+            while (k_need < pp.k && u32(ceil(ceil((k_need + 1) * l2s + 1e-9) / 8.0)) <= passes) k_need++;
+        }
+        if (k_need < pp.k) {
+            pp.k = k_need;
+            pp.top = 1;
+            for (u32 j = 1; j < pp.k; j++) pp.top *= sigma;
         }
     }
     u32 sigbits;
