@@ -78,3 +78,32 @@ def test_sim_lcp_only_routes(simlib, oracle):
             f = c.factors(z)
             got = np.stack([f["pos"], f["src"], f["len"]], 1) if z else np.zeros((0, 3), np.uint32)
             assert np.array_equal(got, oracle.factorize(ds, t.size, 3)), name
+
+
+def test_sim_key_layouts(simlib, oracle):
+    """Initial-key layouts: power-of-two alphabets (length field) and others (sentinel code 0), texts ending in runs of
+    the smallest symbol (the case the length field exists for), and forced short keys (many doubling rounds)."""
+    from tudocomp_b200 import synth
+    rng = np.random.default_rng(77)
+    cases = []
+    for sigma in (1, 2, 3, 4, 7, 8, 16, 100, 128, 254, 255):
+        body = rng.integers(1, sigma + 1, 2500, dtype=np.uint16).astype(np.uint8)
+        cases.append((f"sigma{sigma}", synth.with_sentinel(body)))
+        tail = np.concatenate([body[:700], np.full(40, 1, np.uint8)])  # ...AAAA$ : padded keys would tie
+        cases.append((f"sigma{sigma}_tailrun", synth.with_sentinel(tail)))
+    try:
+        for ksym in (None, "1", "3"):
+            if ksym is None:
+                os.environ.pop("TDCGPU_SA_SYMBOLS", None)
+            else:
+                os.environ["TDCGPU_SA_SYMBOLS"] = ksym
+            for name, t in cases:
+                _check(simlib, oracle, f"{name}/k={ksym}", t, thresholds=(2,))
+                with _abi.Context(simlib) as c:  # LCP alone: seeded from the keys + direct comparison (or Phi route)
+                    c.set_text(t)
+                    c.build(_abi.SA | _abi.LCP)
+                    ds = oracle.textds(t)
+                    assert np.array_equal(c.get(_abi.LCP), ds["lcp"]), (name, ksym, c.sa_stats())
+                    assert c.max_lcp() == ds["max_lcp"], (name, ksym)
+    finally:
+        os.environ.pop("TDCGPU_SA_SYMBOLS", None)

@@ -243,6 +243,36 @@ lcp_direct_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, 
     }
 }
 
+// Seeded variant: the initial sort already wrote the LCP of every pair its keys separate (suffix_array.cu,
+// key_common_symbols); only pairs marked LCP_UNKNOWN — same k-symbol prefix — are compared, starting at offset k.
+__global__ void __launch_bounds__(256)
+lcp_fix_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u64 n, u32* __restrict__ lcp, u32 l0,
+               u32* __restrict__ queue, u32* __restrict__ queue_len, u32* __restrict__ max_lcp) {
+    __shared__ u32 s_max[256 / 32];
+    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool valid = j < n;
+    u32 l = valid ? lcp[j] : 0u;
+    const bool unknown = valid && l == LCP_UNKNOWN;
+    if (__any_sync(kFull, unknown)) {
+        const u32 own = valid ? sa[j] : 0u;
+        u32 prev = __shfl_up_sync(kFull, own, 1);
+        if (unknown) {
+            if (lane_id() == 0) prev = sa[j - 1];  // j >= 1: slot 0 is never unknown
+            bool done;
+            l = lce_thread(text, own, prev, l0, l0 + LCPD_THREAD_LIMIT, &done);
+            if (!done) queue[atomicAdd(queue_len, 1u)] = u32(j);
+            lcp[j] = l;
+        }
+    }
+    u32 mx = warp_max(l);
+    if (lane_id() == 0) s_max[warp_id()] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < 256 / 32; q++) mx = max(mx, s_max[q]);
+        if (mx) atomicMax(max_lcp, mx);
+    }
+}
+
 __global__ void __launch_bounds__(256)
 lcp_direct_long_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u32* __restrict__ lcp,
                        const u32* __restrict__ queue, const u32* __restrict__ queue_len, u32* __restrict__ max_lcp) {
@@ -266,7 +296,13 @@ int build_lcp_direct(Ctx& c) {
     u32* d_qlen = c.d_scalars + 0;
     u32* d_max = c.d_scalars + 1;
     TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
-    TDC_LAUNCH(lcp_direct_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, queue, d_qlen, d_max);
+    if (c.sa_lcp_seeded) {
+        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
+        prof_add_bytes("lcp_fix_kernel", double(n) * 4 + double(c.sa_first_residue) * 72);
+    } else {
+        TDC_LAUNCH(lcp_direct_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, queue, d_qlen, d_max);
+        prof_add_bytes("lcp_direct_kernel", double(n) * 72);
+    }
     TDC_LAUNCH(lcp_direct_long_kernel, u32(c.sm_count * 4), 256, 0, st, c.d_text, c.d_sa, c.d_lcp, queue, d_qlen, d_max);
     TDC_KCHECK();
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -288,7 +324,7 @@ int build_phi_bwt(Ctx& c, bool want_phi, bool want_bwt) {
     TDC_LAUNCH(phi_bwt_kernel, u32(div_up(n, 256)), 256, 0, c.stream, c.d_sa, c.d_text, n, sc_idx[0], sc_val[0],
                want_bwt ? c.d_bwt : nullptr);
     TDC_KCHECK();
-    if (want_phi) TDC_TRY(partitioned_scatter(c.sortws, c.stream, sc_idx, sc_val, n, c.d_phi, n));
+    if (want_phi) TDC_TRY(partitioned_scatter(c.sortws, c.stream, sc_idx, sc_val, n, c.d_phi, n, true));
     return 0;
 }
 

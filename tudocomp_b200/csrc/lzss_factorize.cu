@@ -26,6 +26,10 @@ struct MinTree {
     const u32* l[MT_MAX_LEVELS];  // level 0 = LCP
     u32 sz[MT_MAX_LEVELS];
     int nlev;
+    __device__ __forceinline__ const u32* A(int lvl) const { return a[lvl]; }
+    __device__ __forceinline__ const u32* L(int lvl) const { return l[lvl]; }
+    __device__ __forceinline__ u32 size(int lvl) const { return sz[lvl]; }
+    __device__ __forceinline__ int levels() const { return nlev; }
 };
 
 // one warp per output element: min over 32 inputs
@@ -42,97 +46,156 @@ mintree_level_kernel(const u32* __restrict__ a_in, const u32* __restrict__ l_in,
     if (lane_id() == 0) { a_out[o] = av; l_out[o] = lv; }
 }
 
-// nearest rank q < p with SA[q] < v; m (in: LCP[p]) becomes min LCP[q+1..p].  false: none, or the minimum fell below thr.
-__device__ __forceinline__ bool walk_psv(const MinTree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
-    if (m < thr) return false;
+enum : int { WALK_ABANDONED = 0, WALK_FOUND = 1, WALK_OFF_TREE = 2 };
+
+// Nearest rank q < p with SA[q] < v.  m (in: min LCP over the ranks already passed, LCP[p] at the start) becomes
+// min LCP[q+1..p].  WALK_ABANDONED: the minimum fell below thr (this side cannot produce a factor);
+// WALK_OFF_TREE: no such rank inside this tree (m = minimum over everything passed, so a caller can continue in an
+// enclosing tree from the first rank of this one).
+template <class Tree>
+__device__ __forceinline__ int walk_psv(const Tree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
+    if (m < thr) return WALK_ABANDONED;
     u32 idx = p, q = 0;
     int lvl = 0;
     bool found = false;
     while (!found) {
         const u32 bs = idx & ~31u;
-        const u32* __restrict__ A = T.a[lvl];
-        const u32* __restrict__ L = T.l[lvl];
+        const u32* A = T.A(lvl);
+        const u32* L = T.L(lvl);
         for (q = idx; q-- > bs;) {
             if (A[q] < v) { found = true; break; }
             m = min(m, L[q]);
-            if (m < thr) return false;
+            if (m < thr) return WALK_ABANDONED;
         }
         if (found) break;
-        if (lvl == T.nlev - 1) return false;
+        if (lvl == T.levels() - 1) return WALK_OFF_TREE;
         idx >>= 5;
         lvl++;
     }
     while (lvl > 0) {
-        const u32* __restrict__ A = T.a[lvl - 1];
-        const u32* __restrict__ L = T.l[lvl - 1];
+        const u32* A = T.A(lvl - 1);
+        const u32* L = T.L(lvl - 1);
         const u32 lo = q * 32u;
-        u32 c = min(lo + 32u, T.sz[lvl - 1]);
+        u32 c = min(lo + 32u, T.size(lvl - 1));
         while (c-- > lo) {
             if (A[c] < v) break;
             m = min(m, L[c]);
-            if (m < thr) return false;
+            if (m < thr) return WALK_ABANDONED;
         }
         q = c;
         lvl--;
     }
     q_out = q;
-    return true;
+    return WALK_FOUND;
 }
 
-// nearest rank q > p with SA[q] < v; m becomes min LCP[p+1..q].
-__device__ __forceinline__ bool walk_nsv(const MinTree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
-    m = 0xffffffffu;
+// Nearest rank q > p with SA[q] < v; m (in: minimum so far, 0xffffffff at the start) becomes min LCP[p+1..q].
+template <class Tree>
+__device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
     u32 idx = p, q = 0;
     int lvl = 0;
     bool found = false;
     while (!found) {
-        const u32 be = min((idx | 31u) + 1u, T.sz[lvl]);
-        const u32* __restrict__ A = T.a[lvl];
-        const u32* __restrict__ L = T.l[lvl];
+        const u32 be = min((idx | 31u) + 1u, T.size(lvl));
+        const u32* A = T.A(lvl);
+        const u32* L = T.L(lvl);
         for (q = idx + 1; q < be; q++) {
             if (A[q] < v) { found = true; break; }
             m = min(m, L[q]);
-            if (m < thr) return false;
+            if (m < thr) return WALK_ABANDONED;
         }
         if (found) break;
-        if (lvl == T.nlev - 1) return false;
+        if (lvl == T.levels() - 1) return WALK_OFF_TREE;
         idx >>= 5;
         lvl++;
     }
     while (lvl > 0) {
-        const u32* __restrict__ A = T.a[lvl - 1];
-        const u32* __restrict__ L = T.l[lvl - 1];
+        const u32* A = T.A(lvl - 1);
+        const u32* L = T.L(lvl - 1);
         u32 c = q * 32u;
         while (true) {
             if (A[c] < v) break;
             m = min(m, L[c]);
-            if (m < thr) return false;
+            if (m < thr) return WALK_ABANDONED;
             c++;
         }
         q = c;
         lvl--;
     }
-    m = min(m, T.l[0][q]);
-    if (m < thr) return false;
+    m = min(m, T.L(0)[q]);
+    if (m < thr) return WALK_ABANDONED;
     q_out = q;
-    return true;
+    return WALK_FOUND;
 }
 
-// per rank: longest previous factor length and winning side, scattered to text order
-__global__ void __launch_bounds__(256)
-lpf_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_pos, u32* __restrict__ out_lenside) {
-    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    const u32 v = T.a[0][p];
-    u32 q;
-    u32 mu = T.l[0][p];
-    const u32 lu = walk_psv(T, p, v, thr, mu, q) ? mu : 0u;
-    u32 md;
-    const u32 ld = walk_nsv(T, p, v, thr, md, q) ? md : 0u;
-    const u32 len = max(lu, ld);
-    // lenside[v] = ..., applied by the partitioned scatter that follows (text order is random with respect to ranks)
-    out_pos[p] = v;
-    out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+// Per rank: longest previous factor length and winning side.  A tile of LPF_TILE consecutive ranks of SA and LCP is
+// staged in shared memory together with two local min-tree levels; almost every PSV/NSV walk ends inside its tile at
+// shared-memory latency (a walk is a chain of dependent loads), the few that leave it continue in the global tree.
+// Output in rank order; the partitioned scatter that follows moves it to text order (index side = SA itself).
+#ifdef TDC_CUSIM
+static const int LPF_THREADS = 128;  // small tiles so that the CPU tests leave their tile often
+static const int LPF_TILE = 1024;
+#else
+static const int LPF_THREADS = 512;
+static const int LPF_TILE = 4096;
+#endif
+static const int LPF_L1 = LPF_TILE / 32;  // 128
+static const int LPF_L2 = LPF_L1 / 32;    // 4
+
+// the tile's three levels lie back to back in shared memory: no pointer table, no dynamic indexing
+struct TileTree {
+    const u32* sA;
+    const u32* sL;
+    __device__ __forceinline__ static u32 off(int lvl) { return lvl == 0 ? 0u : (lvl == 1 ? u32(LPF_TILE) : u32(LPF_TILE + LPF_L1)); }
+    __device__ __forceinline__ const u32* A(int lvl) const { return sA + off(lvl); }
+    __device__ __forceinline__ const u32* L(int lvl) const { return sL + off(lvl); }
+    __device__ __forceinline__ u32 size(int lvl) const { return lvl == 0 ? u32(LPF_TILE) : (lvl == 1 ? u32(LPF_L1) : u32(LPF_L2)); }
+    __device__ __forceinline__ int levels() const { return 3; }
+};
+
+__global__ void __launch_bounds__(LPF_THREADS)
+lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
+    __shared__ u32 sA[LPF_TILE + LPF_L1 + LPF_L2];
+    __shared__ u32 sL[LPF_TILE + LPF_L1 + LPF_L2];
+    const u32 base = blockIdx.x * LPF_TILE;
+    for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
+        const u32 i = base + j;
+        sA[j] = i < n ? T.a[0][i] : 0xffffffffu;
+        sL[j] = i < n ? T.l[0][i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (u32 g = warp_id(); g < LPF_L1; g += LPF_THREADS / 32) {
+        const u32 av = warp_min(sA[g * 32 + lane_id()]);
+        const u32 lv = warp_min(sL[g * 32 + lane_id()]);
+        if (lane_id() == 0) { sA[LPF_TILE + g] = av; sL[LPF_TILE + g] = lv; }
+    }
+    __syncthreads();
+    if (warp_id() < LPF_L2) {
+        const u32 av = warp_min(sA[LPF_TILE + warp_id() * 32 + lane_id()]);
+        const u32 lv = warp_min(sL[LPF_TILE + warp_id() * 32 + lane_id()]);
+        if (lane_id() == 0) { sA[LPF_TILE + LPF_L1 + warp_id()] = av; sL[LPF_TILE + LPF_L1 + warp_id()] = lv; }
+    }
+    __syncthreads();
+    TileTree S;
+    S.sA = sA;
+    S.sL = sL;
+    const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
+    for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
+        const u32 p = base + j;
+        if (p >= n) break;
+        const u32 v = sA[j];
+        u32 q;
+        u32 mu = sL[j];
+        int r = walk_psv(S, j, v, thr, mu, q);
+        if (r == WALK_OFF_TREE) r = walk_psv(T, base, v, thr, mu, q);
+        const u32 lu = r == WALK_FOUND ? mu : 0u;
+        u32 md = 0xffffffffu;
+        r = walk_nsv(S, j, v, thr, md, q);
+        if (r == WALK_OFF_TREE) r = walk_nsv(T, last, v, thr, md, q);
+        const u32 ld = r == WALK_FOUND ? md : 0u;
+        const u32 len = max(lu, ld);
+        out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -290,7 +353,7 @@ emit_factors_kernel(MinTree T, const u32* __restrict__ isa, const u32* __restric
         const u32 ls = lenside[i];
         const u32 len = ls >> 1;
         const u32 p = isa[i];
-        u32 q = 0, m;
+        u32 q = 0, m = 0xffffffffu;
         if (ls & 1u) {
             walk_nsv(T, p, i, thr, m, q);
         } else {
@@ -365,12 +428,14 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
 
     // ---- 2. LPF per rank ----
     {
-        u32* sc_idx[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
+        // (index, value) pairs of the scatter to text order: the index side is SA itself (read only)
+        u32* sc_idx[2] = {c.d_sa, c.arena.take<u32>(n)};
         u32* sc_val[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
-        if (!sc_idx[0] || !sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("lzss_lcp: scratch arena too small"); return -2; }
-        TDC_LAUNCH(lpf_kernel, u32(div_up(u64(n), 256)), 256, 0, st, T, n, threshold, sc_idx[0], sc_val[0]);
+        if (!sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+        TDC_LAUNCH(lpf_tile_kernel, u32(div_up(u64(n), LPF_TILE)), LPF_THREADS, 0, st, T, n, threshold, sc_val[0]);
+        prof_add_bytes("lpf_tile_kernel", double(n) * 12);
         TDC_KCHECK();
-        TDC_TRY(partitioned_scatter(c.sortws, st, sc_idx, sc_val, n, lenside, n));
+        TDC_TRY(partitioned_scatter(c.sortws, st, sc_idx, sc_val, n, lenside, n, true));
     }
     // ---- 3. chain ----
     TDC_LAUNCH(chain_exit_kernel, ntiles, CH_THREADS, 0, st, lenside, n, exitp);

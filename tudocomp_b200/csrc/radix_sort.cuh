@@ -239,6 +239,12 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     }
 }
 
+// bucket starts of a single pass over keys that are a permutation of 0..m-1: no need to read the keys
+static __global__ void __launch_bounds__(256) rs_perm_starts_kernel(u32* __restrict__ ghist, u64 m, u32 shift) {
+    const u64 s = u64(threadIdx.x) << shift;
+    ghist[threadIdx.x] = u32(s < m ? s : m);
+}
+
 static __global__ void rs_iota_kernel(u32* v, u64 m) {
     u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < m) v[i] = u32(i);
@@ -259,10 +265,11 @@ void sort_workspace_free(SortWorkspace& ws);
 
 // Sorts m pairs by key bits [begin_bit, end_bit).  Buffers ping-pong between (k[0], v[0]) and (k[1], v[1]); the input
 // is in slot 0 and *result receives the slot holding the output.  With iota=true the input values are implicitly
-// 0..m-1 (v[0] is not read).  Stable.
+// 0..m-1 (v[0] is not read).  keys_are_perm: the keys are a permutation of 0..m-1 and [begin_bit, end_bit) is one
+// digit reaching the top key bit, so the bucket starts are known without a histogram.  Stable.
 template <class K>
 int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64 m, int begin_bit, int end_bit,
-                     bool iota, int* result) {
+                     bool iota, int* result, bool keys_are_perm = false) {
     *result = 0;
     if (m == 0) return 0;
     const int bits = end_bit - begin_bit;
@@ -281,7 +288,10 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
     }
     int cur = 0;
     bool need_iota = iota;
-    if (plan.npass > 0) {
+    if (plan.npass == 1 && keys_are_perm) {
+        TDC_LAUNCH(rs_perm_starts_kernel, 1, 256, 0, st, ws.hist, m, plan.shift[0]);
+        ws.h_uniform[0] = 0;
+    } else if (plan.npass > 0) {
         TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
         TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
         const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
@@ -292,6 +302,8 @@ int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64
         TDC_KCHECK();
         TDC_CUDA(cudaMemcpyAsync(ws.h_uniform, ws.uniform, sizeof(u32) * RS_MAX_PASSES, cudaMemcpyDeviceToHost, st));
         TDC_CUDA(cudaStreamSynchronize(st));
+    }
+    if (plan.npass > 0) {
         const u32 grid = u32(rs_tiles<K>(m));
         const size_t smem = rs_smem_bytes<K>();
         for (int p = 0; p < plan.npass; p++) {
@@ -349,13 +361,15 @@ static const int PS_WINDOW_BITS = 22;             // window = 2^22 elements = 16
 #endif
 
 // idx[0]/val[0] hold the pairs; idx[1]/val[1] are scratch of the same size.  n_dst = size of dst (bounds the idx bits).
-static inline int partitioned_scatter(SortWorkspace& ws, cudaStream_t st, u32* idx[2], u32* val[2], u64 m, u32* dst, u64 n_dst) {
+// full_perm: idx is a permutation of 0..n_dst-1 (m == n_dst), which makes the partition pass histogram-free.
+static inline int partitioned_scatter(SortWorkspace& ws, cudaStream_t st, u32* idx[2], u32* val[2], u64 m, u32* dst, u64 n_dst,
+                                      bool full_perm = false) {
     if (m == 0) return 0;
     int res = 0;
     const int bits = int(bits_for_host(n_dst > 1 ? n_dst - 1 : 1));
     if (m >= PS_DIRECT_BELOW && bits > PS_WINDOW_BITS) {
         const int wbits = bits - PS_WINDOW_BITS > 8 ? 8 : bits - PS_WINDOW_BITS;  // at most 256 windows
-        TDC_TRY(radix_sort_pairs<u32>(ws, st, idx, val, m, bits - wbits, bits, false, &res));
+        TDC_TRY(radix_sort_pairs<u32>(ws, st, idx, val, m, bits - wbits, bits, false, &res, full_perm && m == n_dst));
     }
     TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256)), 256, 0, st, idx[res], val[res], m, dst);
     prof_add_bytes("scatter_pairs_kernel", double(m) * 12);

@@ -75,15 +75,18 @@ struct Ctx {
     u64 sa_active_sum = 0;
     u32 alphabet = 0, symbols_per_key = 0;
     double sa_prefix_work = 0;  // sum over doubling rounds of (active suffixes x already-known common prefix): LCP-sum estimate
+    bool sa_lcp_seeded = false;  // d_lcp holds key-derived LCPs / LCP_UNKNOWN marks from the initial sort
+    u64 sa_first_residue = 0;    // suffixes the initial sort left in groups
     u32 lcp_route = 0;          // 1 = direct comparison in SA order, 2 = Phi/PLCP route
 };
 
 // suffix_array.cu
-int build_suffix_array(Ctx& c);  // fills d_sa and d_isa
+int build_suffix_array(Ctx& c, bool want_lcp);  // fills d_sa and d_isa; want_lcp: seed d_lcp from the initial keys
 // lcp.cu
 int build_phi_bwt(Ctx& c, bool want_phi, bool want_bwt);
 int build_plcp_lcp(Ctx& c, bool want_lcp);
 int build_lcp_direct(Ctx& c);  // LCP without Phi/PLCP (texts with short common prefixes)
+static const u32 LCP_UNKNOWN = 0xffffffffu;  // LCP slot of a pair the initial keys could not separate
 // lzss_factorize.cu
 int factorize_lzss_lcp(Ctx& c, u32 threshold);
 

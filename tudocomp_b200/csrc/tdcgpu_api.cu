@@ -147,7 +147,8 @@ static int do_build(Ctx& c, u32 flags) {
     if ((need & DS_LCP) && !(c.have & DS_LCP) && !((need | c.have) & (DS_PHI | DS_PLCP))) {
         if (!(c.have & DS_SA)) {
             PhaseTimer t(c, "Construct SA");
-            TDC_TRY(build_suffix_array(c));
+            TDC_TRY(lazy_alloc(&c.d_lcp, c.cap_n));  // the initial sort seeds it with the LCPs its keys decide
+            TDC_TRY(build_suffix_array(c, true));
             c.have |= DS_SA | DS_ISA;
         }
         lcp_direct = c.sa_prefix_work / double(c.n) <= 48.0;
@@ -168,7 +169,7 @@ static int do_build(Ctx& c, u32 flags) {
     if (!need) return 0;
     if (need & DS_SA) {
         PhaseTimer t(c, "Construct SA");  // also yields ISA ("Construct ISA" is free on this path)
-        TDC_TRY(build_suffix_array(c));
+        TDC_TRY(build_suffix_array(c, false));
         c.have |= DS_SA | DS_ISA;
     }
     if (need & (DS_PHI | DS_BWT)) {
