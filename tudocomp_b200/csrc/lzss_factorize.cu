@@ -26,8 +26,8 @@ struct MinTree {
     const u32* l[MT_MAX_LEVELS];  // level 0 = LCP
     u32 sz[MT_MAX_LEVELS];
     int nlev;
-    __device__ __forceinline__ const u32* A(int lvl) const { return a[lvl]; }
-    __device__ __forceinline__ const u32* L(int lvl) const { return l[lvl]; }
+    __device__ __forceinline__ u32 A(int lvl, u32 i) const { return a[lvl][i]; }
+    __device__ __forceinline__ u32 L(int lvl, u32 i) const { return l[lvl][i]; }
     __device__ __forceinline__ u32 size(int lvl) const { return sz[lvl]; }
     __device__ __forceinline__ int levels() const { return nlev; }
 };
@@ -60,11 +60,9 @@ __device__ __forceinline__ int walk_psv(const Tree& T, u32 p, u32 v, u32 thr, u3
     bool found = false;
     while (!found) {
         const u32 bs = idx & ~31u;
-        const u32* A = T.A(lvl);
-        const u32* L = T.L(lvl);
         for (q = idx; q-- > bs;) {
-            if (A[q] < v) { found = true; break; }
-            m = min(m, L[q]);
+            if (T.A(lvl, q) < v) { found = true; break; }
+            m = min(m, T.L(lvl, q));
             if (m < thr) return WALK_ABANDONED;
         }
         if (found) break;
@@ -73,13 +71,11 @@ __device__ __forceinline__ int walk_psv(const Tree& T, u32 p, u32 v, u32 thr, u3
         lvl++;
     }
     while (lvl > 0) {
-        const u32* A = T.A(lvl - 1);
-        const u32* L = T.L(lvl - 1);
         const u32 lo = q * 32u;
         u32 c = min(lo + 32u, T.size(lvl - 1));
         while (c-- > lo) {
-            if (A[c] < v) break;
-            m = min(m, L[c]);
+            if (T.A(lvl - 1, c) < v) break;
+            m = min(m, T.L(lvl - 1, c));
             if (m < thr) return WALK_ABANDONED;
         }
         q = c;
@@ -92,16 +88,15 @@ __device__ __forceinline__ int walk_psv(const Tree& T, u32 p, u32 v, u32 thr, u3
 // Nearest rank q > p with SA[q] < v; m (in: minimum so far, 0xffffffff at the start) becomes min LCP[p+1..q].
 template <class Tree>
 __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u32& m, u32& q_out) {
+    if (m < thr) return WALK_ABANDONED;
     u32 idx = p, q = 0;
     int lvl = 0;
     bool found = false;
     while (!found) {
         const u32 be = min((idx | 31u) + 1u, T.size(lvl));
-        const u32* A = T.A(lvl);
-        const u32* L = T.L(lvl);
         for (q = idx + 1; q < be; q++) {
-            if (A[q] < v) { found = true; break; }
-            m = min(m, L[q]);
+            if (T.A(lvl, q) < v) { found = true; break; }
+            m = min(m, T.L(lvl, q));
             if (m < thr) return WALK_ABANDONED;
         }
         if (found) break;
@@ -110,91 +105,223 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
         lvl++;
     }
     while (lvl > 0) {
-        const u32* A = T.A(lvl - 1);
-        const u32* L = T.L(lvl - 1);
         u32 c = q * 32u;
         while (true) {
-            if (A[c] < v) break;
-            m = min(m, L[c]);
+            if (T.A(lvl - 1, c) < v) break;
+            m = min(m, T.L(lvl - 1, c));
             if (m < thr) return WALK_ABANDONED;
             c++;
         }
         q = c;
         lvl--;
     }
-    m = min(m, T.L(0)[q]);
+    m = min(m, T.L(0, q));
     if (m < thr) return WALK_ABANDONED;
     q_out = q;
     return WALK_FOUND;
 }
 
-// Per rank: longest previous factor length and winning side.  A tile of LPF_TILE consecutive ranks of SA and LCP is
-// staged in shared memory together with two local min-tree levels; almost every PSV/NSV walk ends inside its tile at
-// shared-memory latency (a walk is a chain of dependent loads), the few that leave it continue in the global tree.
-// Output in rank order; the partitioned scatter that follows moves it to text order (index side = SA itself).
+// ---------------------------------------------------------------------------------------------------------------
+// Per rank: longest previous factor length and winning side.
+//
+// A tile of LPF_TILE consecutive ranks of SA and LCP is staged in shared memory; ONE THREAD owns a chunk of 32
+// consecutive ranks and runs the sequential all-nearest-smaller-values recurrence over it: "pop" = follow the PSV
+// pointer of the current candidate, carrying the LCP minimum of the skipped range.  That is amortised O(1) per rank
+// whatever the distribution of distances, so a warp never waits for one lane's long linear walk (the first version, one
+// independent walk per rank, spent 50 instructions per rank on exactly that divergence).  Only a chunk's prefix minima
+// (PSV side) / suffix minima (NSV side) are unresolved; their answers are nested, so ONE continuing tree walk per chunk
+// and side resolves all of them: three tile-local levels in shared memory first, the global tree for the few that leave
+// the tile.  Output in rank order; the partitioned scatter that follows moves it to text order.
+// ---------------------------------------------------------------------------------------------------------------
 #ifdef TDC_CUSIM
-static const int LPF_THREADS = 128;  // small tiles so that the CPU tests leave their tile often
-static const int LPF_TILE = 1024;
+static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
-static const int LPF_THREADS = 512;
-static const int LPF_TILE = 4096;
+static const int LPF_THREADS = 128;
 #endif
-static const int LPF_L1 = LPF_TILE / 32;  // 128
-static const int LPF_L2 = LPF_L1 / 32;    // 4
+static const int LPF_TILE = LPF_THREADS * 32;
+static const int LPF_L1 = LPF_TILE / 32;           // one entry per chunk
+static const int LPF_L2 = (LPF_L1 + 31) / 32;
+static const u32 LPF_INF = 0xffffffffu;
 
-// the tile's three levels lie back to back in shared memory: no pointer table, no dynamic indexing
+// level 0 is XOR-swizzled: a thread walking its own chunk (index t*32 + s) and a warp reading 32 consecutive ranks
+// both touch 32 different banks
+__device__ __forceinline__ u32 lpf_phys(u32 i) { return i ^ ((i >> 5) & 31u); }
+
 struct TileTree {
-    const u32* sA;
+    const u32* sA;  // [LPF_TILE] swizzled, then LPF_L1, then LPF_L2 plain
     const u32* sL;
-    __device__ __forceinline__ static u32 off(int lvl) { return lvl == 0 ? 0u : (lvl == 1 ? u32(LPF_TILE) : u32(LPF_TILE + LPF_L1)); }
-    __device__ __forceinline__ const u32* A(int lvl) const { return sA + off(lvl); }
-    __device__ __forceinline__ const u32* L(int lvl) const { return sL + off(lvl); }
+    __device__ __forceinline__ u32 A(int lvl, u32 i) const {
+        return lvl == 0 ? sA[lpf_phys(i)] : (lvl == 1 ? sA[LPF_TILE + i] : sA[LPF_TILE + LPF_L1 + i]);
+    }
+    __device__ __forceinline__ u32 L(int lvl, u32 i) const {
+        return lvl == 0 ? sL[lpf_phys(i)] : (lvl == 1 ? sL[LPF_TILE + i] : sL[LPF_TILE + LPF_L1 + i]);
+    }
     __device__ __forceinline__ u32 size(int lvl) const { return lvl == 0 ? u32(LPF_TILE) : (lvl == 1 ? u32(LPF_L1) : u32(LPF_L2)); }
     __device__ __forceinline__ int levels() const { return 3; }
 };
 
+static inline size_t lpf_smem_bytes() {
+    return sizeof(u32) * (2 * (LPF_TILE + LPF_L1 + LPF_L2) + 2 * LPF_TILE) + LPF_TILE;
+}
+
 __global__ void __launch_bounds__(LPF_THREADS)
 lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
-    __shared__ u32 sA[LPF_TILE + LPF_L1 + LPF_L2];
-    __shared__ u32 sL[LPF_TILE + LPF_L1 + LPF_L2];
+    TDC_DYN_SMEM(smem_raw);
+    u32* sA = reinterpret_cast<u32*>(smem_raw);
+    u32* sL = sA + (LPF_TILE + LPF_L1 + LPF_L2);
+    u32* sU = sL + (LPF_TILE + LPF_L1 + LPF_L2);  // l_up per rank, later the combined result (swizzled like level 0)
+    u32* sD = sU + LPF_TILE;                       // l_dn per rank
+    uint8_t* sP = reinterpret_cast<uint8_t*>(sD + LPF_TILE);  // chunk-local PSV / NSV pointer (+1, 0 = none), swizzled
     const u32 base = blockIdx.x * LPF_TILE;
     for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
         const u32 i = base + j;
-        sA[j] = i < n ? T.a[0][i] : 0xffffffffu;
-        sL[j] = i < n ? T.l[0][i] : 0xffffffffu;
+        sA[lpf_phys(j)] = i < n ? T.a[0][i] : LPF_INF;
+        sL[lpf_phys(j)] = i < n ? T.l[0][i] : LPF_INF;
     }
     __syncthreads();
-    for (u32 g = warp_id(); g < LPF_L1; g += LPF_THREADS / 32) {
-        const u32 av = warp_min(sA[g * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[g * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPF_TILE + g] = av; sL[LPF_TILE + g] = lv; }
+    const u32 cs = threadIdx.x * 32u;  // this thread's chunk [cs, cs + 32)
+    const u32 sw = threadIdx.x & 31u;  // swizzle of the chunk: phys(cs + s) = cs + (s ^ sw)
+
+    // ---- pass 1: PSV inside the chunk, left to right; flat loop (every iteration either pops or finishes a rank) ----
+    u32 unres_up = 0;  // bit s: rank cs+s has no smaller value to its left inside the chunk
+    {
+        u32 s = 0, v = sA[cs + (0 ^ sw)], m = sL[cs + (0 ^ sw)];
+        int j = -1;  // candidate (chunk-local), -1 = none left
+        u32 amin = v, lmin = m;
+        while (true) {
+            if (j >= 0 && sA[cs + (u32(j) ^ sw)] > v) {
+                m = min(m, sU[cs + (u32(j) ^ sw)]);
+                j = int(sP[cs + (u32(j) ^ sw)]) - 1;
+            } else {
+                sU[cs + (s ^ sw)] = m;
+                sP[cs + (s ^ sw)] = uint8_t(j + 1);
+                if (j < 0) unres_up |= 1u << s;
+                if (++s == 32) break;
+                v = sA[cs + (s ^ sw)];
+                m = sL[cs + (s ^ sw)];
+                amin = min(amin, v);
+                lmin = min(lmin, m);
+                j = int(s) - 1;
+            }
+        }
+        sA[LPF_TILE + threadIdx.x] = amin;
+        sL[LPF_TILE + threadIdx.x] = lmin;
     }
     __syncthreads();
-    if (warp_id() < LPF_L2) {
-        const u32 av = warp_min(sA[LPF_TILE + warp_id() * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[LPF_TILE + warp_id() * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPF_TILE + LPF_L1 + warp_id()] = av; sL[LPF_TILE + LPF_L1 + warp_id()] = lv; }
+    if (threadIdx.x < LPF_L2) {
+        u32 av = LPF_INF, lv = LPF_INF;
+        for (u32 k = threadIdx.x * 32; k < min(threadIdx.x * 32 + 32, u32(LPF_L1)); k++) {
+            av = min(av, sA[LPF_TILE + k]);
+            lv = min(lv, sL[LPF_TILE + k]);
+        }
+        sA[LPF_TILE + LPF_L1 + threadIdx.x] = av;
+        sL[LPF_TILE + LPF_L1 + threadIdx.x] = lv;
     }
     __syncthreads();
     TileTree S;
     S.sA = sA;
     S.sL = sL;
-    const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
+    // ---- PSV of the chunk's prefix minima: one continuing walk to the left (values fall, answers move left) ----
+    {
+        u32 m = LPF_INF, pos = cs;
+        int mode = 0;  // 0: inside the tile, 1: global tree, 2: no smaller value further left / below the threshold
+        u32 bits = unres_up;
+        while (bits) {
+            const u32 s = __ffs(int(bits)) - 1;
+            bits &= bits - 1;
+            const u32 v = sA[cs + (s ^ sw)];
+            u32 lu = 0;
+            if (v != LPF_INF && mode != 2) {
+                m = min(m, sU[cs + (s ^ sw)]);  // + min LCP[cs..cs+s]
+                u32 q = 0;
+                int r = WALK_OFF_TREE;
+                if (mode == 0) {
+                    r = walk_psv(S, pos, v, thr, m, q);
+                    if (r == WALK_FOUND) pos = q + 1;
+                    if (r == WALK_OFF_TREE) { mode = 1; pos = base; }
+                }
+                if (mode == 1 && r == WALK_OFF_TREE) {
+                    r = walk_psv(T, pos, v, thr, m, q);
+                    if (r == WALK_FOUND) pos = q + 1;
+                }
+                if (r == WALK_FOUND) lu = m; else mode = 2;
+            }
+            sU[cs + (s ^ sw)] = lu;
+        }
+    }
+    // ---- pass 2: NSV inside the chunk, right to left ----
+    u32 unres_dn = 0;
+    {
+        int s = 31;
+        u32 v = sA[cs + (31u ^ sw)], m = LPF_INF;
+        u32 j = 32;  // candidate (chunk-local), 32 = none left
+        bool fresh = true;  // candidate j has not been examined yet (its own LCP is not in m)
+        while (true) {
+            bool finish = j >= 32;
+            if (!finish) {
+                const u32 pj = cs + (j ^ sw);
+                if (fresh) m = min(m, sL[pj]);
+                if (sA[pj] < v) {
+                    finish = true;
+                } else {
+                    m = min(m, sD[pj]);
+                    const u32 nx = sP[pj];
+                    j = nx ? nx - 1 : 32u;
+                    fresh = false;  // LCP[N[j]] is part of l_dn[j]
+                }
+            }
+            if (finish) {
+                sD[cs + (u32(s) ^ sw)] = m;
+                sP[cs + (u32(s) ^ sw)] = uint8_t(j < 32 ? j + 1 : 0);
+                if (j >= 32) unres_dn |= 1u << s;
+                if (--s < 0) break;
+                v = sA[cs + (u32(s) ^ sw)];
+                m = LPF_INF;
+                j = u32(s) + 1;
+                fresh = true;
+            }
+        }
+    }
+    // ---- NSV of the chunk's suffix minima: one continuing walk to the right ----
+    {
+        const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
+        u32 m = LPF_INF, pos = cs + 31;
+        int mode = 0;
+        u32 bits = unres_dn;
+        while (bits) {
+            const u32 s = 31u - u32(__clz(int(bits)));
+            bits &= ~(1u << s);
+            const u32 v = sA[cs + (s ^ sw)];
+            u32 ld = 0;
+            if (v != LPF_INF && mode != 2) {
+                m = min(m, sD[cs + (s ^ sw)]);  // + min LCP[cs+s+1..cs+31]
+                u32 q = 0;
+                int r = WALK_OFF_TREE;
+                if (mode == 0) {
+                    r = walk_nsv(S, pos, v, thr, m, q);
+                    if (r == WALK_FOUND) pos = q - 1;
+                    if (r == WALK_OFF_TREE) { mode = 1; pos = last; }
+                }
+                if (mode == 1 && r == WALK_OFF_TREE) {
+                    r = walk_nsv(T, pos, v, thr, m, q);
+                    if (r == WALK_FOUND) pos = q - 1;
+                }
+                if (r == WALK_FOUND) ld = m; else mode = 2;
+            }
+            sD[cs + (s ^ sw)] = ld;
+        }
+    }
+    // ---- combine (PSV wins ties, LZSSLCPCompressor.hpp:101) ----
+#pragma unroll 4
+    for (u32 s = 0; s < 32; s++) {
+        const u32 lu = sU[cs + (s ^ sw)], ld = sD[cs + (s ^ sw)];
+        const u32 len = max(lu, ld);
+        sU[cs + (s ^ sw)] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+    }
+    __syncthreads();
     for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
         const u32 p = base + j;
-        if (p >= n) break;
-        const u32 v = sA[j];
-        u32 q;
-        u32 mu = sL[j];
-        int r = walk_psv(S, j, v, thr, mu, q);
-        if (r == WALK_OFF_TREE) r = walk_psv(T, base, v, thr, mu, q);
-        const u32 lu = r == WALK_FOUND ? mu : 0u;
-        u32 md = 0xffffffffu;
-        r = walk_nsv(S, j, v, thr, md, q);
-        if (r == WALK_OFF_TREE) r = walk_nsv(T, last, v, thr, md, q);
-        const u32 ld = r == WALK_FOUND ? md : 0u;
-        const u32 len = max(lu, ld);
-        out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+        if (p < n) out_lenside[p] = sU[lpf_phys(j)];
     }
 }
 
@@ -432,7 +559,8 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         u32* sc_idx[2] = {c.d_sa, c.arena.take<u32>(n)};
         u32* sc_val[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
         if (!sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("lzss_lcp: scratch arena too small"); return -2; }
-        TDC_LAUNCH(lpf_tile_kernel, u32(div_up(u64(n), LPF_TILE)), LPF_THREADS, 0, st, T, n, threshold, sc_val[0]);
+        TDC_CUDA(cudaFuncSetAttribute(lpf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lpf_smem_bytes())));
+        TDC_LAUNCH(lpf_tile_kernel, u32(div_up(u64(n), LPF_TILE)), LPF_THREADS, lpf_smem_bytes(), st, T, n, threshold, sc_val[0]);
         prof_add_bytes("lpf_tile_kernel", double(n) * 12);
         TDC_KCHECK();
         TDC_TRY(partitioned_scatter(c.sortws, st, sc_idx, sc_val, n, lenside, n, true));
