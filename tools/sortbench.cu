@@ -66,7 +66,7 @@ int main(int argc, char** argv) {
     cudaError_t e = cudaGetLastError();
     const int npass = (bits + 7) / 8;
     printf("threads=%d ipt=%d minctas=%d smem=%zu m=2^%d bits=%d: %.3f ms total, %.3f ms/pass incl. histogram, %.1f GB/s per pass (24 B/elem), unsorted=%u %s\n",
-           RS_THREADS, RsCfg<u64>::IPT, RS_MIN_CTAS, rs_smem_bytes<u64>(), lg, bits, best, best / npass, 24.0 * m / 1e9 / (best / npass / 1e3), hbad,
+           RS_THREADS, RsCfg<u64>::IPT, RsCfg<u64>::MIN_CTAS, rs_smem_bytes<u64>(), lg, bits, best, best / npass, 24.0 * m / 1e9 / (best / npass / 1e3), hbad,
            e == cudaSuccess ? "" : cudaGetErrorString(e));
     return hbad != 0;
 }

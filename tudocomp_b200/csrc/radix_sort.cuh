@@ -16,10 +16,10 @@ namespace tdc {
 #define RS_THREADS_CFG 256
 #endif
 #ifndef RS_IPT64_CFG
-#define RS_IPT64_CFG 12
+#define RS_IPT64_CFG 16
 #endif
 #ifndef RS_MIN_CTAS_CFG
-#define RS_MIN_CTAS_CFG 4
+#define RS_MIN_CTAS_CFG 3
 #endif
 static const int RS_THREADS = RS_THREADS_CFG;  // >= 256: one thread per digit in the look-back
 static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
@@ -46,8 +46,8 @@ struct SortWorkspace {
 };
 
 template <class K> struct RsCfg;
-template <> struct RsCfg<u64> { static const int IPT = RS_IPT64_CFG; };
-template <> struct RsCfg<u32> { static const int IPT = 16; };
+template <> struct RsCfg<u64> { static const int IPT = RS_IPT64_CFG; static const int MIN_CTAS = RS_MIN_CTAS_CFG; };
+template <> struct RsCfg<u32> { static const int IPT = 16; static const int MIN_CTAS = 4; };
 
 static const ull RS_STATUS_AGG = 1, RS_STATUS_PREFIX = 2;
 
@@ -132,7 +132,7 @@ __device__ __forceinline__ u32 match_digit(u32 d, u32 nbits_mask) {
 // Tile ids are blockIdx.x: CTAs of a 1-D grid are dispatched in index order, so every predecessor a tile looks back
 // at is resident or finished (the same assumption CUB's decoupled look-back scan makes).
 template <class K, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
+__global__ void __launch_bounds__(RS_THREADS, RsCfg<K>::MIN_CTAS)
 rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* __restrict__ vin, u32* __restrict__ vout,
                    u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc, u32 epoch) {
     constexpr int IPT = RsCfg<K>::IPT;
@@ -268,10 +268,18 @@ void sort_workspace_free(SortWorkspace& ws);
 // 0..m-1 (v[0] is not read).  keys_are_perm: the keys are a permutation of 0..m-1 and [begin_bit, end_bit) is one
 // digit reaching the top key bit, so the bucket starts are known without a histogram.  Stable.
 template <class K>
-int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64 m, int begin_bit, int end_bit,
-                     bool iota, int* result, bool keys_are_perm = false) {
+static int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64 m, int begin_bit, int end_bit,
+                            bool iota, int* result, bool keys_are_perm = false) {
     *result = 0;
     if (m == 0) return 0;
+    {
+        // > 48 KB of dynamic shared memory needs an opt-in per kernel, per device and per translation unit (internal
+        // linkage: every TU that sorts has its own copy of this function and of the kernels it launches); a few us
+        auto k1 = rs_onesweep_kernel<K, true>;
+        auto k2 = rs_onesweep_kernel<K, false>;
+        TDC_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<K>())));
+        TDC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<K>())));
+    }
     const int bits = end_bit - begin_bit;
     PassPlan plan;
     plan.npass = bits <= 0 ? 0 : (bits + 7) / 8;
