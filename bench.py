@@ -134,6 +134,112 @@ def cpu_reference_run(sample: np.ndarray, steps: int):
     return kind, times
 
 
+def main_dist(args, rank, local_rank, world, n_body, seed):
+    """One text of n_body bytes sharded over all ranks (config 4 of BASELINE.json): distributed prefix-doubling SA with
+    NCCL all-to-all exchanges, LCP, lzss_lcp factorisation.  Strong scaling: value = n_body / step time (max over ranks)."""
+    import torch
+
+    import tudocomp_b200 as tdc
+    from tudocomp_b200 import blockmode
+    from tudocomp_b200.dist import DistContext
+
+    dist = None
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = tdc.load()
+    ctx = DistContext.create_nccl(lib, local_rank, dist)
+    text = gen_text(args.workload, n_body, seed)  # the same text on every rank
+    n = int(text.size)
+    h_text = torch.from_numpy(text).pin_memory()
+    d_text = h_text.to(f"cuda:{local_rank}")
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(host):
+        ctx.set_text_ptr(h_text.data_ptr() if host else d_text.data_ptr(), n, on_device=not host)
+        ctx.build()
+        return ctx.factorize(THRESHOLD)
+
+    zl, zt, mn, mx = step(False)
+    h_factors = torch.empty(int(zl * 1.05) + 1024, 3, dtype=torch.int32).pin_memory()
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.profile_reset()
+    lib.profile_enable(True)
+    barrier()
+    launches0 = lib.launch_count()
+    ctx.event_record(0)
+    for _ in range(args.steps):
+        zl, zt, mn, mx = step(False)
+    ctx.event_record(1)
+    barrier()
+    dev_ms = ctx.event_elapsed_ms(0, 1)
+    launches = lib.launch_count() - launches0
+    lib.profile_enable(False)
+    prof = lib.profile()
+    phases = ctx.phases()
+    stats = ctx.stats()
+    info = ctx.shard_info()
+    barrier()
+    t1 = time.perf_counter()
+    ctx.event_record(2)
+    for _ in range(args.steps):
+        zl, zt, mn, mx = step(True)
+        ctx.get_factors_into(h_factors.data_ptr(), h_factors.shape[0])
+    ctx.event_record(3)
+    barrier()
+    e2e_ms = max(ctx.event_elapsed_ms(2, 3), 1e3 * (time.perf_counter() - t1))
+    clocks = sampler.stop()
+    ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist)
+    ms_step_e2e = blockmode.reduce_step_time(e2e_ms / args.steps, dist)
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+        roof = None
+        if dom:
+            dd = prof[dom]
+            plb, plm = dd["bytes"] / max(dd["launches"], 1), dd["ms"] / max(dd["launches"], 1)
+            ach = plb / 1e9 / (plm / 1e3) if dd["bytes"] else None
+            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                    "traffic": None, "launches": dd["launches"], "avg_launch_ms": plm, "share_of_step": dd["ms"] / dev_ms,
+                    "note": "rank 0's kernels; the NCCL exchanges are not in this list (they are the gap between the kernel sum and the step time)"}
+        line = {"metric": METRIC, "value": blockmode.job_throughput_mb_s(n_body, ms_step), "unit": "MB/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}_2^{args.log2_bytes}B_single_text_sharded: distributed SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD})",
+                           "text_bytes": n, "threshold": THRESHOLD, "index_bits": 32,
+                           "l2_policy": "working set per GPU far larger than the 126 MB L2; no flush needed",
+                           "parallelism": f"one text sharded over {world} GPUs; NCCL all-to-all of rank buckets, rank updates and rank requests"},
+                "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
+                        "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
+                "dist_stats": stats, "shard_rank0": info,
+                "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "last_step_phases_ms": {k: round(v, 3) for k, v in phases}}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +249,9 @@ def main():
     ap.add_argument("--workload", default="dna", choices=["dna", "markov", "repetitive"])
     ap.add_argument("--log2-bytes", type=int, default=30, help="text body size per GPU = 2^L bytes (default 1 GiB)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="block", choices=["block", "dist"],
+                    help="N > 1: 'block' = one independent text per GPU (weak scaling, no collective); 'dist' = ONE text of "
+                         "2^L bytes sharded over all GPUs (strong scaling, NCCL all-to-all of rank buckets)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -172,6 +281,9 @@ def main():
                 "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
+
+    if args.mode == "dist":
+        return main_dist(args, rank, local_rank, world, n_body, seed_of)
 
     # ------------------------------------------------------------------------------------------------------ our arm
     import torch

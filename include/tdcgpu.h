@@ -117,6 +117,39 @@ void tdcgpu_profile_reset(void);
 int tdcgpu_profile_count(void);
 int tdcgpu_profile_entry(int i, const char** name, uint64_t* launches, double* ms, double* bytes);
 
+/* ---- one text sharded over several GPUs (no reference counterpart: tudocomp is single-threaded) -------------------
+ * One rank = one process = one GPU; ranks exchange data with NCCL (all-to-all of rank buckets, see
+ * tudocomp_b200/csrc/dist_textds.cu).  Every rank passes the SAME full text; results come back as shards:
+ *   SA, LCP   slots   [slot_lo, slot_lo + slot_cnt)   (ranks in increasing order; concatenation = the full array)
+ *   ISA       positions [pos_lo, pos_lo + pos_cnt)
+ *   factors   the factors whose pos lies in the rank's position range, in position order
+ * All functions are collective: every rank of the communicator must call them in the same order.
+ * n < 2^32 - 1 (unsigned 32-bit indices); common prefixes must stay below 2^31. */
+typedef struct tdcgpu_dist tdcgpu_dist;
+/* rank 0 creates the id (ncclGetUniqueId) and hands the 128 bytes to the other ranks by any means */
+int tdcgpu_dist_unique_id(uint8_t id[128]);
+int tdcgpu_dist_create(int device, int rank, int nranks, const uint8_t id[128], tdcgpu_dist** out);
+void tdcgpu_dist_destroy(tdcgpu_dist* h);
+int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on_device);
+/* flags: TDCGPU_SA | TDCGPU_ISA | TDCGPU_LCP */
+int tdcgpu_dist_build(tdcgpu_dist* h, uint32_t flags);
+/* out = { slot_lo, slot_cnt, pos_lo, pos_cnt } */
+int tdcgpu_dist_shard_info(tdcgpu_dist* h, uint64_t out[4]);
+int tdcgpu_dist_get(tdcgpu_dist* h, uint32_t which, void* dst, int to_device);
+int tdcgpu_dist_max_lcp(tdcgpu_dist* h, uint32_t* max_lcp);
+int tdcgpu_dist_lzss_lcp_factorize(tdcgpu_dist* h, uint32_t threshold, uint64_t* local_count, uint64_t* total_count,
+                                   uint32_t* min_len, uint32_t* max_len);
+int tdcgpu_dist_get_factors(tdcgpu_dist* h, tdcgpu_factor* dst, uint64_t cap, int to_device);
+int tdcgpu_dist_sync(tdcgpu_dist* h);
+int tdcgpu_dist_event_record(tdcgpu_dist* h, int slot);
+int tdcgpu_dist_event_elapsed_ms(tdcgpu_dist* h, int slot_a, int slot_b, float* ms);
+/* [0] rounds, [1] sum of active suffixes (this rank), [2] radix passes, [3] elements moved by them, [4] alphabet,
+ * [5] symbols per initial key, [6] per-rank element capacity, [7] total number of factors */
+int tdcgpu_dist_stats(tdcgpu_dist* h, uint64_t out[8]);
+int tdcgpu_dist_phase_count(tdcgpu_dist* h);
+const char* tdcgpu_dist_phase_name(tdcgpu_dist* h, int i);
+float tdcgpu_dist_phase_ms(tdcgpu_dist* h, int i);
+
 #ifdef __cplusplus
 }
 #endif

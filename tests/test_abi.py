@@ -22,7 +22,9 @@ def _declared_symbols():
 def test_library_exports_every_declared_symbol():
     syms = _declared_symbols()
     assert len(syms) >= 15
-    assert sorted(syms) == sorted(_abi.EXPORTS)
+    from tudocomp_b200 import dist as tdist
+
+    assert sorted(syms) == sorted(_abi.EXPORTS + tdist.DIST_EXPORTS)
     lib = ctypes.CDLL(tdc.lib_path())
     for s in syms:
         assert hasattr(lib, s), s
@@ -43,6 +45,17 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == -1
     with pytest.raises(tdc.TdcGpuError):
         tdc.TextDS(np.frombuffer(b"banana\0", np.uint8))
+
+
+def test_multi_gpu_entry_points_fail_loudly_without_device():
+    from tudocomp_b200 import dist as tdist
+
+    lib = tdc.load()
+    if lib.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(tdc.TdcGpuError) as e:
+        tdist.DistContext.create_nccl(lib, 0, None)
+    assert e.value.code == -1 and "no CUDA device" in str(e.value)
 
 
 def test_missing_sentinel_is_rejected_like_the_reference():

@@ -1,0 +1,270 @@
+// Kernels that exist only in the sharded multi-GPU text index (dist_textds.cu): bucket partition for the exchanges,
+// request/reply gathers, the LPF variant that carries source positions and queues walks leaving the shard, and the
+// resolution of such walks on the neighbouring shards.
+#pragma once
+#include "lcp_kernels.cuh"
+#include "lzss_kernels.cuh"
+#include "sa_kernels.cuh"
+
+namespace tdc {
+
+static const int DIST_MAX_RANKS = 16;
+
+// ---------------------------------------------------------------------------------------------------------------
+// bucket functors: which rank does an element go to, and what is sent
+// ---------------------------------------------------------------------------------------------------------------
+struct SplitterFn {  // initial sort: bucket = number of splitters <= key (equal keys share a bucket)
+    u64 spl[DIST_MAX_RANKS - 1];
+    int nspl;
+    __device__ __forceinline__ u32 bucket(u64 key) const {
+        u32 b = 0;
+#pragma unroll
+        for (int i = 0; i < DIST_MAX_RANKS - 1; i++)
+            if (i < nspl && spl[i] <= key) b++;
+        return b;
+    }
+    __device__ __forceinline__ u64 out(u64 key, u32) const { return key; }
+};
+struct OwnerFn {  // position-sharded arrays: owner = position / block, the owner receives its local index
+    u32 block;
+    __device__ __forceinline__ u32 bucket(u32 pos) const { return pos / block; }
+    __device__ __forceinline__ u32 out(u32 pos, u32 b) const { return pos - b * block; }
+};
+
+static const int BP_THREADS = 256;
+static const int BP_IPT = 4;
+static const int BP_TILE = BP_THREADS * BP_IPT;
+
+template <class K, class F>
+static __global__ void __launch_bounds__(BP_THREADS)
+bucket_count_kernel(const K* __restrict__ keys, u64 m, F f, int nbuckets, ull* __restrict__ gcount) {
+    __shared__ u32 cnt[DIST_MAX_RANKS];
+    if (threadIdx.x < DIST_MAX_RANKS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 m_round = (m + 31) & ~u64(31);
+    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < m_round; i += u64(gridDim.x) * blockDim.x) {
+        const u32 b = i < m ? f.bucket(keys[i]) : 0xffffffffu;
+        for (int bb = 0; bb < nbuckets; bb++) {
+            const u32 mask = __ballot_sync(kFull, b == u32(bb));
+            if (lane_id() == 0 && mask) atomicAdd(&cnt[bb], u32(__popc(mask)));
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < u32(nbuckets) && cnt[threadIdx.x]) atomicAdd(&gcount[threadIdx.x], ull(cnt[threadIdx.x]));
+}
+
+// cursor[b] starts at the bucket's first output slot; order inside a bucket is arbitrary (the consumers sort or scatter).
+// vals == nullptr: the value of element i is vbase + i.
+template <class K, class F>
+static __global__ void __launch_bounds__(BP_THREADS)
+bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 vbase, u64 m, F f, int nbuckets,
+                      ull* __restrict__ cursor, K* __restrict__ kout, u32* __restrict__ vout) {
+    __shared__ u32 cnt[DIST_MAX_RANKS];
+    __shared__ ull gbase[DIST_MAX_RANKS];
+    if (threadIdx.x < DIST_MAX_RANKS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 t0 = u64(blockIdx.x) * BP_TILE;
+    K key[BP_IPT];
+    u32 b[BP_IPT], lr[BP_IPT];
+#pragma unroll
+    for (int q = 0; q < BP_IPT; q++) {
+        const u64 i = t0 + u64(q) * BP_THREADS + threadIdx.x;
+        key[q] = i < m ? keys[i] : K(0);
+        b[q] = i < m ? f.bucket(key[q]) : 0xffffffffu;
+        lr[q] = 0;
+        for (int bb = 0; bb < nbuckets; bb++) {
+            const u32 mask = __ballot_sync(kFull, b[q] == u32(bb));
+            u32 base = 0;
+            if (lane_id() == 0 && mask) base = atomicAdd(&cnt[bb], u32(__popc(mask)));
+            base = __shfl_sync(kFull, base, 0);
+            if (b[q] == u32(bb)) lr[q] = base + __popc(mask & lanemask_lt());
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < u32(nbuckets)) gbase[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], ull(cnt[threadIdx.x])) : 0;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < BP_IPT; q++) {
+        const u64 i = t0 + u64(q) * BP_THREADS + threadIdx.x;
+        if (i < m) {
+            const u64 o = gbase[b[q]] + lr[q];
+            kout[o] = f.out(key[q], b[q]);
+            vout[o] = vals ? vals[i] : vbase + u32(i);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// small element-wise helpers
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void add_offset_kernel(const u32* __restrict__ in, u64 m, u32 off, u32* __restrict__ out) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = in[i] + off;
+}
+static __global__ void gather_u32_kernel(const u32* __restrict__ table, const u32* __restrict__ idx, u64 m, u32* __restrict__ out) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = table[idx[i]];
+}
+static __global__ void sample_keys_kernel(const u64* __restrict__ keys, u64 m, u32 samples, u64* __restrict__ out) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < samples) out[j] = m ? keys[(u64(j) * m) / samples] : ~u64(0);
+}
+// doubling key from an already gathered second rank
+static __global__ void build_keys_from_kernel(const u32* __restrict__ gid, const u32* __restrict__ r2, u64 m, u32 rbits,
+                                              u64* __restrict__ keys) {
+    const u64 o = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (o < m) keys[o] = (u64(gid[o]) << rbits) | r2[o];
+}
+// LCP of the first slot of a shard against the last suffix of the previous shard (one warp)
+static __global__ void lcp_boundary_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u32 prev_sa,
+                                           u32* __restrict__ lcp, u32* __restrict__ max_lcp) {
+    const u32 l = lce_warp(text, sa[0], prev_sa, 0);
+    if (lane_id() == 0) { lcp[0] = l; atomicMax(max_lcp, l); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LPF per rank with source positions; walks that leave the shard are queued for the neighbouring shards
+// ---------------------------------------------------------------------------------------------------------------
+struct WalkQuery {  // p: slot index inside the origin shard; v = SA[p]; m = LCP minimum collected so far
+    u32 p, v, m;
+};
+struct WalkAnswer {
+    u32 p, m, src;
+};
+
+#ifdef TDC_CUSIM
+static const int LPFD_THREADS = 128;
+static const int LPFD_TILE = 1024;
+#else
+static const int LPFD_THREADS = 512;
+static const int LPFD_TILE = 4096;
+#endif
+static const int LPFD_L1 = LPFD_TILE / 32;
+static const int LPFD_L2 = LPFD_L1 / 32;
+struct DTileTree {
+    const u32* sA;
+    const u32* sL;
+    __device__ __forceinline__ static u32 off(int lvl) { return lvl == 0 ? 0u : (lvl == 1 ? u32(LPFD_TILE) : u32(LPFD_TILE + LPFD_L1)); }
+    __device__ __forceinline__ u32 A(int lvl, u32 i) const { return sA[off(lvl) + i]; }
+    __device__ __forceinline__ u32 L(int lvl, u32 i) const { return sL[off(lvl) + i]; }
+    __device__ __forceinline__ u32 size(int lvl) const { return lvl == 0 ? u32(LPFD_TILE) : (lvl == 1 ? u32(LPFD_L1) : u32(LPFD_L2)); }
+    __device__ __forceinline__ int levels() const { return 3; }
+};
+
+static __global__ void __launch_bounds__(LPFD_THREADS)
+lpf_dist_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lu_out, u32* __restrict__ su_out, u32* __restrict__ ld_out,
+                u32* __restrict__ sd_out, WalkQuery* __restrict__ q_up, WalkQuery* __restrict__ q_dn,
+                u32* __restrict__ q_cnt /*[2]*/, u32 qcap) {
+    __shared__ u32 sA[LPFD_TILE + LPFD_L1 + LPFD_L2];
+    __shared__ u32 sL[LPFD_TILE + LPFD_L1 + LPFD_L2];
+    const u32 base = blockIdx.x * LPFD_TILE;
+    for (u32 j = threadIdx.x; j < LPFD_TILE; j += LPFD_THREADS) {
+        const u32 i = base + j;
+        sA[j] = i < n ? T.a[0][i] : 0xffffffffu;
+        sL[j] = i < n ? T.l[0][i] : 0xffffffffu;
+    }
+    __syncthreads();
+    for (u32 g = warp_id(); g < LPFD_L1; g += LPFD_THREADS / 32) {
+        const u32 av = warp_min(sA[g * 32 + lane_id()]);
+        const u32 lv = warp_min(sL[g * 32 + lane_id()]);
+        if (lane_id() == 0) { sA[LPFD_TILE + g] = av; sL[LPFD_TILE + g] = lv; }
+    }
+    __syncthreads();
+    if (warp_id() < LPFD_L2) {
+        const u32 av = warp_min(sA[LPFD_TILE + warp_id() * 32 + lane_id()]);
+        const u32 lv = warp_min(sL[LPFD_TILE + warp_id() * 32 + lane_id()]);
+        if (lane_id() == 0) { sA[LPFD_TILE + LPFD_L1 + warp_id()] = av; sL[LPFD_TILE + LPFD_L1 + warp_id()] = lv; }
+    }
+    __syncthreads();
+    DTileTree S;
+    S.sA = sA;
+    S.sL = sL;
+    const u32 last = min(base + u32(LPFD_TILE), n) - 1u;
+    for (u32 j = threadIdx.x; j < LPFD_TILE; j += LPFD_THREADS) {
+        const u32 p = base + j;
+        if (p >= n) break;
+        const u32 v = sA[j];
+        u32 q = 0, lu = 0, su = 0, ld = 0, sd = 0;
+        u32 mu = sL[j];
+        int r = walk_psv(S, j, v, thr, mu, q);
+        if (r == WALK_FOUND) { lu = mu; su = S.A(0, q); }
+        if (r == WALK_OFF_TREE) {
+            r = walk_psv(T, base, v, thr, mu, q);
+            if (r == WALK_FOUND) { lu = mu; su = T.A(0, q); }
+            if (r == WALK_OFF_TREE) {  // nothing smaller further up in this shard: continue on the previous one
+                const u32 slot = atomicAdd(&q_cnt[0], 1u);
+                if (slot < qcap) { WalkQuery w; w.p = p; w.v = v; w.m = mu; q_up[slot] = w; }
+            }
+        }
+        u32 md = 0xffffffffu;
+        r = walk_nsv(S, j, v, thr, md, q);
+        if (r == WALK_FOUND) { ld = md; sd = S.A(0, q); }
+        if (r == WALK_OFF_TREE) {
+            r = walk_nsv(T, last, v, thr, md, q);
+            if (r == WALK_FOUND) { ld = md; sd = T.A(0, q); }
+            if (r == WALK_OFF_TREE) {
+                const u32 slot = atomicAdd(&q_cnt[1], 1u);
+                if (slot < qcap) { WalkQuery w; w.p = p; w.v = v; w.m = md; q_dn[slot] = w; }
+            }
+        }
+        lu_out[p] = lu;
+        su_out[p] = su;
+        ld_out[p] = ld;
+        sd_out[p] = sd;
+    }
+}
+
+// Queries arriving from a neighbouring shard, answered against this shard's tree.  UP: the walk enters at the shard's
+// last slot and moves towards slot 0; otherwise it enters at slot 0 and moves up.  Found -> answer for the origin;
+// not found -> forwarded (with the minimum over this whole shard folded in); below the threshold -> dropped.
+template <bool UP>
+static __global__ void __launch_bounds__(128)
+resolve_queries_kernel(MinTree T, u32 n, u32 thr, const WalkQuery* __restrict__ in, u32 nq, WalkAnswer* __restrict__ ans,
+                       WalkQuery* __restrict__ fwd, u32* __restrict__ cnt /*[0] answers, [1] forwards*/) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq) return;
+    WalkQuery w = in[t];
+    u32 q = 0;
+    int r = WALK_OFF_TREE;
+    if (n > 0) {
+        if (UP) {
+            r = walk_psv(T, n, w.v, thr, w.m, q);
+        } else {
+            w.m = min(w.m, T.l[0][0]);
+            if (w.m < thr) r = WALK_ABANDONED;
+            else if (T.a[0][0] < w.v) { r = WALK_FOUND; q = 0; }
+            else r = walk_nsv(T, 0, w.v, thr, w.m, q);
+        }
+    }
+    if (r == WALK_FOUND) {
+        WalkAnswer a;
+        a.p = w.p;
+        a.m = w.m;
+        a.src = T.a[0][q];
+        ans[atomicAdd(&cnt[0], 1u)] = a;
+    } else if (r == WALK_OFF_TREE) {
+        fwd[atomicAdd(&cnt[1], 1u)] = w;
+    }
+}
+
+static __global__ void apply_answers_kernel(const WalkAnswer* __restrict__ ans, u32 na, u32* __restrict__ l_out, u32* __restrict__ s_out) {
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= na) return;
+    const WalkAnswer a = ans[t];
+    l_out[a.p] = a.m;
+    s_out[a.p] = a.src;
+}
+
+// (l_up, src_up, l_dn, src_dn) -> (len << 1 | side, src); PSV wins ties (LZSSLCPCompressor.hpp:101)
+static __global__ void lpf_combine_kernel(const u32* __restrict__ lu, const u32* __restrict__ su, const u32* __restrict__ ld,
+                                          const u32* __restrict__ sd, u64 m, u32 thr, u32* __restrict__ lenside, u32* __restrict__ src) {
+    const u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const u32 a = lu[i], b = ld[i];
+    const u32 len = max(a, b);
+    const bool up = a >= b;
+    lenside[i] = len >= thr ? ((len << 1) | (up ? 0u : 1u)) : 0u;
+    src[i] = up ? su[i] : sd[i];
+}
+
+}  // namespace tdc

@@ -1,0 +1,832 @@
+// Sharded multi-GPU text index + lzss_lcp factoriser: ONE text, P ranks (one process and one GPU each).
+// No reference counterpart (tudocomp is single-threaded); results are the same SA / ISA / LCP / factor list the
+// single-GPU path and the reference produce (SADivSufSort.hpp:28-51, ISAFromSA.hpp:37-39, LCPFromPLCP.hpp:43-47,
+// LZSSLCPCompressor.hpp:60-115), cut into shards.
+//
+// Layout.  The text (n bytes) is replicated on every rank.  Position-indexed arrays (the rank array = ISA, the
+// text-order LPF table) are sharded by blocks of `block` positions: rank r owns positions [r*block, (r+1)*block).
+// Slot-indexed arrays (SA, LCP) are sharded by the buckets of the initial sort: rank r owns the slots
+// [slot_lo(r), slot_lo(r) + slot_cnt(r)), the ranks in increasing key order.
+//
+// Suffix array by prefix doubling:
+//   round 0  every rank packs the k-symbol keys of its positions, P-1 splitters come from an all-gathered regular
+//            sample, the (key, suffix) pairs are partitioned by splitter and exchanged (ALL-TO-ALL #1: 12 B per
+//            suffix), each rank radix-sorts its bucket.  Equal keys share a bucket, so a group never spans ranks and
+//            every later sort is rank-local.  The new ranks (suffix -> head slot) go to the owners of the positions
+//            (ALL-TO-ALL #2: 8 B per suffix) and are applied with the partitioned scatter.
+//   round r  for the suffixes still in groups: rank[suffix + h] is fetched from its owner (request/reply ALL-TO-ALLs,
+//            4 + 4 B per active suffix), local segmented sort by (group, rank[suffix + h]), re-rank, rank updates to
+//            their owners.  Stops when no rank has a group left (all-gathered count).
+// LCP: compared directly on the replicated text in SA order (seeded by the initial keys); the first slot of a shard is
+//      compared with the previous shard's last suffix.
+// Factorisation: PSV/NSV + range minima per slot on the local min-tree; walks that leave the shard are queued and
+//      travel shard by shard (neighbour exchange, at most P-1 hops; typically a few dozen queries per shard);
+//      (len|side, src) go to text order through the position owners; the greedy chain is walked rank after rank
+//      (one 8-byte hand-over per rank); factors are emitted per rank, already in position order.
+#include <algorithm>
+#include <new>
+
+#include "../../include/tdcgpu.h"
+#include "dist_comm.h"
+#include "dist_kernels.cuh"
+
+namespace tdc {
+
+struct DistCtx {
+    Ctx c;  // device, stream, replicated text, scalars, sort workspace, scratch arena, phase times
+    Comm* comm = nullptr;
+    int P = 1, rank = 0;
+    u64 n = 0;
+    u32 block = 0;
+    u64 pos_lo = 0, pos_cnt = 0, slot_lo = 0, slot_cnt = 0;
+    std::vector<u64> slot_cnts;
+    u64 cap = 0, qcap = 0;
+    u32 *d_sa = nullptr, *d_rank = nullptr, *d_lcp = nullptr;
+    u32 have = 0;
+    ull* d_counts = nullptr;  // [2 * DIST_MAX_RANKS] bucket counts / cursors
+    ull* h_counts = nullptr;  // pinned, [64]
+    u64 total_factors = 0;
+    std::vector<u64> xchg;  // scratch for count matrices
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// exchange helpers
+// ---------------------------------------------------------------------------------------------------------------
+// matrix[r * P + p] = number of elements rank r sends to rank p
+static int exchange_matrix(DistCtx& d, const u64* send_cnt, std::vector<u64>& matrix) {
+    matrix.assign(size_t(d.P) * d.P, 0);
+    return d.comm->allgather_host(send_cnt, matrix.data(), sizeof(u64) * d.P);
+}
+
+static int a2a_elems(DistCtx& d, const void* send, const u64* scnt, void* recv, const u64* rcnt, size_t esz) {
+    u64 soff[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], sb[DIST_MAX_RANKS], rb[DIST_MAX_RANKS];
+    u64 so = 0, ro = 0;
+    for (int p = 0; p < d.P; p++) {
+        soff[p] = so * esz; roff[p] = ro * esz;
+        sb[p] = scnt[p] * esz; rb[p] = rcnt[p] * esz;
+        so += scnt[p]; ro += rcnt[p];
+    }
+    return d.comm->alltoallv(send, soff, sb, recv, roff, rb, d.c.stream);
+}
+
+// one value per rank
+static int allgather_u64(DistCtx& d, const u64* mine, int words, std::vector<u64>& all) {
+    all.assign(size_t(d.P) * words, 0);
+    return d.comm->allgather_host(mine, all.data(), sizeof(u64) * words);
+}
+
+template <class K, class F>
+static int bucket_partition(DistCtx& d, const K* kin, const u32* vin, u32 vbase, u64 m, F f, K* kout, u32* vout, u64* cnt_out) {
+    cudaStream_t st = d.c.stream;
+    TDC_CUDA(cudaMemsetAsync(d.d_counts, 0, sizeof(ull) * 2 * DIST_MAX_RANKS, st));
+    if (m) {
+        const u32 grid = u32(std::min<u64>(u64(d.c.sm_count) * 8, div_up(m, BP_THREADS)));
+        auto bucket_count = bucket_count_kernel<K, F>;
+        TDC_LAUNCH(bucket_count, grid, BP_THREADS, 0, st, kin, m, f, d.P, d.d_counts);
+        TDC_KCHECK();
+    }
+    TDC_CUDA(cudaMemcpyAsync(d.h_counts, d.d_counts, sizeof(ull) * d.P, cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    ull run = 0;
+    for (int p = 0; p < d.P; p++) {
+        cnt_out[p] = d.h_counts[p];
+        d.h_counts[DIST_MAX_RANKS + p] = run;
+        run += d.h_counts[p];
+    }
+    TDC_CUDA(cudaMemcpyAsync(d.d_counts + DIST_MAX_RANKS, d.h_counts + DIST_MAX_RANKS, sizeof(ull) * d.P, cudaMemcpyHostToDevice, st));
+    if (m) {
+        auto bucket_scatter = bucket_scatter_kernel<K, F>;
+        TDC_LAUNCH(bucket_scatter, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, d.P, d.d_counts + DIST_MAX_RANKS, kout, vout);
+        prof_add_bytes("bucket_scatter", double(m) * 2 * (sizeof(K) + 4));
+        TDC_KCHECK();
+    }
+    TDC_CUDA(cudaStreamSynchronize(st));  // h_counts is reused by the next call
+    return 0;
+}
+
+// dst_shard[idx - owner*block] = val on the owner of idx.  bufs: six u32 buffers of d.cap elements.
+static int dist_scatter(DistCtx& d, const u32* idx, const u32* val, u64 m, u32* dst_shard, u32* bufs[6]) {
+    OwnerFn f;
+    f.block = d.block;
+    u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
+    TDC_TRY((bucket_partition<u32, OwnerFn>(d, idx, val, 0, m, f, bufs[0], bufs[1], scnt)));
+    TDC_TRY(exchange_matrix(d, scnt, d.xchg));
+    u64 R = 0;
+    for (int p = 0; p < d.P; p++) { rcnt[p] = d.xchg[size_t(p) * d.P + d.rank]; R += rcnt[p]; }
+    if (R > d.cap) { set_error("dist_scatter: %llu updates exceed the shard capacity", (unsigned long long)R); return TDCGPU_ERR_INTERNAL; }
+    TDC_TRY(a2a_elems(d, bufs[0], scnt, bufs[2], rcnt, 4));
+    TDC_TRY(a2a_elems(d, bufs[1], scnt, bufs[3], rcnt, 4));
+    u32* si[2] = {bufs[2], bufs[4]};
+    u32* sv[2] = {bufs[3], bufs[5]};
+    TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si, sv, R, dst_shard, d.pos_cnt, R == d.pos_cnt));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// suffix array + ISA (+ key-seeded LCP)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool FIRST>
+static int dist_rerank(DistCtx& d, const u64* keys, const u32* vals, const u32* pos_in, u64 m, u32* agg_lasthead, ull* agg_cnt,
+                       u32* rank_idx, u32* rank_val, u32* pos_out, u32* idx_out, u32* gid_out, u32* lcp_out, PackParams pp,
+                       u64* m_out, u64* g_out) {
+    Ctx& c = d.c;
+    *m_out = 0;
+    *g_out = 0;
+    if (m == 0) return 0;
+    const u32 ntiles = u32(div_up(m, RR_TILE));
+    auto rerank_reduce = rerank_reduce_kernel<u64>;
+    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt);
+    TDC_LAUNCH(rerank_scan_kernel, 1, 1024, 0, c.stream, agg_lasthead, agg_cnt, ntiles, c.d_scalars);
+    auto rerank_apply = rerank_apply_kernel<u64, FIRST>;
+    TDC_LAUNCH(rerank_apply, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, d.d_sa, rank_idx,
+               rank_val, pos_out, idx_out, gid_out, lcp_out, pp, u32(d.slot_lo));
+    TDC_KCHECK();
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    *m_out = c.h_scalars[0];
+    *g_out = c.h_scalars[1];
+    return 0;
+}
+
+static int dist_build_sa(DistCtx& d) {
+    Ctx& c = d.c;
+    const u64 n = d.n, cap = d.cap;
+    const int P = d.P;
+    cudaStream_t st = c.stream;
+    c.sa_rounds = 0;
+    c.sa_active_sum = 0;
+    c.sortws.stat_passes = 0;
+    c.sortws.stat_elems = 0;
+    // ---- alphabet (every rank reads the whole replicated text: identical key layout everywhere) ----
+    u32* d_hist = c.d_scalars + 16;
+    TDC_CUDA(cudaMemsetAsync(d_hist, 0, 256 * sizeof(u32), st));
+    {
+        const u32 grid = u32(std::min<u64>(u64(c.sm_count) * 8, div_up(div_up(n, 16), 256)));
+        TDC_LAUNCH(byte_histogram_kernel, grid, 256, 0, st, c.d_text, n, d_hist);
+        TDC_KCHECK();
+    }
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 16, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    const u32* hist = c.h_scalars + 16;
+    if (hist[0] != 1) {
+        set_error("text must contain exactly one 0 byte, at its end (found %u)", hist[0]);
+        return TDCGPU_ERR_SENTINEL;
+    }
+    PackParams pp;
+    u32 sigbits;
+    choose_key_layout(hist, n, &pp, &sigbits);
+    uint8_t code_map[256];
+    u32 sigma = 1;
+    {
+        u32 next = pp.lenbits ? 0 : 1;
+        code_map[0] = 0;
+        for (int b = 1; b < 256; b++) {
+            code_map[b] = uint8_t(next);
+            if (hist[b]) { next++; sigma++; }
+        }
+    }
+    c.alphabet = sigma;
+    c.symbols_per_key = pp.k;
+
+    // ---- scratch ----
+    c.arena.reset();
+    u64* K[2] = {c.arena.take<u64>(cap), c.arena.take<u64>(cap)};
+    u32* V[2] = {c.arena.take<u32>(cap), c.arena.take<u32>(cap)};
+    u32* Q[2] = {c.arena.take<u32>(cap), c.arena.take<u32>(cap)};
+    u32* G = c.arena.take<u32>(cap);
+    u32* S[4] = {c.arena.take<u32>(cap), c.arena.take<u32>(cap), c.arena.take<u32>(cap), c.arena.take<u32>(cap)};
+    const u64 rr_tiles = div_up(cap, RR_TILE);
+    u32* agg_lasthead = c.arena.take<u32>(rr_tiles);
+    ull* agg_cnt = c.arena.take<ull>(rr_tiles);
+    uint8_t* d_code_map = c.arena.take<uint8_t>(256);
+    const u32 NS = 1024;  // samples per rank
+    u64* d_samples = c.arena.take<u64>(NS);
+    if (!K[0] || !K[1] || !V[0] || !V[1] || !Q[0] || !Q[1] || !G || !S[0] || !S[1] || !S[2] || !S[3] || !agg_lasthead ||
+        !agg_cnt || !d_code_map || !d_samples) {
+        set_error("dist suffix array: scratch arena too small");
+        return TDCGPU_ERR_NOMEM;
+    }
+    TDC_CUDA(cudaMemcpyAsync(d_code_map, code_map, 256, cudaMemcpyHostToDevice, st));
+
+    // ---- round 0: keys of my positions, splitters, exchange, local sort ----
+    if (d.pos_cnt) {
+        TDC_LAUNCH(pack_keys_kernel, u32(div_up(d.pos_cnt, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, K[0], d.pos_lo, d.pos_cnt);
+        TDC_KCHECK();
+    }
+    SplitterFn sf;
+    sf.nspl = P - 1;
+    for (int i = 0; i < DIST_MAX_RANKS - 1; i++) sf.spl[i] = ~u64(0);
+    if (P > 1) {
+        TDC_LAUNCH(sample_keys_kernel, u32(div_up(NS, 256)), 256, 0, st, K[0], d.pos_cnt, NS, d_samples);
+        TDC_KCHECK();
+        std::vector<u64> mine(NS), all(size_t(NS) * P);
+        TDC_CUDA(cudaMemcpyAsync(mine.data(), d_samples, sizeof(u64) * NS, cudaMemcpyDeviceToHost, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        TDC_TRY(d.comm->allgather_host(mine.data(), all.data(), sizeof(u64) * NS));
+        std::sort(all.begin(), all.end());
+        for (int i = 0; i + 1 < P; i++) sf.spl[i] = all[size_t(i + 1) * NS];
+    }
+    u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
+    TDC_TRY((bucket_partition<u64, SplitterFn>(d, K[0], nullptr, u32(d.pos_lo), d.pos_cnt, sf, K[1], V[1], scnt)));
+    TDC_TRY(exchange_matrix(d, scnt, d.xchg));
+    d.slot_cnts.assign(P, 0);
+    for (int r = 0; r < P; r++)
+        for (int p = 0; p < P; p++) d.slot_cnts[r] += d.xchg[size_t(p) * P + r];
+    d.slot_lo = 0;
+    for (int r = 0; r < P; r++) {
+        if (d.slot_cnts[r] > cap) {
+            set_error("dist suffix array: bucket of rank %d holds %llu suffixes, capacity %llu (skewed keys)", r,
+                      (unsigned long long)d.slot_cnts[r], (unsigned long long)cap);
+            return TDCGPU_ERR_NOMEM;
+        }
+        if (r < d.rank) d.slot_lo += d.slot_cnts[r];
+    }
+    d.slot_cnt = d.slot_cnts[d.rank];
+    for (int p = 0; p < P; p++) rcnt[p] = d.xchg[size_t(p) * P + d.rank];
+    TDC_TRY(a2a_elems(d, K[1], scnt, K[0], rcnt, 8));  // ALL-TO-ALL #1: keys ...
+    TDC_TRY(a2a_elems(d, V[1], scnt, V[0], rcnt, 4));  // ... and suffix ids
+    const u64 mr = d.slot_cnt;
+    int res = 0;
+    TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, K, V, mr, 0, int(sigbits), false, &res));
+    u64 m = 0, g = 0;
+    int pcur = 0;
+    TDC_TRY((dist_rerank<true>(d, K[res], V[res], nullptr, mr, agg_lasthead, agg_cnt, nullptr, reinterpret_cast<u32*>(K[res ^ 1]),
+                               Q[pcur], V[res ^ 1], G, d.d_lcp, pp, &m, &g)));
+    {
+        // ALL-TO-ALL #2: rank[suffix] = head slot, to the owner of the position
+        u32* bufs[6] = {S[0], S[1], S[2], S[3], reinterpret_cast<u32*>(K[res]), reinterpret_cast<u32*>(K[res]) + cap};
+        TDC_TRY(dist_scatter(d, V[res], reinterpret_cast<u32*>(K[res ^ 1]), mr, d.d_rank, bufs));
+    }
+    c.sa_rounds = 1;
+    c.sa_active_sum = mr;
+    c.sa_first_residue = m;
+
+    // ---- doubling rounds ----
+    const u32 rbits = bits_for_host(n - 1);
+    OwnerFn of;
+    of.block = d.block;
+    u64 h = pp.k;
+    while (true) {
+        u64 mine[1] = {m};
+        std::vector<u64> all;
+        TDC_TRY(allgather_u64(d, mine, 1, all));
+        u64 m_tot = 0;
+        for (u64 x : all) m_tot += x;
+        if (m_tot == 0) break;
+        if (h > 2 * n) { set_error("dist suffix array: doubling did not converge"); return TDCGPU_ERR_INTERNAL; }
+        u32* Vact = V[res ^ 1];
+        // rank[suffix + h] from its owner: request / reply
+        if (m) TDC_LAUNCH(add_offset_kernel, u32(div_up(m, 256)), 256, 0, st, Vact, m, u32(h), S[0]);
+        TDC_TRY((bucket_partition<u32, OwnerFn>(d, S[0], nullptr, 0u, m, of, S[1], S[2], scnt)));
+        TDC_TRY(exchange_matrix(d, scnt, d.xchg));
+        u64 R = 0;
+        for (int p = 0; p < P; p++) { rcnt[p] = d.xchg[size_t(p) * P + d.rank]; R += rcnt[p]; }
+        if (R > cap) { set_error("dist suffix array: request overflow"); return TDCGPU_ERR_INTERNAL; }
+        TDC_TRY(a2a_elems(d, S[1], scnt, S[3], rcnt, 4));
+        if (R) TDC_LAUNCH(gather_u32_kernel, u32(div_up(R, 256)), 256, 0, st, d.d_rank, S[3], R, S[0]);
+        TDC_TRY(a2a_elems(d, S[0], rcnt, S[1], scnt, 4));
+        if (m) {
+            TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256)), 256, 0, st, S[2], S[1], m, S[3]);
+            TDC_LAUNCH(build_keys_from_kernel, u32(div_up(m, 256)), 256, 0, st, G, S[3], m, rbits, K[0]);
+            TDC_KCHECK();
+        }
+        const int gbits = g > 1 ? int(bits_for_host(g - 1)) : 0;
+        u64* k2[2] = {K[0], K[1]};
+        u32* v2[2] = {V[res ^ 1], V[res]};
+        int r2 = 0;
+        TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, k2, v2, m, 0, int(rbits) + gbits, false, &r2));
+        c.sa_rounds++;
+        c.sa_active_sum += m;
+        u64 m_new = 0, g_new = 0;
+        u32* rank_idx = reinterpret_cast<u32*>(k2[r2 ^ 1]);
+        u32* rank_val = reinterpret_cast<u32*>(k2[r2 ^ 1]) + cap;
+        TDC_TRY((dist_rerank<false>(d, k2[r2], v2[r2], Q[pcur], m, agg_lasthead, agg_cnt, rank_idx, rank_val, Q[pcur ^ 1],
+                                    v2[r2 ^ 1], G, nullptr, pp, &m_new, &g_new)));
+        {
+            u32* bufs[6] = {S[0], S[1], S[2], S[3], reinterpret_cast<u32*>(k2[r2]), reinterpret_cast<u32*>(k2[r2]) + cap};
+            TDC_TRY(dist_scatter(d, rank_idx, rank_val, m, d.d_rank, bufs));
+        }
+        if (v2[r2 ^ 1] != V[res ^ 1]) res ^= 1;
+        pcur ^= 1;
+        m = m_new;
+        g = g_new;
+        h *= 2;
+    }
+    return 0;
+}
+
+static int dist_build_lcp(DistCtx& d) {
+    Ctx& c = d.c;
+    cudaStream_t st = c.stream;
+    const u64 mr = d.slot_cnt;
+    c.arena.reset();
+    u32* queue = c.arena.take<u32>(d.cap);
+    if (!queue) { set_error("dist lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+    u32* d_qlen = c.d_scalars + 0;
+    u32* d_max = c.d_scalars + 1;
+    TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
+    u64 mine[2] = {0, mr};
+    if (mr) {
+        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(mr, 256)), 256, 0, st, c.d_text, d.d_sa, mr, d.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
+        TDC_KCHECK();
+        TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 8, d.d_sa + (mr - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        mine[0] = c.h_scalars[8];
+    }
+    std::vector<u64> all;
+    TDC_TRY(allgather_u64(d, mine, 2, all));
+    if (mr && d.slot_lo > 0) {
+        int pr = d.rank - 1;
+        while (pr >= 0 && all[size_t(pr) * 2 + 1] == 0) pr--;
+        if (pr < 0) { set_error("dist lcp: inconsistent slot ranges"); return TDCGPU_ERR_INTERNAL; }
+        TDC_LAUNCH(lcp_boundary_kernel, 1, 32, 0, st, c.d_text, d.d_sa, u32(all[size_t(pr) * 2]), d.d_lcp, d_max);
+    }
+    if (mr) TDC_LAUNCH(lcp_direct_long_kernel, u32(c.sm_count * 4), 256, 0, st, c.d_text, d.d_sa, d.d_lcp, queue, d_qlen, d_max);
+    TDC_KCHECK();
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    u64 mx[1] = {c.h_scalars[1]};
+    TDC_TRY(allgather_u64(d, mx, 1, all));
+    c.max_lcp = 0;
+    for (u64 x : all) c.max_lcp = std::max<u32>(c.max_lcp, u32(x));
+    c.lcp_route = 1;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// factorisation
+// ---------------------------------------------------------------------------------------------------------------
+static int dist_factorize(DistCtx& d, u32 threshold) {
+    Ctx& c = d.c;
+    cudaStream_t st = c.stream;
+    const int P = d.P, rank = d.rank;
+    const u64 cap = d.cap, qcap = d.qcap;
+    const u32 mr = u32(d.slot_cnt);
+    c.num_factors = 0;
+    d.total_factors = 0;
+    c.flen_min = 0xffffffffu;
+    c.flen_max = 0;
+    c.arena.reset();
+    // ---- local min-tree ----
+    MinTree T;
+    T.a[0] = d.d_sa;
+    T.l[0] = d.d_lcp;
+    T.sz[0] = mr;
+    T.nlev = 1;
+    while (T.sz[T.nlev - 1] > 32) {
+        if (T.nlev >= MT_MAX_LEVELS) { set_error("min-tree too deep"); return TDCGPU_ERR_INTERNAL; }
+        const u32 szi = T.sz[T.nlev - 1], szo = u32(div_up(szi, 32));
+        u32* a = c.arena.take<u32>(szo);
+        u32* l = c.arena.take<u32>(szo);
+        if (!a || !l) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+        TDC_LAUNCH(mintree_level_kernel, u32(div_up(u64(szo) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
+        T.a[T.nlev] = a;
+        T.l[T.nlev] = l;
+        T.sz[T.nlev] = szo;
+        T.nlev++;
+    }
+    for (int i = T.nlev; i < MT_MAX_LEVELS; i++) { T.a[i] = nullptr; T.l[i] = nullptr; T.sz[i] = 0; }
+    TDC_KCHECK();
+
+    u32* W[8];  // lu, su, ld, sd, then four more work buffers
+    for (int i = 0; i < 8; i++) W[i] = c.arena.take<u32>(cap);
+    u32* lenside_t = c.arena.take<u32>(cap + 64);  // text order
+    u32* src_t = c.arena.take<u32>(cap + 64);
+    WalkQuery* qb[6];  // up A/B, down A/B, received up, received down
+    for (int i = 0; i < 6; i++) qb[i] = c.arena.take<WalkQuery>(qcap);
+    WalkAnswer* ab[3];  // answers up, answers down, received answers
+    for (int i = 0; i < 3; i++) ab[i] = c.arena.take<WalkAnswer>(qcap);
+    u32* d_cnt = c.d_scalars + 8;  // [4]
+    if (!W[7] || !lenside_t || !src_t || !qb[5] || !ab[2]) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+    u32 *lu = W[0], *su = W[1], *ld = W[2], *sd = W[3];
+
+    // ---- LPF per slot; walks leaving the shard are queued ----
+    TDC_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(u32), st));
+    if (mr) {
+        TDC_LAUNCH(lpf_dist_kernel, u32(div_up(u64(mr), LPFD_TILE)), LPFD_THREADS, 0, st, T, mr, threshold, lu, su, ld, sd, qb[0], qb[2], d_cnt, u32(qcap));
+        TDC_KCHECK();
+    }
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 8, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    u64 cu = c.h_scalars[8], cd = c.h_scalars[9];
+    int cur = 0;  // qb[cur] / qb[2 + cur] hold the queries to send
+    std::vector<u64> all;
+    for (int hop = 1; hop < P; hop++) {
+        u64 mine[2] = {cu, cd};
+        TDC_TRY(allgather_u64(d, mine, 2, all));
+        u64 outstanding = 0, worst = 0;
+        for (u64 x : all) { outstanding += x; worst = std::max(worst, x); }
+        if (worst > qcap) { set_error("dist lzss_lcp: %llu PSV/NSV walks leave a shard (capacity %llu)", (unsigned long long)worst, (unsigned long long)qcap); return TDCGPU_ERR_NOMEM; }
+        if (outstanding == 0) break;
+        // queries: up-queue to rank-1, down-queue to rank+1
+        u64 sc[DIST_MAX_RANKS] = {0}, rc[DIST_MAX_RANKS] = {0};
+        if (rank > 0) sc[rank - 1] = cu;
+        const u64 nru = rank + 1 < P ? all[size_t(rank + 1) * 2] : 0;
+        if (rank + 1 < P) rc[rank + 1] = nru;
+        TDC_TRY(a2a_elems(d, qb[cur], sc, qb[4], rc, sizeof(WalkQuery)));
+        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
+        if (rank + 1 < P) sc[rank + 1] = cd;
+        const u64 nrd = rank > 0 ? all[size_t(rank - 1) * 2 + 1] : 0;
+        if (rank > 0) rc[rank - 1] = nrd;
+        TDC_TRY(a2a_elems(d, qb[2 + cur], sc, qb[5], rc, sizeof(WalkQuery)));
+        // resolve against my tree
+        TDC_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(u32), st));
+        if (nru) {
+            auto resolve_up = resolve_queries_kernel<true>;
+            TDC_LAUNCH(resolve_up, u32(div_up(nru, 128)), 128, 0, st, T, mr, threshold, qb[4], u32(nru), ab[0], qb[cur ^ 1], d_cnt);
+        }
+        if (nrd) {
+            auto resolve_dn = resolve_queries_kernel<false>;
+            TDC_LAUNCH(resolve_dn, u32(div_up(nrd, 128)), 128, 0, st, T, mr, threshold, qb[5], u32(nrd), ab[1], qb[2 + (cur ^ 1)], d_cnt + 2);
+        }
+        TDC_KCHECK();
+        TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 8, d_cnt, 4 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        const u64 au = c.h_scalars[8], fu = c.h_scalars[9], ad = c.h_scalars[10], fd = c.h_scalars[11];
+        // answers straight back to the origin: up-queries seen at this hop came from rank + hop, down from rank - hop
+        u64 am[2] = {au, ad};
+        TDC_TRY(allgather_u64(d, am, 2, all));
+        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
+        if (rank + hop < P) sc[rank + hop] = au;
+        const u64 rau = rank - hop >= 0 ? all[size_t(rank - hop) * 2] : 0;
+        if (rank - hop >= 0) rc[rank - hop] = rau;
+        TDC_TRY(a2a_elems(d, ab[0], sc, ab[2], rc, sizeof(WalkAnswer)));
+        if (rau) TDC_LAUNCH(apply_answers_kernel, u32(div_up(rau, 256)), 256, 0, st, ab[2], u32(rau), lu, su);
+        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
+        if (rank - hop >= 0) sc[rank - hop] = ad;
+        const u64 rad = rank + hop < P ? all[size_t(rank + hop) * 2 + 1] : 0;
+        if (rank + hop < P) rc[rank + hop] = rad;
+        TDC_TRY(a2a_elems(d, ab[1], sc, ab[2], rc, sizeof(WalkAnswer)));
+        if (rad) TDC_LAUNCH(apply_answers_kernel, u32(div_up(rad, 256)), 256, 0, st, ab[2], u32(rad), ld, sd);
+        TDC_KCHECK();
+        cu = rank > 0 ? fu : 0;        // rank 0 has nobody above: what is still open has no PSV
+        cd = rank + 1 < P ? fd : 0;
+        cur ^= 1;
+    }
+    // ---- combine, then to text order through the position owners ----
+    u32 *lenside_r = W[4], *src_r = W[5];
+    if (mr) {
+        TDC_LAUNCH(lpf_combine_kernel, u32(div_up(u64(mr), 256)), 256, 0, st, lu, su, ld, sd, u64(mr), threshold, lenside_r, src_r);
+        TDC_KCHECK();
+    }
+    {
+        u32* bufs[6] = {W[0], W[1], W[2], W[3], W[6], W[7]};
+        TDC_TRY(dist_scatter(d, d.d_sa, lenside_r, mr, lenside_t, bufs));
+        TDC_TRY(dist_scatter(d, d.d_sa, src_r, mr, src_t, bufs));
+    }
+    // ---- greedy chain over my positions; the entry point comes from the previous rank ----
+    const u32 n_eff = u32(rank == P - 1 ? d.pos_cnt : d.pos_cnt + 1);  // positions < n_eff - 1 are chain nodes here
+    const u32 ntiles = u32(div_up(u64(n_eff), CH_TILE));
+    u32* exitp = W[0];
+    u32* entry = W[1];
+    u32* tile_cnt = W[2];
+    u32* region_exit = W[3];
+    u32* fmask = W[6];
+    u32 regions = 1, tiles_per_region = 1;
+    if (n_eff > 1) {
+        TDC_LAUNCH(chain_exit_kernel, ntiles, CH_THREADS, 0, st, lenside_t, n_eff, exitp);
+        TDC_LAUNCH(fill_u32_kernel, u32(div_up(u64(ntiles), 256)), 256, 0, st, entry, u64(ntiles), CH_NONE);
+        while (u64(regions) * regions * 2 < ntiles) regions *= 2;
+        tiles_per_region = u32(div_up(u64(ntiles), regions));
+        regions = u32(div_up(u64(ntiles), tiles_per_region));
+        TDC_LAUNCH(chain_entries_spec_kernel, u32(div_up(u64(regions), 128)), 128, 0, st, exitp, n_eff, tiles_per_region, regions, entry, region_exit);
+        TDC_CUDA(cudaMemsetAsync(fmask, 0, sizeof(u32) * u64(ntiles) * (CH_TILE / 32), st));
+        TDC_KCHECK();
+    }
+    u64 chain_pos = 0;  // global position where the chain enters the next rank's range
+    for (int r = 0; r < P; r++) {
+        u64 mine[1] = {chain_pos};
+        if (r == rank && n_eff > 1) {
+            // always run the stitcher: it also erases the speculative entries when the chain jumps over this range
+            const u64 first = chain_pos > d.pos_lo ? chain_pos - d.pos_lo : 0;
+            TDC_LAUNCH(chain_entries_stitch_kernel, 1, 32, 0, st, exitp, n_eff, tiles_per_region, entry, region_exit, u32(first), c.d_scalars + 12);
+            TDC_KCHECK();
+            TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 12, c.d_scalars + 12, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            TDC_CUDA(cudaStreamSynchronize(st));
+            mine[0] = d.pos_lo + c.h_scalars[12];
+        }
+        TDC_TRY(allgather_u64(d, mine, 1, all));
+        chain_pos = all[r];
+    }
+    u32* d_total = c.d_scalars + 0;
+    u32* d_minmax = c.d_scalars + 2;
+    u64 z = 0;
+    c.h_scalars[2] = 0xffffffffu;
+    c.h_scalars[3] = 0;
+    TDC_CUDA(cudaMemcpyAsync(d_minmax, c.h_scalars + 2, 2 * sizeof(u32), cudaMemcpyHostToDevice, st));
+    if (n_eff > 1) {
+        TDC_LAUNCH(chain_mark_kernel, u32(div_up(u64(ntiles), 128)), 128, 0, st, lenside_t, n_eff, ntiles, entry, fmask, tile_cnt);
+        TDC_LAUNCH(scan_counts_kernel, 1, 1024, 0, st, tile_cnt, ntiles, d_total);
+        TDC_KCHECK();
+        TDC_CUDA(cudaMemcpyAsync(c.h_scalars, d_total, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        z = c.h_scalars[0];
+        if (z > c.factors_cap) {
+            if (c.d_factors) TDC_CUDA(cudaFree(c.d_factors));
+            c.d_factors = nullptr;
+            c.factors_cap = 0;
+            const u64 fcap = z + z / 8 + 1024;
+            TDC_CUDA(cudaMalloc(&c.d_factors, fcap * sizeof(Factor)));
+            c.factors_cap = fcap;
+        }
+        if (z > 0) {
+            auto emit_factors = emit_factors_kernel<true>;
+            TDC_LAUNCH(emit_factors, ntiles, CH_TILE / 32, 0, st, T, (const u32*)nullptr, lenside_t, fmask, tile_cnt, threshold, c.d_factors, d_minmax, src_t, u32(d.pos_lo));
+            TDC_KCHECK();
+        }
+    }
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 2, d_minmax, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    u64 mine[3] = {z, c.h_scalars[2], c.h_scalars[3]};
+    TDC_TRY(allgather_u64(d, mine, 3, all));
+    c.num_factors = z;
+    for (int r = 0; r < P; r++) {
+        d.total_factors += all[size_t(r) * 3];
+        c.flen_min = std::min<u32>(c.flen_min, u32(all[size_t(r) * 3 + 1]));
+        c.flen_max = std::max<u32>(c.flen_max, u32(all[size_t(r) * 3 + 2]));
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------------------------
+static void dist_free_arrays(DistCtx& d) {
+    Ctx& c = d.c;
+    void* ps[] = {c.d_text, d.d_sa, d.d_rank, d.d_lcp, c.arena.base};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+    c.d_text = nullptr;
+    d.d_sa = d.d_rank = d.d_lcp = nullptr;
+    c.arena = Arena();
+    c.cap_n = 0;
+    d.cap = 0;
+    d.have = 0;
+}
+
+static int dist_ensure_capacity(DistCtx& d, u64 n) {
+    Ctx& c = d.c;
+    const u64 per = div_up(n, u64(d.P));
+    const u64 cap = per + per / 4 + (u64(1) << 20);  // 25 % head room for uneven buckets
+    if (n <= c.cap_n && cap <= d.cap) return 0;
+    dist_free_arrays(d);
+    d.qcap = std::min<u64>(cap, u64(1) << 24);
+    TDC_CUDA(cudaMalloc(&c.d_text, n + 1024 + 16));
+    TDC_CUDA(cudaMalloc(&d.d_sa, sizeof(u32) * cap));
+    TDC_CUDA(cudaMalloc(&d.d_rank, sizeof(u32) * cap));
+    TDC_CUDA(cudaMalloc(&d.d_lcp, sizeof(u32) * cap));
+    const size_t arena_bytes = size_t(64) * cap + cap / 4 + size_t(9 * 12) * d.qcap + (size_t(16) << 20);
+    TDC_CUDA(cudaMalloc(&c.arena.base, arena_bytes));
+    c.arena.cap = arena_bytes;
+    c.arena.off = 0;
+    TDC_TRY(sort_workspace_init(c.sortws, cap, c.sm_count));
+    c.cap_n = n;
+    d.cap = cap;
+    return 0;
+}
+
+}  // namespace tdc
+
+using namespace tdc;
+
+struct tdcgpu_dist {
+    DistCtx d;
+};
+
+static int dist_create_common(int device, Comm* comm, tdcgpu_dist* h) {
+    DistCtx& d = h->d;
+    Ctx& c = d.c;
+    d.comm = comm;
+    d.P = comm->nranks;
+    d.rank = comm->rank;
+    c.device = device;
+    TDC_CUDA(cudaMalloc(&d.d_counts, sizeof(ull) * 2 * DIST_MAX_RANKS));
+    TDC_CUDA(cudaMallocHost(&d.h_counts, sizeof(ull) * 64));
+    return 0;
+}
+
+#define DIST_GUARD(h)                                                          \
+    if (!(h)) { set_error("null context"); return TDCGPU_ERR_ARG; }            \
+    DistCtx& d = (h)->d;                                                       \
+    Ctx& c = d.c;                                                              \
+    (void)c;                                                                   \
+    if (cudaSetDevice(c.device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", c.device); return TDCGPU_ERR_CUDA; }
+
+static int dist_ctx_init(Ctx& c, int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("no CUDA device available (tdcgpu has no CPU fallback)");
+        return TDCGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (have %d)", device, ndev); return TDCGPU_ERR_ARG; }
+    TDC_CUDA(cudaSetDevice(device));
+    c.device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) c.sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMalloc(&c.d_scalars, 512 * sizeof(u32)) != cudaSuccess || cudaMallocHost(&c.h_scalars, 512 * sizeof(u32)) != cudaSuccess) {
+        set_error("context allocation failed");
+        return TDCGPU_ERR_CUDA;
+    }
+    return 0;
+}
+
+extern "C" {
+
+#ifdef TDC_CUSIM
+int tdcsim_dist_create(int rank, int nranks, tdcsim_allgather_fn ag, tdcsim_alltoallv_fn a2a, void* user, tdcgpu_dist** out) {
+    if (!out || nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks) { set_error("bad arguments"); return TDCGPU_ERR_ARG; }
+    tdcgpu_dist* h = new (std::nothrow) tdcgpu_dist();
+    if (!h) return TDCGPU_ERR_NOMEM;
+    int rc = dist_ctx_init(h->d.c, 0);
+    if (rc == 0) rc = dist_create_common(0, make_callback_comm(rank, nranks, ag, a2a, user), h);
+    if (rc < 0) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+#else
+int tdcgpu_dist_unique_id(uint8_t id[128]) {
+    if (!id) { set_error("null id"); return TDCGPU_ERR_ARG; }
+    return nccl_unique_id(id) < 0 ? TDCGPU_ERR_CUDA : 0;
+}
+
+int tdcgpu_dist_create(int device, int rank, int nranks, const uint8_t id[128], tdcgpu_dist** out) {
+    if (!out || nranks < 1 || nranks > DIST_MAX_RANKS || rank < 0 || rank >= nranks || (nranks > 1 && !id)) {
+        set_error("tdcgpu_dist_create: bad arguments (1 <= nranks <= %d)", DIST_MAX_RANKS);
+        return TDCGPU_ERR_ARG;
+    }
+    *out = nullptr;
+    tdcgpu_dist* h = new (std::nothrow) tdcgpu_dist();
+    if (!h) { set_error("out of host memory"); return TDCGPU_ERR_NOMEM; }
+    int rc = dist_ctx_init(h->d.c, device);
+    if (rc < 0) { delete h; return rc; }
+    Comm* comm = make_nccl_comm(rank, nranks, id, h->d.c.stream);
+    if (!comm) { delete h; return TDCGPU_ERR_CUDA; }
+    rc = dist_create_common(device, comm, h);
+    if (rc < 0) { delete comm; delete h; return rc; }
+    *out = h;
+    return 0;
+}
+#endif
+
+void tdcgpu_dist_destroy(tdcgpu_dist* h) {
+    if (!h) return;
+    DistCtx& d = h->d;
+    Ctx& c = d.c;
+    cudaSetDevice(c.device);
+    cudaStreamSynchronize(c.stream);
+    delete d.comm;
+    dist_free_arrays(d);
+    sort_workspace_free(c.sortws);
+    if (c.d_factors) cudaFree(c.d_factors);
+    if (c.d_scalars) cudaFree(c.d_scalars);
+    if (c.h_scalars) cudaFreeHost(c.h_scalars);
+    if (d.d_counts) cudaFree(d.d_counts);
+    if (d.h_counts) cudaFreeHost(d.h_counts);
+    for (auto& e : c.user_events)
+        if (e) cudaEventDestroy(e);
+    cudaStreamDestroy(c.stream);
+    delete h;
+}
+
+int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on_device) {
+    DIST_GUARD(h);
+    if (!text || n == 0) { set_error("empty text (the path always sees at least the sentinel)"); return TDCGPU_ERR_ARG; }
+    if (n >= (uint64_t(1) << 32) - 1) { set_error("n = %llu: indices are 32-bit", (unsigned long long)n); return TDCGPU_ERR_ARG; }
+    TDC_TRY(dist_ensure_capacity(d, n));
+    d.n = n;
+    c.n = n;
+    d.block = u32(div_up(n, u64(d.P)));
+    d.pos_lo = std::min<u64>(n, u64(d.rank) * d.block);
+    d.pos_cnt = std::min<u64>(n - d.pos_lo, d.block);
+    d.have = 0;
+    c.max_lcp = 0;
+    c.num_factors = 0;
+    c.phases.clear();
+    TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
+    TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_dist_build(tdcgpu_dist* h, uint32_t flags) {
+    DIST_GUARD(h);
+    if (d.n == 0) { set_error("no text loaded"); return TDCGPU_ERR_STATE; }
+    if (flags & ~(DS_SA | DS_ISA | DS_LCP)) { set_error("multi-GPU mode builds SA, ISA and LCP (flags 0x%x)", flags); return TDCGPU_ERR_ARG; }
+    c.phases.clear();
+    if (!(d.have & DS_SA)) {
+        PhaseTimer t(c, "Construct SA");
+        TDC_TRY(dist_build_sa(d));
+        d.have |= DS_SA | DS_ISA;
+    }
+    if ((flags & DS_LCP) && !(d.have & DS_LCP)) {
+        PhaseTimer t(c, "Construct LCP Array");
+        TDC_TRY(dist_build_lcp(d));
+        d.have |= DS_LCP;
+    }
+    return 0;
+}
+
+int tdcgpu_dist_shard_info(tdcgpu_dist* h, uint64_t out[4]) {
+    DIST_GUARD(h);
+    out[0] = d.slot_lo;
+    out[1] = d.slot_cnt;
+    out[2] = d.pos_lo;
+    out[3] = d.pos_cnt;
+    return 0;
+}
+
+int tdcgpu_dist_get(tdcgpu_dist* h, uint32_t which, void* dst, int to_device) {
+    DIST_GUARD(h);
+    if (!(d.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
+    const u32* src = which == DS_SA ? d.d_sa : which == DS_ISA ? d.d_rank : which == DS_LCP ? d.d_lcp : nullptr;
+    if (!src || !dst) { set_error("bad arguments"); return TDCGPU_ERR_ARG; }
+    const u64 cnt = which == DS_ISA ? d.pos_cnt : d.slot_cnt;
+    if (cnt) TDC_CUDA(cudaMemcpyAsync(dst, src, sizeof(u32) * cnt, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_dist_max_lcp(tdcgpu_dist* h, uint32_t* max_lcp) {
+    DIST_GUARD(h);
+    if (!(d.have & DS_LCP)) { set_error("LCP has not been built"); return TDCGPU_ERR_STATE; }
+    if (max_lcp) *max_lcp = c.max_lcp;
+    return 0;
+}
+
+int tdcgpu_dist_lzss_lcp_factorize(tdcgpu_dist* h, uint32_t threshold, uint64_t* local_count, uint64_t* total_count,
+                                   uint32_t* min_len, uint32_t* max_len) {
+    DIST_GUARD(h);
+    if (threshold < 1) { set_error("lzss_lcp: threshold must be >= 1"); return TDCGPU_ERR_ARG; }
+    TDC_TRY(tdcgpu_dist_build(h, DS_SA | DS_ISA | DS_LCP));
+    if (c.max_lcp >= (1u << 31)) { set_error("multi-GPU lzss_lcp: common prefixes of 2^31 bytes or more are not supported"); return TDCGPU_ERR_ARG; }
+    {
+        PhaseTimer t(c, "Factorize");
+        TDC_TRY(dist_factorize(d, threshold));
+    }
+    if (local_count) *local_count = c.num_factors;
+    if (total_count) *total_count = d.total_factors;
+    if (min_len) *min_len = c.flen_min;
+    if (max_len) *max_len = c.flen_max;
+    return 0;
+}
+
+int tdcgpu_dist_get_factors(tdcgpu_dist* h, tdcgpu_factor* dst, uint64_t cap, int to_device) {
+    DIST_GUARD(h);
+    if (c.num_factors > cap) { set_error("factor buffer too small"); return TDCGPU_ERR_ARG; }
+    if (c.num_factors == 0) return 0;
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_dist_sync(tdcgpu_dist* h) {
+    DIST_GUARD(h);
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_dist_event_record(tdcgpu_dist* h, int slot) {
+    DIST_GUARD(h);
+    if (slot < 0 || slot >= 8) { set_error("event slot out of range"); return TDCGPU_ERR_ARG; }
+    if (!c.user_events[slot]) TDC_CUDA(cudaEventCreate(&c.user_events[slot]));
+    TDC_CUDA(cudaEventRecord(c.user_events[slot], c.stream));
+    return 0;
+}
+
+int tdcgpu_dist_event_elapsed_ms(tdcgpu_dist* h, int slot_a, int slot_b, float* ms) {
+    DIST_GUARD(h);
+    if (slot_a < 0 || slot_a >= 8 || slot_b < 0 || slot_b >= 8 || !c.user_events[slot_a] || !c.user_events[slot_b] || !ms) {
+        set_error("bad event slots");
+        return TDCGPU_ERR_ARG;
+    }
+    TDC_CUDA(cudaEventSynchronize(c.user_events[slot_b]));
+    TDC_CUDA(cudaEventElapsedTime(ms, c.user_events[slot_a], c.user_events[slot_b]));
+    return 0;
+}
+
+int tdcgpu_dist_stats(tdcgpu_dist* h, uint64_t out[8]) {
+    DIST_GUARD(h);
+    out[0] = c.sa_rounds;
+    out[1] = c.sa_active_sum;
+    out[2] = c.sortws.stat_passes;
+    out[3] = c.sortws.stat_elems;
+    out[4] = c.alphabet;
+    out[5] = c.symbols_per_key;
+    out[6] = d.cap;
+    out[7] = d.total_factors;
+    return 0;
+}
+
+int tdcgpu_dist_phase_count(tdcgpu_dist* h) { return h ? int(h->d.c.phases.size()) : 0; }
+const char* tdcgpu_dist_phase_name(tdcgpu_dist* h, int i) {
+    if (!h || i < 0 || i >= int(h->d.c.phases.size())) return nullptr;
+    return h->d.c.phases[i].name.c_str();
+}
+float tdcgpu_dist_phase_ms(tdcgpu_dist* h, int i) {
+    if (!h || i < 0 || i >= int(h->d.c.phases.size())) return -1.f;
+    return h->d.c.phases[i].ms;
+}
+
+}  // extern "C"

@@ -86,7 +86,7 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         u32* region_exit = c.arena.take<u32>(regions);
         if (!region_exit) { set_error("lzss_lcp: scratch arena too small"); return -2; }
         TDC_LAUNCH(chain_entries_spec_kernel, u32(div_up(u64(regions), 128)), 128, 0, st, exitp, n, tiles_per_region, regions, entry, region_exit);
-        TDC_LAUNCH(chain_entries_stitch_kernel, 1, 32, 0, st, exitp, n, tiles_per_region, entry, region_exit);
+        TDC_LAUNCH(chain_entries_stitch_kernel, 1, 32, 0, st, exitp, n, tiles_per_region, entry, region_exit, 0u, (u32*)nullptr);
     }
     TDC_CUDA(cudaMemsetAsync(fmask, 0, sizeof(u32) * u64(ntiles) * (CH_TILE / 32), st));
     TDC_LAUNCH(chain_mark_kernel, u32(div_up(u64(ntiles), 128)), 128, 0, st, lenside, n, ntiles, entry, fmask, tile_cnt);
@@ -110,7 +110,9 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
     }
     // ---- 4. emit ----
     if (z > 0) {
-        TDC_LAUNCH(emit_factors_kernel, ntiles, CH_TILE / 32, 0, st, T, c.d_isa, lenside, fmask, tile_cnt, threshold, c.d_factors, d_minmax);
+        auto emit_factors = emit_factors_kernel<false>;
+        TDC_LAUNCH(emit_factors, ntiles, CH_TILE / 32, 0, st, T, c.d_isa, lenside, fmask, tile_cnt, threshold, c.d_factors, d_minmax,
+                   (const u32*)nullptr, 0u);
         TDC_KCHECK();
     }
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 2, d_minmax, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));

@@ -249,9 +249,11 @@ chain_entries_spec_kernel(const u32* __restrict__ exitp, u32 n, u32 tiles_per_re
 }
 
 static __global__ void chain_entries_stitch_kernel(const u32* __restrict__ exitp, u32 n, u32 tiles_per_region,
-                                            u32* __restrict__ entry, const u32* __restrict__ region_exit) {
+                                            u32* __restrict__ entry, const u32* __restrict__ region_exit, u32 first,
+                                            u32* __restrict__ last_out) {
+    // first: where the chain enters this position range (0 on a single GPU); *last_out: where it leaves it
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
-    u32 x = 0, clear_from = 0;
+    u32 x = first, clear_from = 0;
     while (x < n - 1) {
         const u32 t = x / CH_TILE;
         for (u32 tt = clear_from; tt < t; tt++) entry[tt] = CH_NONE;
@@ -267,6 +269,7 @@ static __global__ void chain_entries_stitch_kernel(const u32* __restrict__ exitp
     }
     const u32 ntiles = (n + CH_TILE - 1) / CH_TILE;
     for (u32 tt = clear_from; tt < ntiles; tt++) entry[tt] = CH_NONE;
+    if (last_out) *last_out = x;
 }
 
 // Mark the visited positions of every tile: with the tile entries known the tiles are independent, so ONE THREAD walks
@@ -312,10 +315,14 @@ static __global__ void __launch_bounds__(1024) scan_counts_kernel(u32* __restric
     if (threadIdx.x == 0) *total = carry;
 }
 
-// emit (pos, src, len) in position order; one thread per 32-bit mask word
+// emit (pos, src, len) in position order; one thread per 32-bit mask word.  HAVE_SRC: the source positions were
+// carried along (src_arr, sharded multi-GPU path) instead of being recovered by a walk; pos_base = first text position
+// of this rank's range.
+template <bool HAVE_SRC>
 static __global__ void __launch_bounds__(CH_TILE / 32)
 emit_factors_kernel(MinTree T, const u32* __restrict__ isa, const u32* __restrict__ lenside, const u32* __restrict__ fmask,
-                    const u32* __restrict__ tile_off, u32 thr, Factor* __restrict__ out, u32* __restrict__ minmax) {
+                    const u32* __restrict__ tile_off, u32 thr, Factor* __restrict__ out, u32* __restrict__ minmax,
+                    const u32* __restrict__ src_arr, u32 pos_base) {
     __shared__ u32 scratch[33];
     __shared__ u32 s_min[CH_TILE / 32 / 32], s_max[CH_TILE / 32 / 32];
     const u32 base = blockIdx.x * CH_TILE;
@@ -329,17 +336,21 @@ emit_factors_kernel(MinTree T, const u32* __restrict__ isa, const u32* __restric
         const u32 i = base + threadIdx.x * 32 + b;
         const u32 ls = lenside[i];
         const u32 len = ls >> 1;
-        const u32 p = isa[i];
-        u32 q = 0, m = 0xffffffffu;
-        if (ls & 1u) {
-            walk_nsv(T, p, i, thr, m, q);
-        } else {
-            m = T.l[0][p];
-            walk_psv(T, p, i, thr, m, q);
-        }
         Factor f;
-        f.pos = i;
-        f.src = T.a[0][q];
+        if (HAVE_SRC) {
+            f.src = src_arr[i];
+        } else {
+            const u32 p = isa[i];
+            u32 q = 0, m = 0xffffffffu;
+            if (ls & 1u) {
+                walk_nsv(T, p, i, thr, m, q);
+            } else {
+                m = T.l[0][p];
+                walk_psv(T, p, i, thr, m, q);
+            }
+            f.src = T.a[0][q];
+        }
+        f.pos = pos_base + i;
         f.len = len;
         out[o++] = f;
         mn = min(mn, len);

@@ -54,12 +54,13 @@ static const int PK_HALO = 64;  // k <= 64 (b >= 1)
 
 static __global__ void __launch_bounds__(PK_THREADS)
 pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restrict__ code_map, PackParams pp,
-                 u64* __restrict__ keys) {
+                 u64* __restrict__ keys, u64 pos0, u64 cnt) {  // keys[j] = key of suffix pos0 + j, j < cnt
     __shared__ uint8_t codes[PK_TILE + PK_HALO];
     __shared__ uint8_t cmap[256];
     cmap[threadIdx.x] = code_map[threadIdx.x];
     __syncthreads();
-    const u64 base = u64(blockIdx.x) * PK_TILE;
+    const u64 base = pos0 + u64(blockIdx.x) * PK_TILE;
+    const u64 end = pos0 + cnt;
     for (u32 j = threadIdx.x; j < PK_TILE + PK_HALO; j += PK_THREADS) {
         const u64 p = base + j;
         codes[j] = p < n ? cmap[text[p]] : uint8_t(0);
@@ -82,15 +83,15 @@ pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restr
         out[q] = key;
         packed = ((packed << pp.b) & mask) | codes[l0 + q + pp.k];  // roll one symbol
     }
-    if (base + l0 + PK_IPT <= n) {
-        ulonglong2* o2 = reinterpret_cast<ulonglong2*>(keys + base + l0);
+    if (base + l0 + PK_IPT <= end) {
+        ulonglong2* o2 = reinterpret_cast<ulonglong2*>(keys + (base - pos0) + l0);
 #pragma unroll
         for (int q = 0; q < PK_IPT / 2; q++) o2[q] = make_ulonglong2(out[2 * q], out[2 * q + 1]);
     } else {
 #pragma unroll
         for (int q = 0; q < PK_IPT; q++) {
             const u64 p = base + l0 + q;
-            if (p < n) keys[p] = out[q];
+            if (p < end) keys[p - pos0] = out[q];
         }
     }
 }
@@ -239,7 +240,8 @@ static __global__ void __launch_bounds__(RR_THREADS)
 rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, const u32* __restrict__ pos_in, u64 m,
                     const u32* __restrict__ pre_lasthead, const ull* __restrict__ pre_cnt, u32* __restrict__ sa,
                     u32* __restrict__ rank_idx, u32* __restrict__ rank_val, u32* __restrict__ pos_out,
-                    u32* __restrict__ idx_out, u32* __restrict__ gid_out, u32* __restrict__ lcp_out, PackParams pp) {
+                    u32* __restrict__ idx_out, u32* __restrict__ gid_out, u32* __restrict__ lcp_out, PackParams pp,
+                    u32 slot_base) {  // slot_base: global SA slot of this rank's first slot (0 on a single GPU)
     __shared__ ull scratch_s[33];
     __shared__ u32 scratch_m[33];
     const u64 t0 = u64(blockIdx.x) * RR_TILE + u64(threadIdx.x) * RR_IPT;
@@ -284,8 +286,8 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
         const bool h = (hb >> q) & 1u, ns = (nb >> q) & 1u;
         if (h) cur_head = u32(t) + 1u;
         const u32 hidx = cur_head - 1u;
-        const u32 slot = FIRST ? u32(t) : pos_in[t];
-        const u32 headslot = FIRST ? hidx : pos_in[hidx];
+        const u32 slot = FIRST ? slot_base + u32(t) : pos_in[t];
+        const u32 headslot = FIRST ? slot_base + hidx : pos_in[hidx];
         const u32 sfx = sfxv[q];
         headv[q] = headslot;  // rank[sfx] = headslot, applied by the partitioned scatter that follows
         if (FIRST) {
@@ -302,7 +304,7 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
             gid_out[o] = u32(run_s >> 32) - 1u;
             run_s += 1;
         } else if (!FIRST) {
-            sa[slot] = sfx;  // singleton group: final position
+            sa[slot - slot_base] = sfx;  // singleton group: final position
         }
     }
     if (FIRST) {

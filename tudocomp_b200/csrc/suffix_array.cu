@@ -63,7 +63,7 @@ static int rerank(Ctx& c, const K* keys, const u32* vals, const u32* pos_in, u64
     TDC_LAUNCH(rerank_scan_kernel, 1, 1024, 0, c.stream, agg_lasthead, agg_cnt, ntiles, c.d_scalars);
     auto rerank_apply = rerank_apply_kernel<K, FIRST>;
     TDC_LAUNCH(rerank_apply, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, c.d_sa, sc_idx[0],
-               sc_val[0], pos_out, idx_out, gid_out, lcp_out, pp);
+               sc_val[0], pos_out, idx_out, gid_out, lcp_out, pp, 0u);
     prof_add_bytes("rerank_apply", double(m) * (sizeof(K) + 4 + (FIRST ? 8 + (lcp_out ? 4 : 0) : 12)));
     TDC_KCHECK();
     // first round: the pairs are (vals[t], head slot) and vals is a permutation of 0..n-1
@@ -141,7 +141,7 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     TDC_CUDA(cudaMemcpyAsync(d_code_map, code_map, 256, cudaMemcpyHostToDevice, st));
 
     // ---- initial sort by k-symbol prefix ----
-    TDC_LAUNCH(pack_keys_kernel, u32(div_up(n, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, keys[0]);
+    TDC_LAUNCH(pack_keys_kernel, u32(div_up(n, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, keys[0], u64(0), n);
     prof_add_bytes("pack_keys_kernel", double(n) * 9);
     TDC_KCHECK();
     int res = 0;
