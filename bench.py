@@ -27,6 +27,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the image sets NCCL_DEBUG=VERSION, which makes NCCL print a banner on STDOUT next to the one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 METRIC = "input MB/s for SA+LCP+lzss_lcp factorization"
 THRESHOLD = 3

@@ -105,74 +105,222 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
     return WALK_FOUND;
 }
 
-// Per rank: longest previous factor length and winning side.  A tile of LPF_TILE consecutive ranks of SA and LCP is
-// staged in shared memory together with two local min-tree levels; almost every PSV/NSV walk ends inside its tile at
-// shared-memory latency (a walk is a chain of dependent loads), the few that leave it continue in the global tree.
-// Output in rank order; the partitioned scatter that follows moves it to text order (index side = SA itself).
+// ---------------------------------------------------------------------------------------------------------------
+// Per rank: longest previous factor length and winning side (all nearest smaller values of SA + LCP range minima).
+//
+// A tile of LPF_TILE consecutive ranks is staged in shared memory and solved in three steps:
+//  1. ONE THREAD per chunk of 32 ranks runs the sequential nearest-smaller-value recurrence ("pop" = follow the pointer
+//     of the current candidate, carrying the LCP minimum of the skipped range): amortised O(1) per rank, whatever the
+//     distribution of distances.  Written as a flat, predicated loop (one candidate per iteration).
+//     Unresolved afterwards: the chunk's prefix minima (PSV side) and suffix minima (NSV side).
+//  2. a binary merge tree over the chunks: the suffix minima of the left node and the prefix minima of the right node
+//     are two lists of falling values, linked by the very PSV/NSV pointers already computed; one two-pointer merge
+//     resolves the PSV of the right list and the NSV of the left list at once (O(list length) per merge), the
+//     leftovers form the lists of the merged node.  log2(chunks) levels, half of the threads each time.
+//  3. what is still unresolved (the tile's own prefix/suffix minima, ~ln(LPF_TILE) per side) walks the global min-tree.
+// Output in rank order; the partitioned scatter that follows moves it to text order.
+// (History, profiles/r1d_ncu_summary.md: one independent linear walk per rank spends ~50 instructions per rank on
+// divergence; per-chunk recurrences + tree walks for the leftovers spend even more on the walks.)
+// ---------------------------------------------------------------------------------------------------------------
 #ifdef TDC_CUSIM
-static const int LPF_THREADS = 128;  // small tiles so that the CPU tests leave their tile often
-static const int LPF_TILE = 1024;
+static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
-static const int LPF_THREADS = 512;
-static const int LPF_TILE = 4096;
+static const int LPF_THREADS = 128;
 #endif
-static const int LPF_L1 = LPF_TILE / 32;  // 128
-static const int LPF_L2 = LPF_L1 / 32;    // 4
+static const int LPF_TILE = LPF_THREADS * 32;
+static const u32 LPF_INF = 0xffffffffu;
+static const u32 LPF_NONE = 0xffffffffu;
 
-// the tile's three levels lie back to back in shared memory: no pointer table, no dynamic indexing
-struct TileTree {
-    const u32* sA;
-    const u32* sL;
-    __device__ __forceinline__ static u32 off(int lvl) { return lvl == 0 ? 0u : (lvl == 1 ? u32(LPF_TILE) : u32(LPF_TILE + LPF_L1)); }
-    __device__ __forceinline__ u32 A(int lvl, u32 i) const { return sA[off(lvl) + i]; }
-    __device__ __forceinline__ u32 L(int lvl, u32 i) const { return sL[off(lvl) + i]; }
-    __device__ __forceinline__ u32 size(int lvl) const { return lvl == 0 ? u32(LPF_TILE) : (lvl == 1 ? u32(LPF_L1) : u32(LPF_L2)); }
-    __device__ __forceinline__ int levels() const { return 3; }
-};
+// XOR swizzle: a thread walking its own chunk (index t*32 + s) and a warp reading 32 consecutive ranks both touch 32
+// different banks
+__device__ __forceinline__ u32 lpf_phys(u32 i) { return i ^ ((i >> 5) & 31u); }
+
+static inline size_t lpf_smem_bytes() { return sizeof(u32) * 3 * LPF_TILE + sizeof(unsigned short) * 2 * LPF_TILE + sizeof(u32) * (LPF_THREADS + 2 * LPF_TILE / 16 + 8); }
 
 static __global__ void __launch_bounds__(LPF_THREADS)
 lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
-    __shared__ u32 sA[LPF_TILE + LPF_L1 + LPF_L2];
-    __shared__ u32 sL[LPF_TILE + LPF_L1 + LPF_L2];
+    TDC_DYN_SMEM(smem_raw);
+    u32* sA = reinterpret_cast<u32*>(smem_raw);            // SA values
+    u32* sU = sA + LPF_TILE;                                // LCP values, overwritten in place by l_up
+    u32* sD = sU + LPF_TILE;                                // l_dn
+    unsigned short* sPp = reinterpret_cast<unsigned short*>(sD + LPF_TILE);  // PSV pointer (tile-local index + 1, 0 = open)
+    unsigned short* sPn = sPp + LPF_TILE;                                    // NSV pointer
+    u32* sNL = reinterpret_cast<u32*>(sPn + LPF_TILE);     // [LPF_THREADS] LCP minimum of the node starting at chunk t
+    u32* sQ = sNL + LPF_THREADS;                            // [2 * LPF_TILE / 16] open (index << 1 | side) after the merges
+    u32* sQn = sQ + 2 * LPF_TILE / 16;                      // [1] queue length
     const u32 base = blockIdx.x * LPF_TILE;
     for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
         const u32 i = base + j;
-        sA[j] = i < n ? T.a[0][i] : 0xffffffffu;
-        sL[j] = i < n ? T.l[0][i] : 0xffffffffu;
+        sA[lpf_phys(j)] = i < n ? T.a[0][i] : LPF_INF;
+        sU[lpf_phys(j)] = i < n ? T.l[0][i] : LPF_INF;
+    }
+    if (threadIdx.x == 0) *sQn = 0;
+    __syncthreads();
+    const u32 cs = threadIdx.x * 32u;  // this thread's chunk [cs, cs + 32)
+    const u32 sw = threadIdx.x & 31u;  // swizzle of the chunk: phys(cs + s) = cs + (s ^ sw)
+#define LPF_AT(arr, s) arr[cs + ((s) ^ sw)]
+
+    // ---- 1a. NSV inside the chunk, right to left (reads the raw LCP values) ----
+    {
+        int s = 31;
+        u32 v = LPF_AT(sA, 31u), m = LPF_INF, j = 32;
+        while (true) {
+            const bool valid = j < 32;
+            const u32 jj = valid ? j : 31u;
+            const u32 aj = LPF_AT(sA, jj), lj = LPF_AT(sU, jj), dj = LPF_AT(sD, jj), nj = LPF_AT(sPn, jj);
+            if (valid) m = min(m, lj);  // LCP[j] lies inside the range whether or not j is the answer
+            const bool found = valid && aj < v;
+            if (!valid || found) {
+                LPF_AT(sD, u32(s)) = m;
+                LPF_AT(sPn, u32(s)) = (unsigned short)(found ? cs + j + 1 : 0);
+                if (--s < 0) break;
+                v = LPF_AT(sA, u32(s));
+                m = LPF_INF;
+                j = u32(s) + 1;
+            } else {
+                m = min(m, dj);
+                j = nj ? nj - 1 - cs : 32u;
+            }
+        }
+    }
+    // ---- 1b. PSV inside the chunk, left to right; l_up replaces the LCP value in place ----
+    {
+        u32 s = 0, v = LPF_AT(sA, 0u), m = LPF_AT(sU, 0u), lmin = m;
+        int j = -1;
+        while (true) {
+            const bool valid = j >= 0;
+            const u32 jj = valid ? u32(j) : 0u;
+            const u32 aj = LPF_AT(sA, jj), uj = LPF_AT(sU, jj), pj = LPF_AT(sPp, jj);
+            const bool found = valid && aj < v;
+            if (!valid || found) {
+                LPF_AT(sU, s) = m;
+                LPF_AT(sPp, s) = (unsigned short)(found ? cs + u32(j) + 1 : 0);
+                if (++s == 32) break;
+                v = LPF_AT(sA, s);
+                m = LPF_AT(sU, s);  // still the raw LCP value
+                lmin = min(lmin, m);
+                j = int(s) - 1;
+            } else {
+                m = min(m, uj);
+                j = pj ? int(pj - 1 - cs) : -1;
+            }
+        }
+        sNL[threadIdx.x] = lmin;
     }
     __syncthreads();
-    for (u32 g = warp_id(); g < LPF_L1; g += LPF_THREADS / 32) {
-        const u32 av = warp_min(sA[g * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[g * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPF_TILE + g] = av; sL[LPF_TILE + g] = lv; }
+    // ---- 2. merge tree ----
+    for (u32 half = 1; half < u32(LPF_THREADS); half <<= 1) {  // half = chunks per child node
+        if (threadIdx.x * 2 * half < u32(LPF_THREADS)) {
+            const u32 ca = threadIdx.x * 2 * half, cb = ca + half;  // first chunks of the left / right child
+            u32 a = cb * 32 - 1, b = cb * 32;                        // heads: last rank of A, first rank of B
+            u32 va = sA[lpf_phys(a)], vb = sA[lpf_phys(b)];
+            while (a != LPF_NONE && b != LPF_NONE) {
+                const u32 pa = lpf_phys(a), pb = lpf_phys(b);
+                if (va > vb) {  // NSV(a) = b
+                    sPn[pa] = (unsigned short)(b + 1);
+                    sD[pa] = min(sD[pa], sU[pb]);
+                    const u32 nx = sPp[pa];
+                    a = nx ? nx - 1 : LPF_NONE;
+                    if (a != LPF_NONE) va = sA[lpf_phys(a)];
+                } else {        // PSV(b) = a
+                    sPp[pb] = (unsigned short)(a + 1);
+                    sU[pb] = min(sU[pb], sD[pa]);
+                    const u32 nx = sPn[pb];
+                    b = nx ? nx - 1 : LPF_NONE;
+                    if (b != LPF_NONE) vb = sA[lpf_phys(b)];
+                }
+            }
+            const u32 la = sNL[ca], lb = sNL[cb];
+            while (a != LPF_NONE) {  // smaller than everything in B: still open to the right
+                const u32 pa = lpf_phys(a);
+                sD[pa] = min(sD[pa], lb);
+                const u32 nx = sPp[pa];
+                a = nx ? nx - 1 : LPF_NONE;
+            }
+            while (b != LPF_NONE) {  // smaller than everything in A: still open to the left
+                const u32 pb = lpf_phys(b);
+                sU[pb] = min(sU[pb], la);
+                const u32 nx = sPn[pb];
+                b = nx ? nx - 1 : LPF_NONE;
+            }
+            sNL[ca] = min(la, lb);
+        }
+        __syncthreads();
+    }
+    // ---- 3. the tile's own prefix / suffix minima continue in the global tree ----
+    {
+        u32 open_up = 0, open_dn = 0;
+#pragma unroll 4
+        for (u32 s = 0; s < 32; s++) {
+            if (LPF_AT(sPp, s) == 0) open_up |= 1u << s;
+            if (LPF_AT(sPn, s) == 0) open_dn |= 1u << s;
+        }
+        const u32 cnt = __popc(open_up) + __popc(open_dn);
+        if (cnt) {
+            u32 o = atomicAdd(sQn, cnt);
+            while (open_up) {
+                const u32 s = __ffs(int(open_up)) - 1;
+                open_up &= open_up - 1;
+                if (o < u32(2 * LPF_TILE / 16)) sQ[o] = (cs + s) << 1;
+                o++;
+            }
+            while (open_dn) {
+                const u32 s = __ffs(int(open_dn)) - 1;
+                open_dn &= open_dn - 1;
+                if (o < u32(2 * LPF_TILE / 16)) sQ[o] = ((cs + s) << 1) | 1u;
+                o++;
+            }
+        }
     }
     __syncthreads();
-    if (warp_id() < LPF_L2) {
-        const u32 av = warp_min(sA[LPF_TILE + warp_id() * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[LPF_TILE + warp_id() * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPF_TILE + LPF_L1 + warp_id()] = av; sL[LPF_TILE + LPF_L1 + warp_id()] = lv; }
+    {
+        const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
+        const u32 qn = *sQn;
+        if (qn <= u32(2 * LPF_TILE / 16)) {
+            for (u32 k = threadIdx.x; k < qn; k += LPF_THREADS) {
+                const u32 e = sQ[k] >> 1, side = sQ[k] & 1u, pe = lpf_phys(e);
+                const u32 v = sA[pe];
+                if (v == LPF_INF) continue;  // padding past the end of the array
+                u32 q = 0;
+                if (side == 0) {
+                    u32 m = sU[pe];  // min LCP[tile start .. e]
+                    const int r = walk_psv(T, base, v, thr, m, q);
+                    sU[pe] = r == WALK_FOUND ? m : 0u;
+                } else {
+                    u32 m = sD[pe];  // min LCP[e + 1 .. tile end)
+                    const int r = walk_nsv(T, last, v, thr, m, q);
+                    sD[pe] = r == WALK_FOUND ? m : 0u;
+                }
+            }
+        } else {
+            // pathological tile (e.g. monotone SA): more open ranks than the queue holds; every thread serves its own chunk
+            for (u32 s = 0; s < 32; s++) {
+                const u32 v = LPF_AT(sA, s);
+                if (v == LPF_INF) continue;
+                u32 q = 0;
+                if (LPF_AT(sPp, s) == 0) {
+                    u32 m = LPF_AT(sU, s);
+                    const int r = walk_psv(T, base, v, thr, m, q);
+                    LPF_AT(sU, s) = r == WALK_FOUND ? m : 0u;
+                }
+                if (LPF_AT(sPn, s) == 0) {
+                    u32 m = LPF_AT(sD, s);
+                    const int r = walk_nsv(T, last, v, thr, m, q);
+                    LPF_AT(sD, s) = r == WALK_FOUND ? m : 0u;
+                }
+            }
+        }
     }
     __syncthreads();
-    TileTree S;
-    S.sA = sA;
-    S.sL = sL;
-    const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
+    // ---- combine (PSV wins ties, LZSSLCPCompressor.hpp:101) ----
     for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
         const u32 p = base + j;
         if (p >= n) break;
-        const u32 v = sA[j];
-        u32 q;
-        u32 mu = sL[j];
-        int r = walk_psv(S, j, v, thr, mu, q);
-        if (r == WALK_OFF_TREE) r = walk_psv(T, base, v, thr, mu, q);
-        const u32 lu = r == WALK_FOUND ? mu : 0u;
-        u32 md = 0xffffffffu;
-        r = walk_nsv(S, j, v, thr, md, q);
-        if (r == WALK_OFF_TREE) r = walk_nsv(T, last, v, thr, md, q);
-        const u32 ld = r == WALK_FOUND ? md : 0u;
+        const u32 lu = sU[lpf_phys(j)], ld = sD[lpf_phys(j)];
         const u32 len = max(lu, ld);
         out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
     }
+#undef LPF_AT
 }
 
 // ---------------------------------------------------------------------------------------------------------------
