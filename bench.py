@@ -395,8 +395,19 @@ def main():
             per_launch_bytes = d["bytes"] / max(d["launches"], 1)
             per_launch_ms = d["ms"] / max(d["launches"], 1)
             achieved = per_launch_bytes / 1e9 / (per_launch_ms / 1e3) if d["bytes"] else None
+            # DRAM bytes per launch: the committed `ncu --set full` capture of this kernel (profiles/traffic.json) gives
+            # dram bytes per algorithmic byte; scaled to the average launch of this run
+            traffic, traffic_src = None, None
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
+                if tj and per_launch_bytes:
+                    traffic = tj["dram_per_algorithmic_byte"] * per_launch_bytes
+                    traffic_src = "profiles/traffic.json: " + tj["capture"]
+            except Exception:
+                pass
             roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "launches": d["launches"], "avg_launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
                     "share_of_step": d["ms"] / dev_ms}
         pipeline_bytes = (25.0 * n + 12.0 * z)  # compulsory traffic of SA+ISA+LCP+factorisation

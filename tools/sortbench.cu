@@ -10,7 +10,7 @@
 
 namespace tdc {
 void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
-LaunchScope::LaunchScope(const char*, cudaStream_t s) : slot(-1), st(s) {}
+LaunchScope::LaunchScope(const char*, cudaStream_t s, bool) : slot(-1), st(s) {}
 LaunchScope::~LaunchScope() {}
 void prof_add_bytes(const char*, double) {}
 }  // namespace tdc

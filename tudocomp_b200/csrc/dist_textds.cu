@@ -66,6 +66,10 @@ static int a2a_elems(DistCtx& d, const void* send, const u64* scnt, void* recv, 
         sb[p] = scnt[p] * esz; rb[p] = rcnt[p] * esz;
         so += scnt[p]; ro += rcnt[p];
     }
+#ifndef TDC_CUSIM
+    LaunchScope timed("nccl_alltoallv", d.c.stream, false);  // shows up in the per-kernel profile, not in the launch count
+#endif
+    prof_add_bytes("nccl_alltoallv", double(so - scnt[d.rank]) * double(esz));  // bytes this rank sends to other ranks
     return d.comm->alltoallv(send, soff, sb, recv, roff, rb, d.c.stream);
 }
 

@@ -125,7 +125,10 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
 #ifdef TDC_CUSIM
 static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
-static const int LPF_THREADS = 128;
+#ifndef LPF_THREADS_CFG
+#define LPF_THREADS_CFG 64
+#endif
+static const int LPF_THREADS = LPF_THREADS_CFG;  // chunks (of 32 ranks) per tile
 #endif
 static const int LPF_TILE = LPF_THREADS * 32;
 static const u32 LPF_INF = 0xffffffffu;
@@ -161,50 +164,50 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
 #define LPF_AT(arr, s) arr[cs + ((s) ^ sw)]
 
     // ---- 1a. NSV inside the chunk, right to left (reads the raw LCP values) ----
+    // One candidate per iteration, written with selects so that lanes that finish a rank and lanes that pop a candidate
+    // run the same instructions (a branchy version ran at 15 of 32 active lanes, profiles/r1f_ncu_summary.md).
     {
         int s = 31;
         u32 v = LPF_AT(sA, 31u), m = LPF_INF, j = 32;
-        while (true) {
+        do {
             const bool valid = j < 32;
             const u32 jj = valid ? j : 31u;
             const u32 aj = LPF_AT(sA, jj), lj = LPF_AT(sU, jj), dj = LPF_AT(sD, jj), nj = LPF_AT(sPn, jj);
-            if (valid) m = min(m, lj);  // LCP[j] lies inside the range whether or not j is the answer
+            const u32 m1 = valid ? min(m, lj) : m;  // LCP[j] lies inside the range whether or not j is the answer
             const bool found = valid && aj < v;
-            if (!valid || found) {
-                LPF_AT(sD, u32(s)) = m;
+            const bool fin = !valid || found;
+            if (fin) {
+                LPF_AT(sD, u32(s)) = m1;
                 LPF_AT(sPn, u32(s)) = (unsigned short)(found ? cs + j + 1 : 0);
-                if (--s < 0) break;
-                v = LPF_AT(sA, u32(s));
-                m = LPF_INF;
-                j = u32(s) + 1;
-            } else {
-                m = min(m, dj);
-                j = nj ? nj - 1 - cs : 32u;
             }
-        }
+            j = fin ? u32(s) : (nj ? nj - 1 - cs : 32u);  // next rank s-1 starts at candidate s
+            m = fin ? LPF_INF : min(m1, dj);
+            s -= fin ? 1 : 0;
+            v = LPF_AT(sA, u32(max(s, 0)));
+        } while (s >= 0);
     }
     // ---- 1b. PSV inside the chunk, left to right; l_up replaces the LCP value in place ----
     {
         u32 s = 0, v = LPF_AT(sA, 0u), m = LPF_AT(sU, 0u), lmin = m;
         int j = -1;
-        while (true) {
+        do {
             const bool valid = j >= 0;
             const u32 jj = valid ? u32(j) : 0u;
             const u32 aj = LPF_AT(sA, jj), uj = LPF_AT(sU, jj), pj = LPF_AT(sPp, jj);
             const bool found = valid && aj < v;
-            if (!valid || found) {
+            const bool fin = !valid || found;
+            if (fin) {
                 LPF_AT(sU, s) = m;
                 LPF_AT(sPp, s) = (unsigned short)(found ? cs + u32(j) + 1 : 0);
-                if (++s == 32) break;
-                v = LPF_AT(sA, s);
-                m = LPF_AT(sU, s);  // still the raw LCP value
-                lmin = min(lmin, m);
-                j = int(s) - 1;
-            } else {
-                m = min(m, uj);
-                j = pj ? int(pj - 1 - cs) : -1;
             }
-        }
+            j = fin ? int(s) : (pj ? int(pj - 1 - cs) : -1);  // next rank s+1 starts at candidate s
+            s += fin ? 1u : 0u;
+            const u32 sn = min(s, 31u);
+            const u32 raw = LPF_AT(sU, sn);  // still the raw LCP value when a new rank starts
+            v = LPF_AT(sA, sn);
+            lmin = fin ? min(lmin, raw) : lmin;
+            m = fin ? raw : min(m, uj);
+        } while (s < 32);
         sNL[threadIdx.x] = lmin;
     }
     __syncthreads();

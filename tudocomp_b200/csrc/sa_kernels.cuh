@@ -350,7 +350,11 @@ static const double SA_ACTIVE_COST = 400.0;
 
 static u32 bits_of_lenfield(u32 k) { return bits_for_host(k); }
 
-static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbits) {
+// log2_collide: optional measured table, log2_collide[k] = log2 of the probability that two random suffixes share their
+// first k bytes (k = 1..8, from sample_prefix_collisions; > 0 means "not measured").  It replaces the memoryless
+// estimate 2^(-H0 k), which is far too optimistic for text with context (order-3 Markov English: H0 = 4.1 bit/symbol but
+// ~2.3 bit/symbol of discrimination), and is extrapolated geometrically beyond k = 8.
+static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbits, const double* log2_collide = nullptr) {
     u32 real = 0;
     double h0 = 0;
     for (int b = 1; b < 256; b++)
@@ -376,8 +380,25 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
             const u32 bits = b * k + (pow2 ? bits_of_lenfield(k) : 0);
             const double passes = double((bits + 7) / 8);
             double residue = h0 > 1e-9 ? exp2(log2(double(n)) - h0 * double(k)) : 1.0;
+            double rounds_left = 0.0;
+            if (log2_collide) {
+                // last two measured points with enough collisions give the decay rate for the extrapolation
+                int k2 = 0;
+                for (int q = 8; q >= 2; q--)
+                    if (log2_collide[q] <= 0.0 && log2_collide[q - 1] <= 0.0) { k2 = q; break; }
+                if (k2) {
+                    const int k1 = k2 >= 3 && log2_collide[k2 - 2] <= 0.0 ? k2 - 2 : k2 - 1;
+                    const double rate = (log2_collide[k1] - log2_collide[k2]) / double(k2 - k1);  // bits per symbol
+                    const double lp = int(k) <= k2 ? log2_collide[k >= 1 ? k : 1] : log2_collide[k2] - rate * double(int(k) - k2);
+                    const double expected_twins = exp2(log2(double(n)) + lp);
+                    residue = 1.0 - exp(-expected_twins);
+                    // a text that keeps most suffixes in groups whatever k is (repeats) pays one doubling round per
+                    // factor of two that the initial key is shorter than the longest possible one
+                    rounds_left = 0.5 * log2(double(kmax) / double(k));
+                }
+            }
             if (residue > 1.0) residue = 1.0;
-            const double cost = passes * 24.0 + residue * SA_ACTIVE_COST;
+            const double cost = passes * 24.0 + residue * SA_ACTIVE_COST * (1.0 + rounds_left);
             if (cost <= best_cost) { best_cost = cost; best = k; }  // ties: more symbols
         }
     }
@@ -385,6 +406,46 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
     pp->k = best;
     pp->lenbits = pow2 ? bits_of_lenfield(best) : 0;
     *sigbits = b * best + pp->lenbits;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// collision statistics of a regular sample of suffix prefixes (input of the key-length cost model)
+// ---------------------------------------------------------------------------------------------------------------
+static __global__ void sample_prefix_kernel(const uint8_t* __restrict__ text, u64 n, u32 samples, u64* __restrict__ out) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= samples) return;
+    const u64 p = (u64(j) * n) / samples;
+    u64 key = 0;
+#pragma unroll
+    for (int q = 0; q < 8; q++) key = (key << 8) | (p + q < n ? text[p + q] : 0);  // big-endian: integer order = byte order
+    out[j] = key;
+}
+
+// sorted[0..S): sorted 8-byte prefixes.  log2_collide[k] (k = 1..8) = log2 P(two samples share k bytes), +1 if fewer
+// than 32 colliding pairs were seen (unreliable).
+static void prefix_collision_table(const u64* sorted, u32 S, double log2_collide[9]) {
+    double pairs[9] = {0};
+    u64 run[9];
+    for (int k = 1; k <= 8; k++) run[k] = 1;
+    for (u32 i = 1; i <= S; i++) {
+        int common = 0;
+        if (i < S) {
+            const u64 x = sorted[i] ^ sorted[i - 1];
+            common = x ? int(__builtin_clzll(x) >> 3) : 8;
+        }
+        for (int k = 1; k <= 8; k++) {
+            if (k <= common) {
+                run[k]++;
+            } else {
+                pairs[k] += double(run[k]) * double(run[k] - 1) * 0.5;
+                run[k] = 1;
+            }
+        }
+    }
+    const double all = double(S) * double(S - 1) * 0.5;
+    log2_collide[0] = 0.0;
+    for (int k = 1; k <= 8; k++) log2_collide[k] = pairs[k] >= 32.0 ? log2(pairs[k] / all) : 1.0;
 }
 
 }  // namespace tdc

@@ -75,6 +75,14 @@ static int rerank(Ctx& c, const K* keys, const u32* vals, const u32* pos_in, u64
     return 0;
 }
 
+#ifdef TDC_CUSIM
+static const u32 SA_SAMPLES = 1u << 10;  // small, so that the CPU tests exercise the sampled model
+static const u64 SA_SAMPLE_MIN_N = 3000;
+#else
+static const u32 SA_SAMPLES = 1u << 16;           // sampled suffix prefixes for the key-length cost model
+static const u64 SA_SAMPLE_MIN_N = u64(1) << 22;  // smaller texts: the sampling would cost more than it can save
+#endif
+
 int build_suffix_array(Ctx& c, bool want_lcp) {
     const u64 n = c.n;
     cudaStream_t st = c.stream;
@@ -108,7 +116,26 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     }
     PackParams pp;
     u32 sigbits;
-    choose_key_layout(hist, n, &pp, &sigbits);
+    double log2_collide[9];
+    bool have_collide = false;
+    if (n >= SA_SAMPLE_MIN_N && !getenv("TDCGPU_SA_SYMBOLS")) {
+        // how fast do k-byte prefixes separate suffixes of THIS text?  sort a regular sample of 8-byte prefixes
+        c.arena.reset();
+        u64* sk[2] = {c.arena.take<u64>(SA_SAMPLES), c.arena.take<u64>(SA_SAMPLES)};
+        u32* sv[2] = {c.arena.take<u32>(SA_SAMPLES), c.arena.take<u32>(SA_SAMPLES)};
+        if (sk[0] && sk[1] && sv[0] && sv[1]) {
+            TDC_LAUNCH(sample_prefix_kernel, u32(div_up(SA_SAMPLES, 256)), 256, 0, st, c.d_text, n, SA_SAMPLES, sk[0]);
+            TDC_KCHECK();
+            int sres = 0;
+            TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, sk, sv, SA_SAMPLES, 0, 64, true, &sres));
+            c.h_samples.resize(SA_SAMPLES);
+            TDC_CUDA(cudaMemcpyAsync(c.h_samples.data(), sk[sres], sizeof(u64) * SA_SAMPLES, cudaMemcpyDeviceToHost, st));
+            TDC_CUDA(cudaStreamSynchronize(st));
+            prefix_collision_table(c.h_samples.data(), SA_SAMPLES, log2_collide);
+            have_collide = true;
+        }
+    }
+    choose_key_layout(hist, n, &pp, &sigbits, have_collide ? log2_collide : nullptr);
     uint8_t code_map[256];
     u32 sigma = 1;
     {

@@ -31,7 +31,7 @@ static const u32 kFull = 0xffffffffu;
 struct LaunchScope {
     int slot;
     cudaStream_t st;
-    LaunchScope(const char* name, cudaStream_t stream);
+    LaunchScope(const char* name, cudaStream_t stream, bool is_kernel = true);  // false: timed (e.g. an NCCL exchange) but not counted as a launch
     ~LaunchScope();
 };
 #endif

@@ -69,6 +69,8 @@ struct Ctx {
 
     cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
+    std::vector<u64> h_samples;  // host copy of the sorted prefix sample (key-length cost model)
+
     // stats
     std::vector<PhaseTime> phases;
     u32 sa_rounds = 0;

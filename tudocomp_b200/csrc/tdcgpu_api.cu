@@ -52,8 +52,8 @@ static cudaEvent_t take_event() {
     return e;
 }
 #ifndef TDC_CUSIM
-LaunchScope::LaunchScope(const char* name, cudaStream_t stream) : slot(-1), st(stream) {
-    g_launches++;
+LaunchScope::LaunchScope(const char* name, cudaStream_t stream, bool is_kernel) : slot(-1), st(stream) {
+    if (is_kernel) g_launches++;
     if (!g_prof_on) return;
     PendingLaunch p;
     p.entry = prof_entry(name);
