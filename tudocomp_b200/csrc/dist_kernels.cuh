@@ -54,11 +54,12 @@ bucket_count_kernel(const K* __restrict__ keys, u64 m, F f, int nbuckets, ull* _
 }
 
 // cursor[b] starts at the bucket's first output slot; order inside a bucket is arbitrary (the consumers sort or scatter).
-// vals == nullptr: the value of element i is vbase + i.
+// vals == nullptr: the value of element i is vbase + i.  vals2 / vout2: optional second value travelling with the first.
 template <class K, class F>
 static __global__ void __launch_bounds__(BP_THREADS)
 bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 vbase, u64 m, F f, int nbuckets,
-                      ull* __restrict__ cursor, K* __restrict__ kout, u32* __restrict__ vout) {
+                      ull* __restrict__ cursor, K* __restrict__ kout, u32* __restrict__ vout, const u32* __restrict__ vals2,
+                      u32* __restrict__ vout2) {
     __shared__ u32 cnt[DIST_MAX_RANKS];
     __shared__ ull gbase[DIST_MAX_RANKS];
     if (threadIdx.x < DIST_MAX_RANKS) cnt[threadIdx.x] = 0;
@@ -90,6 +91,7 @@ bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, 
             const u64 o = gbase[b[q]] + lr[q];
             kout[o] = f.out(key[q], b[q]);
             vout[o] = vals ? vals[i] : vbase + u32(i);
+            if (vals2) vout2[o] = vals2[i];
         }
     }
 }
@@ -125,94 +127,9 @@ static __global__ void lcp_boundary_kernel(const uint8_t* __restrict__ text, con
 // ---------------------------------------------------------------------------------------------------------------
 // LPF per rank with source positions; walks that leave the shard are queued for the neighbouring shards
 // ---------------------------------------------------------------------------------------------------------------
-struct WalkQuery {  // p: slot index inside the origin shard; v = SA[p]; m = LCP minimum collected so far
-    u32 p, v, m;
-};
 struct WalkAnswer {
     u32 p, m, src;
 };
-
-#ifdef TDC_CUSIM
-static const int LPFD_THREADS = 128;
-static const int LPFD_TILE = 1024;
-#else
-static const int LPFD_THREADS = 512;
-static const int LPFD_TILE = 4096;
-#endif
-static const int LPFD_L1 = LPFD_TILE / 32;
-static const int LPFD_L2 = LPFD_L1 / 32;
-struct DTileTree {
-    const u32* sA;
-    const u32* sL;
-    __device__ __forceinline__ static u32 off(int lvl) { return lvl == 0 ? 0u : (lvl == 1 ? u32(LPFD_TILE) : u32(LPFD_TILE + LPFD_L1)); }
-    __device__ __forceinline__ u32 A(int lvl, u32 i) const { return sA[off(lvl) + i]; }
-    __device__ __forceinline__ u32 L(int lvl, u32 i) const { return sL[off(lvl) + i]; }
-    __device__ __forceinline__ u32 size(int lvl) const { return lvl == 0 ? u32(LPFD_TILE) : (lvl == 1 ? u32(LPFD_L1) : u32(LPFD_L2)); }
-    __device__ __forceinline__ int levels() const { return 3; }
-};
-
-static __global__ void __launch_bounds__(LPFD_THREADS)
-lpf_dist_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ lu_out, u32* __restrict__ su_out, u32* __restrict__ ld_out,
-                u32* __restrict__ sd_out, WalkQuery* __restrict__ q_up, WalkQuery* __restrict__ q_dn,
-                u32* __restrict__ q_cnt /*[2]*/, u32 qcap) {
-    __shared__ u32 sA[LPFD_TILE + LPFD_L1 + LPFD_L2];
-    __shared__ u32 sL[LPFD_TILE + LPFD_L1 + LPFD_L2];
-    const u32 base = blockIdx.x * LPFD_TILE;
-    for (u32 j = threadIdx.x; j < LPFD_TILE; j += LPFD_THREADS) {
-        const u32 i = base + j;
-        sA[j] = i < n ? T.a[0][i] : 0xffffffffu;
-        sL[j] = i < n ? T.l[0][i] : 0xffffffffu;
-    }
-    __syncthreads();
-    for (u32 g = warp_id(); g < LPFD_L1; g += LPFD_THREADS / 32) {
-        const u32 av = warp_min(sA[g * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[g * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPFD_TILE + g] = av; sL[LPFD_TILE + g] = lv; }
-    }
-    __syncthreads();
-    if (warp_id() < LPFD_L2) {
-        const u32 av = warp_min(sA[LPFD_TILE + warp_id() * 32 + lane_id()]);
-        const u32 lv = warp_min(sL[LPFD_TILE + warp_id() * 32 + lane_id()]);
-        if (lane_id() == 0) { sA[LPFD_TILE + LPFD_L1 + warp_id()] = av; sL[LPFD_TILE + LPFD_L1 + warp_id()] = lv; }
-    }
-    __syncthreads();
-    DTileTree S;
-    S.sA = sA;
-    S.sL = sL;
-    const u32 last = min(base + u32(LPFD_TILE), n) - 1u;
-    for (u32 j = threadIdx.x; j < LPFD_TILE; j += LPFD_THREADS) {
-        const u32 p = base + j;
-        if (p >= n) break;
-        const u32 v = sA[j];
-        u32 q = 0, lu = 0, su = 0, ld = 0, sd = 0;
-        u32 mu = sL[j];
-        int r = walk_psv(S, j, v, thr, mu, q);
-        if (r == WALK_FOUND) { lu = mu; su = S.A(0, q); }
-        if (r == WALK_OFF_TREE) {
-            r = walk_psv(T, base, v, thr, mu, q);
-            if (r == WALK_FOUND) { lu = mu; su = T.A(0, q); }
-            if (r == WALK_OFF_TREE) {  // nothing smaller further up in this shard: continue on the previous one
-                const u32 slot = atomicAdd(&q_cnt[0], 1u);
-                if (slot < qcap) { WalkQuery w; w.p = p; w.v = v; w.m = mu; q_up[slot] = w; }
-            }
-        }
-        u32 md = 0xffffffffu;
-        r = walk_nsv(S, j, v, thr, md, q);
-        if (r == WALK_FOUND) { ld = md; sd = S.A(0, q); }
-        if (r == WALK_OFF_TREE) {
-            r = walk_nsv(T, last, v, thr, md, q);
-            if (r == WALK_FOUND) { ld = md; sd = T.A(0, q); }
-            if (r == WALK_OFF_TREE) {
-                const u32 slot = atomicAdd(&q_cnt[1], 1u);
-                if (slot < qcap) { WalkQuery w; w.p = p; w.v = v; w.m = md; q_dn[slot] = w; }
-            }
-        }
-        lu_out[p] = lu;
-        su_out[p] = su;
-        ld_out[p] = ld;
-        sd_out[p] = sd;
-    }
-}
 
 // Queries arriving from a neighbouring shard, answered against this shard's tree.  UP: the walk enters at the shard's
 // last slot and moves towards slot 0; otherwise it enters at slot 0 and moves up.  Found -> answer for the origin;

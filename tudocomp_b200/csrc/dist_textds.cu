@@ -80,7 +80,8 @@ static int allgather_u64(DistCtx& d, const u64* mine, int words, std::vector<u64
 }
 
 template <class K, class F>
-static int bucket_partition(DistCtx& d, const K* kin, const u32* vin, u32 vbase, u64 m, F f, K* kout, u32* vout, u64* cnt_out) {
+static int bucket_partition(DistCtx& d, const K* kin, const u32* vin, u32 vbase, u64 m, F f, K* kout, u32* vout, u64* cnt_out,
+                            const u32* vin2 = nullptr, u32* vout2 = nullptr) {
     cudaStream_t st = d.c.stream;
     TDC_CUDA(cudaMemsetAsync(d.d_counts, 0, sizeof(ull) * 2 * DIST_MAX_RANKS, st));
     if (m) {
@@ -100,29 +101,38 @@ static int bucket_partition(DistCtx& d, const K* kin, const u32* vin, u32 vbase,
     TDC_CUDA(cudaMemcpyAsync(d.d_counts + DIST_MAX_RANKS, d.h_counts + DIST_MAX_RANKS, sizeof(ull) * d.P, cudaMemcpyHostToDevice, st));
     if (m) {
         auto bucket_scatter = bucket_scatter_kernel<K, F>;
-        TDC_LAUNCH(bucket_scatter, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, d.P, d.d_counts + DIST_MAX_RANKS, kout, vout);
-        prof_add_bytes("bucket_scatter", double(m) * 2 * (sizeof(K) + 4));
+        TDC_LAUNCH(bucket_scatter, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, d.P, d.d_counts + DIST_MAX_RANKS, kout, vout, vin2, vout2);
+        prof_add_bytes("bucket_scatter", double(m) * 2 * (sizeof(K) + 4 + (vin2 ? 4 : 0)));
         TDC_KCHECK();
     }
     TDC_CUDA(cudaStreamSynchronize(st));  // h_counts is reused by the next call
     return 0;
 }
 
-// dst_shard[idx - owner*block] = val on the owner of idx.  bufs: six u32 buffers of d.cap elements.
-static int dist_scatter(DistCtx& d, const u32* idx, const u32* val, u64 m, u32* dst_shard, u32* bufs[6]) {
+// dst_shard[idx - owner*block] = val on the owner of idx (and dst2 / val2 alike when given: one partition and one
+// exchange of the indices serve both).  bufs: six u32 buffers of d.cap elements, eight with a second value.
+static int dist_scatter(DistCtx& d, const u32* idx, const u32* val, u64 m, u32* dst_shard, u32** bufs, const u32* val2 = nullptr,
+                        u32* dst2 = nullptr) {
     OwnerFn f;
     f.block = d.block;
     u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
-    TDC_TRY((bucket_partition<u32, OwnerFn>(d, idx, val, 0, m, f, bufs[0], bufs[1], scnt)));
+    TDC_TRY((bucket_partition<u32, OwnerFn>(d, idx, val, 0, m, f, bufs[0], bufs[1], scnt, val2, val2 ? bufs[6] : nullptr)));
     TDC_TRY(exchange_matrix(d, scnt, d.xchg));
     u64 R = 0;
     for (int p = 0; p < d.P; p++) { rcnt[p] = d.xchg[size_t(p) * d.P + d.rank]; R += rcnt[p]; }
     if (R > d.cap) { set_error("dist_scatter: %llu updates exceed the shard capacity", (unsigned long long)R); return TDCGPU_ERR_INTERNAL; }
     TDC_TRY(a2a_elems(d, bufs[0], scnt, bufs[2], rcnt, 4));
     TDC_TRY(a2a_elems(d, bufs[1], scnt, bufs[3], rcnt, 4));
+    if (val2) TDC_TRY(a2a_elems(d, bufs[6], scnt, bufs[7], rcnt, 4));
     u32* si[2] = {bufs[2], bufs[4]};
     u32* sv[2] = {bufs[3], bufs[5]};
     TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si, sv, R, dst_shard, d.pos_cnt, R == d.pos_cnt));
+    if (val2) {
+        // bufs[0]/bufs[1] have been sent: free as the scratch pair of the second scatter (the received indices are intact)
+        u32* si2[2] = {bufs[2], bufs[0]};
+        u32* sv2[2] = {bufs[7], bufs[1]};
+        TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si2, sv2, R, dst2, d.pos_cnt, R == d.pos_cnt));
+    }
     return 0;
 }
 
@@ -392,8 +402,8 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
     for (int i = T.nlev; i < MT_MAX_LEVELS; i++) { T.a[i] = nullptr; T.l[i] = nullptr; T.sz[i] = 0; }
     TDC_KCHECK();
 
-    u32* W[8];  // lu, su, ld, sd, then four more work buffers
-    for (int i = 0; i < 8; i++) W[i] = c.arena.take<u32>(cap);
+    u32* W[10];  // lu, su, ld, sd, then six more work buffers
+    for (int i = 0; i < 10; i++) W[i] = c.arena.take<u32>(cap);
     u32* lenside_t = c.arena.take<u32>(cap + 64);  // text order
     u32* src_t = c.arena.take<u32>(cap + 64);
     WalkQuery* qb[6];  // up A/B, down A/B, received up, received down
@@ -401,13 +411,18 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
     WalkAnswer* ab[3];  // answers up, answers down, received answers
     for (int i = 0; i < 3; i++) ab[i] = c.arena.take<WalkAnswer>(qcap);
     u32* d_cnt = c.d_scalars + 8;  // [4]
-    if (!W[7] || !lenside_t || !src_t || !qb[5] || !ab[2]) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+    if (!W[9] || !lenside_t || !src_t || !qb[5] || !ab[2]) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
     u32 *lu = W[0], *su = W[1], *ld = W[2], *sd = W[3];
 
     // ---- LPF per slot; walks leaving the shard are queued ----
     TDC_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(u32), st));
     if (mr) {
-        TDC_LAUNCH(lpf_dist_kernel, u32(div_up(u64(mr), LPFD_TILE)), LPFD_THREADS, 0, st, T, mr, threshold, lu, su, ld, sd, qb[0], qb[2], d_cnt, u32(qcap));
+        LpfDistOut lo;
+        lo.lu = lu; lo.su = su; lo.ld = ld; lo.sd = sd;
+        lo.q_up = qb[0]; lo.q_dn = qb[2]; lo.q_cnt = d_cnt; lo.qcap = u32(qcap);
+        auto lpf_tile_dist = lpf_tile_kernel<true>;
+        TDC_CUDA(cudaFuncSetAttribute(lpf_tile_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lpf_smem_bytes())));
+        TDC_LAUNCH(lpf_tile_dist, u32(div_up(u64(mr), LPF_TILE)), LPF_THREADS, lpf_smem_bytes(), st, T, mr, threshold, (u32*)nullptr, lo);
         TDC_KCHECK();
     }
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 8, d_cnt, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -474,9 +489,8 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
         TDC_KCHECK();
     }
     {
-        u32* bufs[6] = {W[0], W[1], W[2], W[3], W[6], W[7]};
-        TDC_TRY(dist_scatter(d, d.d_sa, lenside_r, mr, lenside_t, bufs));
-        TDC_TRY(dist_scatter(d, d.d_sa, src_r, mr, src_t, bufs));
+        u32* bufs[8] = {W[0], W[1], W[2], W[3], W[6], W[7], W[8], W[9]};
+        TDC_TRY(dist_scatter(d, d.d_sa, lenside_r, mr, lenside_t, bufs, src_r, src_t));
     }
     // ---- greedy chain over my positions; the entry point comes from the previous rank ----
     const u32 n_eff = u32(rank == P - 1 ? d.pos_cnt : d.pos_cnt + 1);  // positions < n_eff - 1 are chain nodes here
@@ -579,7 +593,7 @@ static int dist_ensure_capacity(DistCtx& d, u64 n) {
     TDC_CUDA(cudaMalloc(&d.d_sa, sizeof(u32) * cap));
     TDC_CUDA(cudaMalloc(&d.d_rank, sizeof(u32) * cap));
     TDC_CUDA(cudaMalloc(&d.d_lcp, sizeof(u32) * cap));
-    const size_t arena_bytes = size_t(64) * cap + cap / 4 + size_t(9 * 12) * d.qcap + (size_t(16) << 20);
+    const size_t arena_bytes = size_t(72) * cap + cap / 4 + size_t(9 * 12) * d.qcap + (size_t(16) << 20);
     TDC_CUDA(cudaMalloc(&c.arena.base, arena_bytes));
     c.arena.cap = arena_bytes;
     c.arena.off = 0;

@@ -69,8 +69,9 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         u32* sc_idx[2] = {c.d_sa, c.arena.take<u32>(n)};
         u32* sc_val[2] = {c.arena.take<u32>(n), c.arena.take<u32>(n)};
         if (!sc_idx[1] || !sc_val[0] || !sc_val[1]) { set_error("lzss_lcp: scratch arena too small"); return -2; }
+        auto lpf_tile_kernel = tdc::lpf_tile_kernel<false>;
         TDC_CUDA(cudaFuncSetAttribute(lpf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lpf_smem_bytes())));
-        TDC_LAUNCH(lpf_tile_kernel, u32(div_up(u64(n), LPF_TILE)), LPF_THREADS, lpf_smem_bytes(), st, T, n, threshold, sc_val[0]);
+        TDC_LAUNCH(lpf_tile_kernel, u32(div_up(u64(n), LPF_TILE)), LPF_THREADS, lpf_smem_bytes(), st, T, n, threshold, sc_val[0], LpfDistOut());
         prof_add_bytes("lpf_tile_kernel", double(n) * 12);
         TDC_KCHECK();
         TDC_TRY(partitioned_scatter(c.sortws, st, sc_idx, sc_val, n, lenside, n, true));

@@ -122,26 +122,75 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
 // (History, profiles/r1d_ncu_summary.md: one independent linear walk per rank spends ~50 instructions per rank on
 // divergence; per-chunk recurrences + tree walks for the leftovers spend even more on the walks.)
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef LPF_CHUNK_CFG
+#define LPF_CHUNK_CFG 16
+#endif
+static const int LPF_CHUNK = LPF_CHUNK_CFG;  // ranks per thread (16 or 32)
 #ifdef TDC_CUSIM
 static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
 #ifndef LPF_THREADS_CFG
-#define LPF_THREADS_CFG 64
+#define LPF_THREADS_CFG 128
 #endif
-static const int LPF_THREADS = LPF_THREADS_CFG;  // chunks (of 32 ranks) per tile
+static const int LPF_THREADS = LPF_THREADS_CFG;  // chunks per tile (power of two)
 #endif
-static const int LPF_TILE = LPF_THREADS * 32;
+static const int LPF_TILE = LPF_THREADS * LPF_CHUNK;
 static const u32 LPF_INF = 0xffffffffu;
 static const u32 LPF_NONE = 0xffffffffu;
 
-// XOR swizzle: a thread walking its own chunk (index t*32 + s) and a warp reading 32 consecutive ranks both touch 32
-// different banks
+// XOR swizzle: the threads of a warp walking their own chunks (index t*LPF_CHUNK + s, same s) and a warp reading 32
+// consecutive ranks both touch 32 different banks
 __device__ __forceinline__ u32 lpf_phys(u32 i) { return i ^ ((i >> 5) & 31u); }
 
 static inline size_t lpf_smem_bytes() { return sizeof(u32) * 3 * LPF_TILE + sizeof(unsigned short) * 2 * LPF_TILE + sizeof(u32) * (LPF_THREADS + 2 * LPF_TILE / 16 + 8); }
 
+// DIST (sharded multi-GPU path): l_up / l_dn and their source positions are written separately and walks that find
+// nothing smaller inside this shard are queued for the neighbouring shards (dist_textds.cu).
+struct WalkQuery {  // p: slot index inside the origin shard; v = SA[p]; m = LCP minimum collected so far
+    u32 p, v, m;
+};
+struct LpfDistOut {
+    u32 *lu, *su, *ld, *sd;
+    WalkQuery *q_up, *q_dn;
+    u32* q_cnt;  // [2]
+    u32 qcap;
+};
+
+template <bool DIST>
+__device__ __forceinline__ void lpf_resolve_open(const MinTree& T, u32 base, u32 last, u32 thr, u32 e, u32 side, u32* sA, u32* sU, u32* sD,
+                                                 const LpfDistOut& D) {
+    const u32 pe = lpf_phys(e);
+    const u32 v = sA[pe];
+    if (v == LPF_INF) return;  // padding past the end of the array
+    u32 q = 0;
+    if (side == 0) {
+        u32 m = sU[pe];  // min LCP[tile start .. e]
+        const int r = walk_psv(T, base, v, thr, m, q);
+        sU[pe] = r == WALK_FOUND ? m : 0u;
+        if (DIST) {
+            D.su[base + e] = r == WALK_FOUND ? T.a[0][q] : 0u;
+            if (r == WALK_OFF_TREE) {
+                const u32 slot = atomicAdd(&D.q_cnt[0], 1u);
+                if (slot < D.qcap) { WalkQuery w; w.p = base + e; w.v = v; w.m = m; D.q_up[slot] = w; }
+            }
+        }
+    } else {
+        u32 m = sD[pe];  // min LCP[e + 1 .. tile end)
+        const int r = walk_nsv(T, last, v, thr, m, q);
+        sD[pe] = r == WALK_FOUND ? m : 0u;
+        if (DIST) {
+            D.sd[base + e] = r == WALK_FOUND ? T.a[0][q] : 0u;
+            if (r == WALK_OFF_TREE) {
+                const u32 slot = atomicAdd(&D.q_cnt[1], 1u);
+                if (slot < D.qcap) { WalkQuery w; w.p = base + e; w.v = v; w.m = m; D.q_dn[slot] = w; }
+            }
+        }
+    }
+}
+
+template <bool DIST>
 static __global__ void __launch_bounds__(LPF_THREADS)
-lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
+lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside, LpfDistOut D) {
     TDC_DYN_SMEM(smem_raw);
     u32* sA = reinterpret_cast<u32*>(smem_raw);            // SA values
     u32* sU = sA + LPF_TILE;                                // LCP values, overwritten in place by l_up
@@ -159,19 +208,20 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
     }
     if (threadIdx.x == 0) *sQn = 0;
     __syncthreads();
-    const u32 cs = threadIdx.x * 32u;  // this thread's chunk [cs, cs + 32)
-    const u32 sw = threadIdx.x & 31u;  // swizzle of the chunk: phys(cs + s) = cs + (s ^ sw)
-#define LPF_AT(arr, s) arr[cs + ((s) ^ sw)]
+    constexpr u32 CH = u32(LPF_CHUNK);
+    const u32 cs = threadIdx.x * CH;  // this thread's chunk [cs, cs + CH)
+    const u32 sw = (cs >> 5) & 31u;   // swizzle of the chunk: phys(cs + s) = (cs + s) ^ sw
+#define LPF_AT(arr, s) arr[(cs + (s)) ^ sw]
 
     // ---- 1a. NSV inside the chunk, right to left (reads the raw LCP values) ----
     // One candidate per iteration, written with selects so that lanes that finish a rank and lanes that pop a candidate
     // run the same instructions (a branchy version ran at 15 of 32 active lanes, profiles/r1f_ncu_summary.md).
     {
-        int s = 31;
-        u32 v = LPF_AT(sA, 31u), m = LPF_INF, j = 32;
+        int s = int(CH) - 1;
+        u32 v = LPF_AT(sA, CH - 1), m = LPF_INF, j = CH;
         do {
-            const bool valid = j < 32;
-            const u32 jj = valid ? j : 31u;
+            const bool valid = j < CH;
+            const u32 jj = valid ? j : CH - 1;
             const u32 aj = LPF_AT(sA, jj), lj = LPF_AT(sU, jj), dj = LPF_AT(sD, jj), nj = LPF_AT(sPn, jj);
             const u32 m1 = valid ? min(m, lj) : m;  // LCP[j] lies inside the range whether or not j is the answer
             const bool found = valid && aj < v;
@@ -180,7 +230,7 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
                 LPF_AT(sD, u32(s)) = m1;
                 LPF_AT(sPn, u32(s)) = (unsigned short)(found ? cs + j + 1 : 0);
             }
-            j = fin ? u32(s) : (nj ? nj - 1 - cs : 32u);  // next rank s-1 starts at candidate s
+            j = fin ? u32(s) : (nj ? nj - 1 - cs : CH);  // next rank s-1 starts at candidate s
             m = fin ? LPF_INF : min(m1, dj);
             s -= fin ? 1 : 0;
             v = LPF_AT(sA, u32(max(s, 0)));
@@ -202,12 +252,12 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
             }
             j = fin ? int(s) : (pj ? int(pj - 1 - cs) : -1);  // next rank s+1 starts at candidate s
             s += fin ? 1u : 0u;
-            const u32 sn = min(s, 31u);
+            const u32 sn = min(s, CH - 1);
             const u32 raw = LPF_AT(sU, sn);  // still the raw LCP value when a new rank starts
             v = LPF_AT(sA, sn);
             lmin = fin ? min(lmin, raw) : lmin;
             m = fin ? raw : min(m, uj);
-        } while (s < 32);
+        } while (s < CH);
         sNL[threadIdx.x] = lmin;
     }
     __syncthreads();
@@ -215,7 +265,7 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
     for (u32 half = 1; half < u32(LPF_THREADS); half <<= 1) {  // half = chunks per child node
         if (threadIdx.x * 2 * half < u32(LPF_THREADS)) {
             const u32 ca = threadIdx.x * 2 * half, cb = ca + half;  // first chunks of the left / right child
-            u32 a = cb * 32 - 1, b = cb * 32;                        // heads: last rank of A, first rank of B
+            u32 a = cb * CH - 1, b = cb * CH;                        // heads: last rank of A, first rank of B
             u32 va = sA[lpf_phys(a)], vb = sA[lpf_phys(b)];
             while (a != LPF_NONE && b != LPF_NONE) {
                 const u32 pa = lpf_phys(a), pb = lpf_phys(b);
@@ -254,7 +304,7 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
     {
         u32 open_up = 0, open_dn = 0;
 #pragma unroll 4
-        for (u32 s = 0; s < 32; s++) {
+        for (u32 s = 0; s < CH; s++) {
             if (LPF_AT(sPp, s) == 0) open_up |= 1u << s;
             if (LPF_AT(sPn, s) == 0) open_dn |= 1u << s;
         }
@@ -280,37 +330,12 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
         const u32 last = min(base + u32(LPF_TILE), n) - 1u;  // last rank of this tile
         const u32 qn = *sQn;
         if (qn <= u32(2 * LPF_TILE / 16)) {
-            for (u32 k = threadIdx.x; k < qn; k += LPF_THREADS) {
-                const u32 e = sQ[k] >> 1, side = sQ[k] & 1u, pe = lpf_phys(e);
-                const u32 v = sA[pe];
-                if (v == LPF_INF) continue;  // padding past the end of the array
-                u32 q = 0;
-                if (side == 0) {
-                    u32 m = sU[pe];  // min LCP[tile start .. e]
-                    const int r = walk_psv(T, base, v, thr, m, q);
-                    sU[pe] = r == WALK_FOUND ? m : 0u;
-                } else {
-                    u32 m = sD[pe];  // min LCP[e + 1 .. tile end)
-                    const int r = walk_nsv(T, last, v, thr, m, q);
-                    sD[pe] = r == WALK_FOUND ? m : 0u;
-                }
-            }
+            for (u32 k = threadIdx.x; k < qn; k += LPF_THREADS) lpf_resolve_open<DIST>(T, base, last, thr, sQ[k] >> 1, sQ[k] & 1u, sA, sU, sD, D);
         } else {
             // pathological tile (e.g. monotone SA): more open ranks than the queue holds; every thread serves its own chunk
-            for (u32 s = 0; s < 32; s++) {
-                const u32 v = LPF_AT(sA, s);
-                if (v == LPF_INF) continue;
-                u32 q = 0;
-                if (LPF_AT(sPp, s) == 0) {
-                    u32 m = LPF_AT(sU, s);
-                    const int r = walk_psv(T, base, v, thr, m, q);
-                    LPF_AT(sU, s) = r == WALK_FOUND ? m : 0u;
-                }
-                if (LPF_AT(sPn, s) == 0) {
-                    u32 m = LPF_AT(sD, s);
-                    const int r = walk_nsv(T, last, v, thr, m, q);
-                    LPF_AT(sD, s) = r == WALK_FOUND ? m : 0u;
-                }
+            for (u32 s = 0; s < CH; s++) {
+                if (LPF_AT(sPp, s) == 0) lpf_resolve_open<DIST>(T, base, last, thr, cs + s, 0u, sA, sU, sD, D);
+                if (LPF_AT(sPn, s) == 0) lpf_resolve_open<DIST>(T, base, last, thr, cs + s, 1u, sA, sU, sD, D);
             }
         }
     }
@@ -320,8 +345,16 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside) {
         const u32 p = base + j;
         if (p >= n) break;
         const u32 lu = sU[lpf_phys(j)], ld = sD[lpf_phys(j)];
-        const u32 len = max(lu, ld);
-        out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+        if (DIST) {
+            D.lu[p] = lu;
+            D.ld[p] = ld;
+            const u32 pp = sPp[lpf_phys(j)], pn = sPn[lpf_phys(j)];
+            if (pp) D.su[p] = sA[lpf_phys(pp - 1)];  // open ranks were written by lpf_resolve_open
+            if (pn) D.sd[p] = sA[lpf_phys(pn - 1)];
+        } else {
+            const u32 len = max(lu, ld);
+            out_lenside[p] = len >= thr ? ((len << 1) | (lu >= ld ? 0u : 1u)) : 0u;
+        }
     }
 #undef LPF_AT
 }

@@ -175,6 +175,14 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         __syncwarp();
         rank[k] = c + before;
     }
+    // fetch the values now: their latency overlaps the digit scan and the look-back instead of sitting, exposed, between
+    // the last barrier and the staging stores (ncu: long-scoreboard stalls 6.2 per issue, profiles/r1d_ncu_summary.md)
+    u32 val[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const u64 idx = wbase + u32(k) * 32 + lane;
+        val[k] = IOTA ? u32(idx) : (idx < m ? vin[idx] : 0u);
+    }
     __syncthreads();
 
     // ---- per-digit totals, warp offsets, tile-local digit starts ----
@@ -225,7 +233,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
         const u64 idx = wbase + u32(k) * 32 + lane;
         skeys[p] = key[k];
-        if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];
+        if (idx < m) svals[p] = val[k];
     }
     __syncthreads();
 
