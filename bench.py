@@ -137,6 +137,74 @@ def cpu_reference_run(sample: np.ndarray, steps: int):
     return kind, times
 
 
+_REF_BLOCKS = None  # set before the fork: the workers of cpu_reference_parallel read their block from here
+
+
+def _ref_block_worker(b):
+    kind, times = cpu_reference_run(_REF_BLOCKS[b], 1)
+    return kind, times[0]
+
+
+def cpu_reference_parallel(blocks, steps: int):
+    """All host cores: the reference is single-threaded, so the only way it can use C cores is C independent processes,
+    each running the unmodified code on its own block of the workload text (what `tdc` on C files in parallel would do).
+    One step = all C blocks once, wall clock from the common start to the last worker's end."""
+    import multiprocessing as mp
+
+    global _REF_BLOCKS
+    _REF_BLOCKS = blocks
+    kind, times = "reference", []
+    with mp.get_context("fork").Pool(len(blocks)) as pool:
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            res = pool.map(_ref_block_worker, range(len(blocks)), chunksize=1)
+            times.append(time.perf_counter() - t0)
+            kind = res[0][0]
+    return kind, times
+
+
+def verify_shard(ctx, text, info, zl, rank, samples=2000):
+    """Size-independent properties on a random sample of this rank's shard (the CPU oracle cannot reach multi-GB texts):
+    SA[j-1] < SA[j] as suffixes and LCP[j] = their common prefix (direct byte comparison on the host text); every sampled
+    factor copies an earlier occurrence (text[src:src+len] == text[pos:pos+len], src < pos) and cannot be extended."""
+    import tudocomp_b200 as tdc
+
+    rng = np.random.default_rng(1234 + rank)
+    sa, lcp = ctx.get(tdc.SA), ctx.get(tdc.LCP)
+    n = text.size
+    bad = []
+
+    def common(a, b, limit=1 << 16):
+        l = 0
+        while l < limit:
+            step = min(4096, n - max(a, b) - l)
+            if step <= 0:
+                break
+            x, y = text[a + l:a + l + step], text[b + l:b + l + step]
+            d = np.nonzero(x != y)[0]
+            if d.size:
+                return l + int(d[0])
+            l += step
+        return l
+
+    if sa.size > 1:
+        for j in rng.integers(1, sa.size, size=min(samples, sa.size - 1)):
+            a, b = int(sa[j - 1]), int(sa[j])
+            l = common(a, b)
+            if l != int(lcp[j]) or not (text[a + l] < text[b + l]):
+                bad.append(("sa/lcp", int(j), a, b, l, int(lcp[j])))
+    f = ctx.factors(zl)
+    if zl:
+        for k in rng.integers(0, zl, size=min(samples, zl)):
+            pos, src, ln = int(f["pos"][k]), int(f["src"][k]), int(f["len"][k])
+            ok = src < pos and ln >= THRESHOLD and common(src, pos, ln + 1) == ln
+            if not ok:
+                bad.append(("factor", int(k), pos, src, ln))
+        if not (np.all(np.diff(f["pos"].astype(np.int64)) > 0) and int(f["pos"][0]) >= info["pos_lo"] and int(f["pos"][-1]) < info["pos_lo"] + info["pos_cnt"]):
+            bad.append(("factor order/range",))
+    return {"ok": not bad, "sampled_slots": int(min(samples, max(sa.size - 1, 0))), "sampled_factors": int(min(samples, zl)), "first_problems": bad[:3]}
+
+
 def main_dist(args, rank, local_rank, world, n_body, seed):
     """One text of n_body bytes sharded over all ranks (config 4 of BASELINE.json): distributed prefix-doubling SA with
     NCCL all-to-all exchanges, LCP, lzss_lcp factorisation.  Strong scaling: value = n_body / step time (max over ranks)."""
@@ -206,6 +274,13 @@ def main_dist(args, rank, local_rank, world, n_body, seed):
     clocks = sampler.stop()
     ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist)
     ms_step_e2e = blockmode.reduce_step_time(e2e_ms / args.steps, dist)
+    verified = None
+    if args.verify:
+        verified = verify_shard(ctx, text, info, zl, rank)
+        if dist is not None:
+            flag = torch.tensor([0 if verified["ok"] else 1], device=f"cuda:{local_rank}")
+            dist.all_reduce(flag)
+            verified["all_ranks_ok"] = bool(flag.item() == 0)
     if rank == 0:
         peaks = {}
         try:
@@ -225,14 +300,14 @@ def main_dist(args, rank, local_rank, world, n_body, seed):
         line = {"metric": METRIC, "value": blockmode.job_throughput_mb_s(n_body, ms_step), "unit": "MB/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}_2^{args.log2_bytes}B_single_text_sharded: distributed SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD})",
+                "config": {"workload": f"{args.workload}_{n_body}B_single_text_sharded: distributed SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD})",
                            "text_bytes": n, "threshold": THRESHOLD, "index_bits": 32,
                            "l2_policy": "working set per GPU far larger than the 126 MB L2; no flush needed",
                            "parallelism": f"one text sharded over {world} GPUs; NCCL all-to-all of rank buckets, rank updates and rank requests"},
                 "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
                         "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
-                "dist_stats": stats, "shard_rank0": info,
+                "dist_stats": stats, "shard_rank0": info, "verify": verified,
                 "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
                 "last_step_phases_ms": {k: round(v, 3) for k, v in phases}}
         print(json.dumps(line))
@@ -251,6 +326,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dna", choices=["dna", "markov", "repetitive"])
     ap.add_argument("--log2-bytes", type=int, default=30, help="text body size per GPU = 2^L bytes (default 1 GiB)")
+    ap.add_argument("--bytes", type=int, default=0, help="text body size in bytes (overrides --log2-bytes), e.g. 4000000000")
+    ap.add_argument("--verify", action="store_true", help="dist mode: sampled on-host checks of SA order, LCP values and factors")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--mode", default="block", choices=["block", "dist"],
                     help="N > 1: 'block' = one independent text per GPU (weak scaling, no collective); 'dist' = ONE text of "
@@ -260,9 +337,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_body = 1 << args.log2_bytes
+    n_body = args.bytes if args.bytes > 0 else 1 << args.log2_bytes
+    size_name = f"{n_body}B" if args.bytes > 0 else f"2^{args.log2_bytes}B"
     seed_of = {"dna": 2, "markov": 1, "repetitive": 3}[args.workload]
-    workload_name = f"{args.workload}_2^{args.log2_bytes}B_per_gpu: TextDS SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD}) factorize"
+    workload_name = f"{args.workload}_{size_name}_per_gpu: TextDS SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD}) factorize"
     config = {"workload": workload_name, "text_bytes_per_gpu": n_body + 1, "threshold": THRESHOLD, "index_bits": 32,
               "l2_policy": "inputs (>= 1 GiB text, 4 GiB arrays) are far larger than the 126 MB L2; no flush needed",
               "parallelism": f"block mode, {max(world, args.gpus)} independent texts, no collective"}
@@ -271,16 +349,30 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # Bounded sample of the same workload: C blocks of 2^24 B (C = host cores), consecutive pieces of the workload text,
+        # one unmodified single-threaded reference process per block, all at once.  `single_core` is one block on one
+        # core, the figure that corresponds to the reference's own published single-threaded runs.
         sample_body = min(n_body, 1 << CPU_SAMPLE_LOG2)
-        sample = gen_text(args.workload, sample_body, seed_of)  # same generator and seed as rank 0's text
-        kind, times = cpu_reference_run(sample, args.warmup + args.steps)
+        cores = max(1, min(os.cpu_count() or 1, 64, n_body // sample_body))
+        body = gen_text(args.workload, sample_body * cores, seed_of)[:-1]  # same generator and seed as rank 0's text
+        blocks = []
+        for b in range(cores):
+            blk = np.empty(sample_body + 1, np.uint8)
+            blk[:-1] = body[b * sample_body:(b + 1) * sample_body]
+            blk[-1] = 0
+            blocks.append(blk)
+        kind, t1 = cpu_reference_run(blocks[0], 1)
+        single = sample_body / 1e6 / t1[0]
+        kind, times = cpu_reference_parallel(blocks, args.warmup + args.steps)
         times = times[args.warmup:]
-        mbps = sample_body / 1e6 / (sum(times) / len(times))
+        mean_t = sum(times) / len(times)
+        mbps = cores * sample_body / 1e6 / mean_t
         line = {"impl": "reference", "metric": METRIC, "value": mbps, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": 1, "kind": kind,
-                                 "sample": f"first 2^{int(np.log2(sample_body))} B of the workload text + sentinel; the reference is single-threaded"},
+                "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": kind, "single_core": single,
+                                 "sample": f"{cores} consecutive blocks of 2^{int(np.log2(sample_body))} B of the workload text (+ sentinel each), "
+                                           f"one single-threaded reference process per block, all {cores} at once; single_core = one block alone"},
                 "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0

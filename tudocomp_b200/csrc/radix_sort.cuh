@@ -18,6 +18,9 @@ namespace tdc {
 #ifndef RS_IPT64_CFG
 #define RS_IPT64_CFG 16
 #endif
+#ifndef RS_LOOKBACK_W
+#define RS_LOOKBACK_W 4
+#endif
 #ifndef RS_MIN_CTAS_CFG
 #define RS_MIN_CTAS_CFG 3
 #endif
@@ -169,19 +172,18 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 d = u32(key[k] >> shift) & mask;
         const u32 peers = match_digit(d, mask);
         const u32 before = __popc(peers & lanemask_lt());
+#ifdef RS_RANK_ATOMIC
+        // the group's first lane reserves the group's slots in the warp's counter and hands the old count to its peers
+        u32 c = 0;
+        if (before == 0) c = atomicAdd(&my_cnt[d], u32(__popc(peers)));
+        c = __shfl_sync(kFull, c, __ffs(int(peers)) - 1);
+#else
         const u32 c = my_cnt[d];
         __syncwarp();
         if (before == 0) my_cnt[d] = c + __popc(peers);
         __syncwarp();
+#endif
         rank[k] = c + before;
-    }
-    // fetch the values now: their latency overlaps the digit scan and the look-back instead of sitting, exposed, between
-    // the last barrier and the staging stores (ncu: long-scoreboard stalls 6.2 per issue, profiles/r1d_ncu_summary.md)
-    u32 val[IPT];
-#pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        const u64 idx = wbase + u32(k) * 32 + lane;
-        val[k] = IOTA ? u32(idx) : (idx < m ? vin[idx] : 0u);
     }
     __syncthreads();
 
@@ -212,13 +214,28 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         ull* my_desc = desc + u64(tile) * RS_RADIX + tid;
         u32 exclusive = 0;
         if (tile != 0) {
-            const ull* look = my_desc - RS_RADIX;
-            while (true) {
-                const ull v = desc_load(look);
-                if ((v >> 34) != ull(epoch) || ((v >> 32) & 3) == 0) continue;  // predecessor not published yet
-                exclusive += u32(v);
-                if (((v >> 32) & 3) == RS_STATUS_PREFIX) break;
-                look -= RS_RADIX;
+            // A window of RS_LOOKBACK_W predecessors is fetched with independent loads and then consumed in order: the
+            // serial chain "load, test, step back" was 40 % of the kernel's stall samples (~16 dependent L2 round trips
+            // per tile, profiles/r1g_ncu_summary.md).  Entries behind the first PREFIX are ignored; a window that meets an
+            // unpublished predecessor is re-polled from there.  Indices below tile 0 are clamped to tile 0, whose PREFIX
+            // always ends the walk.
+            u32 t = tile - 1;  // nearest predecessor not yet consumed
+            bool done = false;
+            while (!done) {
+                ull v[RS_LOOKBACK_W];
+#pragma unroll
+                for (int w = 0; w < RS_LOOKBACK_W; w++) {
+                    const u32 tw = t >= u32(w) ? t - u32(w) : 0u;
+                    v[w] = desc_load(desc + u64(tw) * RS_RADIX + tid);
+                }
+#pragma unroll
+                for (int w = 0; w < RS_LOOKBACK_W; w++) {
+                    if (done) break;
+                    const u32 status = u32(v[w] >> 32) & 3u;
+                    if ((v[w] >> 34) != ull(epoch) || status == 0) break;  // not published yet: poll again from here
+                    exclusive += u32(v[w]);
+                    if (status == RS_STATUS_PREFIX) done = true; else t--;
+                }
             }
         }
         desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
@@ -233,7 +250,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
         const u64 idx = wbase + u32(k) * 32 + lane;
         skeys[p] = key[k];
-        if (idx < m) svals[p] = val[k];
+        if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];  // (prefetching these before the look-back measured 20 % slower)
     }
     __syncthreads();
 
