@@ -144,7 +144,8 @@ int tdcgpu_dist_sync(tdcgpu_dist* h);
 int tdcgpu_dist_event_record(tdcgpu_dist* h, int slot);
 int tdcgpu_dist_event_elapsed_ms(tdcgpu_dist* h, int slot_a, int slot_b, float* ms);
 /* [0] rounds, [1] sum of active suffixes (this rank), [2] radix passes, [3] elements moved by them, [4] alphabet,
- * [5] symbols per initial key, [6] per-rank element capacity, [7] total number of factors */
+ * [5] symbols per initial key, [6] per-rank element capacity, [7] transport of the exchanges: 1 = pushed through peer
+ * memory (CUDA IPC mappings of the peers' scratch arenas, NVLink), 0 = NCCL send/recv */
 int tdcgpu_dist_stats(tdcgpu_dist* h, uint64_t out[8]);
 int tdcgpu_dist_phase_count(tdcgpu_dist* h);
 const char* tdcgpu_dist_phase_name(tdcgpu_dist* h, int i);

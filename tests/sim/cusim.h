@@ -396,6 +396,9 @@ inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b)
     *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count(); return 0;
 }
 static const unsigned cudaStreamNonBlocking = 1;
+static const unsigned cudaEventDisableTiming = 2;
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = new cudaEvent_st(); return 0; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return 0; }
 static const unsigned cudaHostRegisterDefault = 0;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }

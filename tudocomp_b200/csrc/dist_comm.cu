@@ -1,6 +1,7 @@
 // Comm implementations (see dist_comm.h).
 #include "dist_comm.h"
 
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -107,7 +108,9 @@ struct NcclComm : Comm {
     uint8_t* d_stage = nullptr;  // [(1 + nranks) * STAGE] device staging of the host all-gather
     uint8_t* h_stage = nullptr;  // pinned mirror
     static const size_t STAGE = size_t(1) << 20;
+    void* mapped[64] = {nullptr};  // peer mappings of the registered window (cudaIpcOpenMemHandle)
     ~NcclComm() override {
+        close_window();
         if (comm) g_nccl.CommDestroy(comm);
         if (d_stage) cudaFree(d_stage);
         if (h_stage) cudaFreeHost(h_stage);
@@ -138,6 +141,43 @@ struct NcclComm : Comm {
             TDC_NCCL(g_nccl.GroupEnd());
         }
         return 0;  // stream-ordered: consumers run on the same stream
+    }
+    // CUDA IPC: one process per GPU, so a peer's allocation is mapped through an IPC handle passed over the host all-gather
+    int open_window(void* local, size_t bytes, void** peers) override {
+        (void)bytes;
+        close_window();
+        if (nranks == 1) { peers[0] = local; return 0; }
+        if (getenv("TDCGPU_DIST_NO_P2P")) return -1;
+        struct Item { cudaIpcMemHandle_t h; int dev; int ok; };
+        Item mine;
+        memset(&mine, 0, sizeof(mine));
+        mine.ok = cudaIpcGetMemHandle(&mine.h, local) == cudaSuccess ? 1 : 0;
+        cudaGetDevice(&mine.dev);
+        std::vector<Item> all(nranks);
+        if (allgather_host(&mine, all.data(), sizeof(Item)) < 0) return -1;
+        int good = 1;
+        for (int p = 0; p < nranks; p++) good &= all[p].ok;
+        if (good) {
+            for (int p = 0; p < nranks && good; p++) {
+                if (p == rank) { peers[p] = local; continue; }
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[p].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { good = 0; break; }
+                mapped[p] = ptr;
+                peers[p] = ptr;
+            }
+        }
+        cudaGetLastError();  // clear a sticky-free error state of a failed probe
+        // all or nothing: a rank that could not map must not leave the others on a different transport
+        int flag = good, sum = 0;
+        std::vector<int> flags(nranks);
+        if (allgather_host(&flag, flags.data(), sizeof(int)) < 0) return -1;
+        for (int p = 0; p < nranks; p++) sum += flags[p];
+        if (sum != nranks) { close_window(); return -1; }
+        return 0;
+    }
+    void close_window() override {
+        for (int p = 0; p < 64; p++)
+            if (mapped[p]) { cudaIpcCloseMemHandle(mapped[p]); mapped[p] = nullptr; }
     }
 };
 

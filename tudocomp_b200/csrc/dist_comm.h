@@ -16,6 +16,12 @@ struct Comm {
     // DEVICE buffers; byte offsets and byte counts per peer; returns after the data has arrived
     virtual int alltoallv(const void* dsend, const u64* soff, const u64* scnt, void* drecv, const u64* roff, const u64* rcnt,
                           cudaStream_t st) = 0;
+    // Peer-memory transport (NVLink / NVSwitch): every rank registers ONE device allocation of the same size (the scratch
+    // arena); peers[p] receives a pointer through which rank p's allocation can be read and written from this rank's
+    // kernels and copies (peers[rank] = local).  Returns < 0 when the transport is not available (the caller then keeps
+    // using alltoallv).  Collective.  close_window unmaps.
+    virtual int open_window(void* local, size_t bytes, void** peers) { (void)local; (void)bytes; (void)peers; return -1; }
+    virtual void close_window() {}
 };
 
 #ifdef TDC_CUSIM

@@ -47,6 +47,12 @@ struct DistCtx {
     ull* h_counts = nullptr;  // pinned, [64]
     u64 total_factors = 0;
     std::vector<u64> xchg;  // scratch for count matrices
+    // peer-memory transport: the scratch arena of every rank mapped into this process (nullptr: NCCL send/recv instead)
+    bool p2p = false;
+    void* peer_arena[DIST_MAX_RANKS] = {nullptr};
+    cudaStream_t copy_streams[DIST_MAX_RANKS] = {};
+    cudaEvent_t copy_events[DIST_MAX_RANKS + 1] = {};
+    u64 p2p_bytes = 0, nccl_bytes = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -58,19 +64,78 @@ static int exchange_matrix(DistCtx& d, const u64* send_cnt, std::vector<u64>& ma
     return d.comm->allgather_host(send_cnt, matrix.data(), sizeof(u64) * d.P);
 }
 
-static int a2a_elems(DistCtx& d, const void* send, const u64* scnt, void* recv, const u64* rcnt, size_t esz) {
-    u64 soff[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], sb[DIST_MAX_RANKS], rb[DIST_MAX_RANKS];
-    u64 so = 0, ro = 0;
-    for (int p = 0; p < d.P; p++) {
-        soff[p] = so * esz; roff[p] = ro * esz;
-        sb[p] = scnt[p] * esz; rb[p] = rcnt[p] * esz;
+// All-to-all of n_arrays arrays that share one count matrix (matrix[r * P + p] = elements rank r sends to rank p): the
+// elements for peer p start at sum_{q<p} matrix[rank][q] in every send array and arrive at sum_{r<rank} matrix[r][p] in
+// p's receive array.
+//   peer-memory transport: the receive buffers live in the scratch arenas, which every rank has mapped; the ranks tell
+//   each other the arena offsets of their receive buffers, then one device-to-device copy per peer and array is pushed
+//   over NVLink on P-1 side streams; stream sync + host barrier (the data of all peers has landed).
+//   otherwise: grouped ncclSend/ncclRecv.
+static int a2a_multi(DistCtx& d, int n_arrays, const void* const* sends, void* const* recvs, const size_t* esz, const u64* matrix) {
+    const int P = d.P, rank = d.rank;
+    u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS], soff[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], remote_off[DIST_MAX_RANKS];
+    u64 so = 0, ro = 0, sent = 0;
+    for (int p = 0; p < P; p++) {
+        scnt[p] = matrix[size_t(rank) * P + p];
+        rcnt[p] = matrix[size_t(p) * P + rank];
+        soff[p] = so; roff[p] = ro;
         so += scnt[p]; ro += rcnt[p];
+        remote_off[p] = 0;
+        for (int r = 0; r < rank; r++) remote_off[p] += matrix[size_t(r) * P + p];
+        if (p != rank) sent += scnt[p];
     }
+    cudaStream_t st = d.c.stream;
+    if (d.p2p) {
 #ifndef TDC_CUSIM
-    LaunchScope timed("nccl_alltoallv", d.c.stream, false);  // shows up in the per-kernel profile, not in the launch count
+        LaunchScope timed("p2p_alltoallv", st, false);
 #endif
-    prof_add_bytes("nccl_alltoallv", double(so - scnt[d.rank]) * double(esz));  // bytes this rank sends to other ranks
-    return d.comm->alltoallv(send, soff, sb, recv, roff, rb, d.c.stream);
+        // Which of its buffers a rank receives into is rank-specific (the ping-pong side a radix sort ends on depends on
+        // the passes it could skip), so the receive offsets inside the arenas are exchanged; this all-gather is also the
+        // "ready to receive" barrier: every rank has finished reading what is about to be overwritten.
+        u64 my_off[4] = {0, 0, 0, 0};
+        if (n_arrays > 4) { set_error("a2a_multi: too many arrays"); return TDCGPU_ERR_INTERNAL; }
+        for (int a = 0; a < n_arrays; a++) my_off[a] = u64(static_cast<const uint8_t*>(recvs[a]) - d.c.arena.base);
+        std::vector<u64> peer_off(size_t(P) * 4);
+        TDC_TRY(d.comm->allgather_host(my_off, peer_off.data(), sizeof(my_off)));
+        u64 bytes = 0;
+        TDC_CUDA(cudaEventRecord(d.copy_events[DIST_MAX_RANKS], st));
+        for (int p = 0; p < P; p++) {
+            if (scnt[p] == 0) continue;
+            cudaStream_t cs = p == rank ? st : d.copy_streams[p];
+            if (p != rank) TDC_CUDA(cudaStreamWaitEvent(cs, d.copy_events[DIST_MAX_RANKS], 0));
+            for (int a = 0; a < n_arrays; a++) {
+                uint8_t* dst = static_cast<uint8_t*>(d.peer_arena[p]) + peer_off[size_t(p) * 4 + a] + remote_off[p] * esz[a];
+                const uint8_t* src = static_cast<const uint8_t*>(sends[a]) + soff[p] * esz[a];
+                TDC_CUDA(cudaMemcpyAsync(dst, src, scnt[p] * esz[a], cudaMemcpyDeviceToDevice, cs));
+                if (p != rank) bytes += scnt[p] * esz[a];
+            }
+            if (p != rank) {
+                TDC_CUDA(cudaEventRecord(d.copy_events[p], cs));
+                TDC_CUDA(cudaStreamWaitEvent(st, d.copy_events[p], 0));
+            }
+        }
+        prof_add_bytes("p2p_alltoallv", double(bytes));
+        d.p2p_bytes += bytes;
+        TDC_CUDA(cudaStreamSynchronize(st));
+        u64 token = 1;
+        std::vector<u64> all(P);
+        return d.comm->allgather_host(&token, all.data(), sizeof(u64));  // barrier: every rank's pushes are complete
+    }
+    for (int a = 0; a < n_arrays; a++) {
+        u64 sb[DIST_MAX_RANKS], rb[DIST_MAX_RANKS], sob[DIST_MAX_RANKS], rob[DIST_MAX_RANKS];
+        for (int p = 0; p < P; p++) { sb[p] = scnt[p] * esz[a]; rb[p] = rcnt[p] * esz[a]; sob[p] = soff[p] * esz[a]; rob[p] = roff[p] * esz[a]; }
+#ifndef TDC_CUSIM
+        LaunchScope timed("nccl_alltoallv", st, false);  // shows up in the per-kernel profile, not in the launch count
+#endif
+        prof_add_bytes("nccl_alltoallv", double(sent) * double(esz[a]));
+        d.nccl_bytes += sent * esz[a];
+        TDC_TRY(d.comm->alltoallv(sends[a], sob, sb, recvs[a], rob, rb, st));
+    }
+    return 0;
+}
+
+static int a2a_elems(DistCtx& d, const void* send, void* recv, size_t esz, const u64* matrix) {
+    return a2a_multi(d, 1, &send, &recv, &esz, matrix);
 }
 
 // one value per rank
@@ -121,9 +186,12 @@ static int dist_scatter(DistCtx& d, const u32* idx, const u32* val, u64 m, u32* 
     u64 R = 0;
     for (int p = 0; p < d.P; p++) { rcnt[p] = d.xchg[size_t(p) * d.P + d.rank]; R += rcnt[p]; }
     if (R > d.cap) { set_error("dist_scatter: %llu updates exceed the shard capacity", (unsigned long long)R); return TDCGPU_ERR_INTERNAL; }
-    TDC_TRY(a2a_elems(d, bufs[0], scnt, bufs[2], rcnt, 4));
-    TDC_TRY(a2a_elems(d, bufs[1], scnt, bufs[3], rcnt, 4));
-    if (val2) TDC_TRY(a2a_elems(d, bufs[6], scnt, bufs[7], rcnt, 4));
+    {
+        const void* sends[3] = {bufs[0], bufs[1], val2 ? bufs[6] : nullptr};
+        void* recvs[3] = {bufs[2], bufs[3], val2 ? bufs[7] : nullptr};
+        const size_t esz[3] = {4, 4, 4};
+        TDC_TRY(a2a_multi(d, val2 ? 3 : 2, sends, recvs, esz, d.xchg.data()));
+    }
     u32* si[2] = {bufs[2], bufs[4]};
     u32* sv[2] = {bufs[3], bufs[5]};
     TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si, sv, R, dst_shard, d.pos_cnt, R == d.pos_cnt));
@@ -257,8 +325,12 @@ static int dist_build_sa(DistCtx& d) {
     }
     d.slot_cnt = d.slot_cnts[d.rank];
     for (int p = 0; p < P; p++) rcnt[p] = d.xchg[size_t(p) * P + d.rank];
-    TDC_TRY(a2a_elems(d, K[1], scnt, K[0], rcnt, 8));  // ALL-TO-ALL #1: keys ...
-    TDC_TRY(a2a_elems(d, V[1], scnt, V[0], rcnt, 4));  // ... and suffix ids
+    {
+        const void* sends[2] = {K[1], V[1]};  // ALL-TO-ALL #1: keys and suffix ids
+        void* recvs[2] = {K[0], V[0]};
+        const size_t esz[2] = {8, 4};
+        TDC_TRY(a2a_multi(d, 2, sends, recvs, esz, d.xchg.data()));
+    }
     const u64 mr = d.slot_cnt;
     int res = 0;
     TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, K, V, mr, 0, int(sigbits), false, &res));
@@ -296,9 +368,14 @@ static int dist_build_sa(DistCtx& d) {
         u64 R = 0;
         for (int p = 0; p < P; p++) { rcnt[p] = d.xchg[size_t(p) * P + d.rank]; R += rcnt[p]; }
         if (R > cap) { set_error("dist suffix array: request overflow"); return TDCGPU_ERR_INTERNAL; }
-        TDC_TRY(a2a_elems(d, S[1], scnt, S[3], rcnt, 4));
+        TDC_TRY(a2a_elems(d, S[1], S[3], 4, d.xchg.data()));
         if (R) TDC_LAUNCH(gather_u32_kernel, u32(div_up(R, 256)), 256, 0, st, d.d_rank, S[3], R, S[0]);
-        TDC_TRY(a2a_elems(d, S[0], rcnt, S[1], scnt, 4));
+        {
+            std::vector<u64> back(size_t(P) * P);  // the replies travel the transposed way
+            for (int r = 0; r < P; r++)
+                for (int p = 0; p < P; p++) back[size_t(r) * P + p] = d.xchg[size_t(p) * P + r];
+            TDC_TRY(a2a_elems(d, S[0], S[1], 4, back.data()));
+        }
         if (m) {
             TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256)), 256, 0, st, S[2], S[1], m, S[3]);
             TDC_LAUNCH(build_keys_from_kernel, u32(div_up(m, 256)), 256, 0, st, G, S[3], m, rbits, K[0]);
@@ -408,10 +485,10 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
     u32* src_t = c.arena.take<u32>(cap + 64);
     WalkQuery* qb[6];  // up A/B, down A/B, received up, received down
     for (int i = 0; i < 6; i++) qb[i] = c.arena.take<WalkQuery>(qcap);
-    WalkAnswer* ab[3];  // answers up, answers down, received answers
-    for (int i = 0; i < 3; i++) ab[i] = c.arena.take<WalkAnswer>(qcap);
+    WalkAnswer* ab[4];  // answers up, answers down, received answers up / down
+    for (int i = 0; i < 4; i++) ab[i] = c.arena.take<WalkAnswer>(qcap);
     u32* d_cnt = c.d_scalars + 8;  // [4]
-    if (!W[9] || !lenside_t || !src_t || !qb[5] || !ab[2]) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+    if (!W[9] || !lenside_t || !src_t || !qb[5] || !ab[3]) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
     u32 *lu = W[0], *su = W[1], *ld = W[2], *sd = W[3];
 
     // ---- LPF per slot; walks leaving the shard are queued ----
@@ -437,17 +514,16 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
         for (u64 x : all) { outstanding += x; worst = std::max(worst, x); }
         if (worst > qcap) { set_error("dist lzss_lcp: %llu PSV/NSV walks leave a shard (capacity %llu)", (unsigned long long)worst, (unsigned long long)qcap); return TDCGPU_ERR_NOMEM; }
         if (outstanding == 0) break;
-        // queries: up-queue to rank-1, down-queue to rank+1
-        u64 sc[DIST_MAX_RANKS] = {0}, rc[DIST_MAX_RANKS] = {0};
-        if (rank > 0) sc[rank - 1] = cu;
+        // queries: up-queue to rank-1, down-queue to rank+1 (every rank knows every count: full matrices)
+        std::vector<u64> mx(size_t(P) * P);
+        std::fill(mx.begin(), mx.end(), 0);
+        for (int r = 1; r < P; r++) mx[size_t(r) * P + (r - 1)] = all[size_t(r) * 2];
         const u64 nru = rank + 1 < P ? all[size_t(rank + 1) * 2] : 0;
-        if (rank + 1 < P) rc[rank + 1] = nru;
-        TDC_TRY(a2a_elems(d, qb[cur], sc, qb[4], rc, sizeof(WalkQuery)));
-        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
-        if (rank + 1 < P) sc[rank + 1] = cd;
+        TDC_TRY(a2a_elems(d, qb[cur], qb[4], sizeof(WalkQuery), mx.data()));
+        std::fill(mx.begin(), mx.end(), 0);
+        for (int r = 0; r + 1 < P; r++) mx[size_t(r) * P + (r + 1)] = all[size_t(r) * 2 + 1];
         const u64 nrd = rank > 0 ? all[size_t(rank - 1) * 2 + 1] : 0;
-        if (rank > 0) rc[rank - 1] = nrd;
-        TDC_TRY(a2a_elems(d, qb[2 + cur], sc, qb[5], rc, sizeof(WalkQuery)));
+        TDC_TRY(a2a_elems(d, qb[2 + cur], qb[5], sizeof(WalkQuery), mx.data()));
         // resolve against my tree
         TDC_CUDA(cudaMemsetAsync(d_cnt, 0, 4 * sizeof(u32), st));
         if (nru) {
@@ -465,18 +541,16 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
         // answers straight back to the origin: up-queries seen at this hop came from rank + hop, down from rank - hop
         u64 am[2] = {au, ad};
         TDC_TRY(allgather_u64(d, am, 2, all));
-        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
-        if (rank + hop < P) sc[rank + hop] = au;
+        std::fill(mx.begin(), mx.end(), 0);
+        for (int r = 0; r + hop < P; r++) mx[size_t(r) * P + (r + hop)] = all[size_t(r) * 2];
         const u64 rau = rank - hop >= 0 ? all[size_t(rank - hop) * 2] : 0;
-        if (rank - hop >= 0) rc[rank - hop] = rau;
-        TDC_TRY(a2a_elems(d, ab[0], sc, ab[2], rc, sizeof(WalkAnswer)));
+        TDC_TRY(a2a_elems(d, ab[0], ab[2], sizeof(WalkAnswer), mx.data()));
         if (rau) TDC_LAUNCH(apply_answers_kernel, u32(div_up(rau, 256)), 256, 0, st, ab[2], u32(rau), lu, su);
-        for (int p = 0; p < P; p++) sc[p] = rc[p] = 0;
-        if (rank - hop >= 0) sc[rank - hop] = ad;
+        std::fill(mx.begin(), mx.end(), 0);
+        for (int r = hop; r < P; r++) mx[size_t(r) * P + (r - hop)] = all[size_t(r) * 2 + 1];
         const u64 rad = rank + hop < P ? all[size_t(rank + hop) * 2 + 1] : 0;
-        if (rank + hop < P) rc[rank + hop] = rad;
-        TDC_TRY(a2a_elems(d, ab[1], sc, ab[2], rc, sizeof(WalkAnswer)));
-        if (rad) TDC_LAUNCH(apply_answers_kernel, u32(div_up(rad, 256)), 256, 0, st, ab[2], u32(rad), ld, sd);
+        TDC_TRY(a2a_elems(d, ab[1], ab[3], sizeof(WalkAnswer), mx.data()));
+        if (rad) TDC_LAUNCH(apply_answers_kernel, u32(div_up(rad, 256)), 256, 0, st, ab[3], u32(rad), ld, sd);
         TDC_KCHECK();
         cu = rank > 0 ? fu : 0;        // rank 0 has nobody above: what is still open has no PSV
         cd = rank + 1 < P ? fd : 0;
@@ -571,6 +645,15 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
 // ---------------------------------------------------------------------------------------------------------------
 static void dist_free_arrays(DistCtx& d) {
     Ctx& c = d.c;
+    if (d.p2p && d.comm) {
+        // importers unmap first, then (after a barrier) the owners free
+        cudaStreamSynchronize(c.stream);
+        d.comm->close_window();
+        u64 token = 0;
+        std::vector<u64> all(d.P);
+        d.comm->allgather_host(&token, all.data(), sizeof(u64));
+        d.p2p = false;
+    }
     void* ps[] = {c.d_text, d.d_sa, d.d_rank, d.d_lcp, c.arena.base};
     for (void* p : ps)
         if (p) cudaFree(p);
@@ -593,13 +676,22 @@ static int dist_ensure_capacity(DistCtx& d, u64 n) {
     TDC_CUDA(cudaMalloc(&d.d_sa, sizeof(u32) * cap));
     TDC_CUDA(cudaMalloc(&d.d_rank, sizeof(u32) * cap));
     TDC_CUDA(cudaMalloc(&d.d_lcp, sizeof(u32) * cap));
-    const size_t arena_bytes = size_t(72) * cap + cap / 4 + size_t(9 * 12) * d.qcap + (size_t(16) << 20);
+    const size_t arena_bytes = size_t(72) * cap + cap / 4 + size_t(10 * 12) * d.qcap + (size_t(16) << 20);
     TDC_CUDA(cudaMalloc(&c.arena.base, arena_bytes));
     c.arena.cap = arena_bytes;
     c.arena.off = 0;
     TDC_TRY(sort_workspace_init(c.sortws, cap, c.sm_count));
     c.cap_n = n;
     d.cap = cap;
+    // peer-memory transport for the exchanges: every rank maps every other rank's arena (same size, carved identically)
+    d.p2p = d.comm->open_window(c.arena.base, arena_bytes, d.peer_arena) == 0 && d.P > 1;
+    if (d.p2p) {
+        for (int p = 0; p < d.P; p++) {
+            if (p != d.rank && !d.copy_streams[p]) TDC_CUDA(cudaStreamCreateWithFlags(&d.copy_streams[p], cudaStreamNonBlocking));
+            if (!d.copy_events[p]) TDC_CUDA(cudaEventCreateWithFlags(&d.copy_events[p], cudaEventDisableTiming));
+        }
+        if (!d.copy_events[DIST_MAX_RANKS]) TDC_CUDA(cudaEventCreateWithFlags(&d.copy_events[DIST_MAX_RANKS], cudaEventDisableTiming));
+    }
     return 0;
 }
 
@@ -693,8 +785,12 @@ void tdcgpu_dist_destroy(tdcgpu_dist* h) {
     Ctx& c = d.c;
     cudaSetDevice(c.device);
     cudaStreamSynchronize(c.stream);
-    delete d.comm;
     dist_free_arrays(d);
+    for (int p = 0; p < DIST_MAX_RANKS; p++)
+        if (d.copy_streams[p]) cudaStreamDestroy(d.copy_streams[p]);
+    for (int p = 0; p <= DIST_MAX_RANKS; p++)
+        if (d.copy_events[p]) cudaEventDestroy(d.copy_events[p]);
+    delete d.comm;
     sort_workspace_free(c.sortws);
     if (c.d_factors) cudaFree(c.d_factors);
     if (c.d_scalars) cudaFree(c.d_scalars);
@@ -833,7 +929,7 @@ int tdcgpu_dist_stats(tdcgpu_dist* h, uint64_t out[8]) {
     out[4] = c.alphabet;
     out[5] = c.symbols_per_key;
     out[6] = d.cap;
-    out[7] = d.total_factors;
+    out[7] = d.p2p ? 1 : 0;  // 1: exchanges pushed through peer memory (CUDA IPC over NVLink), 0: NCCL send/recv
     return 0;
 }
 

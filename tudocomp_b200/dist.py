@@ -139,7 +139,7 @@ class DistContext:
     def stats(self) -> dict:
         buf = (C.c_uint64 * 8)()
         self.lib.check(self.lib.lib.tdcgpu_dist_stats(self._h, buf))
-        keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key", "capacity", "total_factors"]
+        keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key", "capacity", "p2p"]
         return dict(zip(keys, [int(x) for x in buf]))
 
     def phases(self):
