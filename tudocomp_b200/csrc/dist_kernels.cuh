@@ -53,16 +53,32 @@ bucket_count_kernel(const K* __restrict__ keys, u64 m, F f, int nbuckets, ull* _
     if (threadIdx.x < u32(nbuckets) && cnt[threadIdx.x]) atomicAdd(&gcount[threadIdx.x], ull(cnt[threadIdx.x]));
 }
 
-// cursor[b] starts at the bucket's first output slot; order inside a bucket is arbitrary (the consumers sort or scatter).
-// vals == nullptr: the value of element i is vbase + i.  vals2 / vout2: optional second value travelling with the first.
+// Where the elements of each bucket go.  With the peer-memory transport k[b] (and v[b], v2[b] when the values travel
+// too) point INTO RANK b's receive buffer, at the place reserved for this rank: the partition kernel's stores are the
+// all-to-all (NVLink writes), there is no send buffer and no separate exchange.  Otherwise they point at the bucket's
+// segment of a local staging buffer.  cursor[b] counts from 0; order inside a bucket is arbitrary.
+struct BucketDst {
+    void* k[DIST_MAX_RANKS];
+    u32* v[DIST_MAX_RANKS];
+    u32* v2[DIST_MAX_RANKS];
+};
+
+// vals == nullptr: the value of element i is vbase + i.  vals2: optional second value travelling with the first.
 template <class K, class F>
 static __global__ void __launch_bounds__(BP_THREADS)
 bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 vbase, u64 m, F f, int nbuckets,
-                      ull* __restrict__ cursor, K* __restrict__ kout, u32* __restrict__ vout, const u32* __restrict__ vals2,
-                      u32* __restrict__ vout2) {
+                      ull* __restrict__ cursor, BucketDst dst, const u32* __restrict__ vals2) {
     __shared__ u32 cnt[DIST_MAX_RANKS];
     __shared__ ull gbase[DIST_MAX_RANKS];
-    if (threadIdx.x < DIST_MAX_RANKS) cnt[threadIdx.x] = 0;
+    __shared__ K* kb[DIST_MAX_RANKS];
+    __shared__ u32* vb[DIST_MAX_RANKS];
+    __shared__ u32* v2b[DIST_MAX_RANKS];
+    if (threadIdx.x < DIST_MAX_RANKS) {
+        cnt[threadIdx.x] = 0;
+        kb[threadIdx.x] = static_cast<K*>(dst.k[threadIdx.x]);
+        vb[threadIdx.x] = dst.v[threadIdx.x];
+        v2b[threadIdx.x] = dst.v2[threadIdx.x];
+    }
     __syncthreads();
     const u64 t0 = u64(blockIdx.x) * BP_TILE;
     K key[BP_IPT];
@@ -89,9 +105,9 @@ bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, 
         const u64 i = t0 + u64(q) * BP_THREADS + threadIdx.x;
         if (i < m) {
             const u64 o = gbase[b[q]] + lr[q];
-            kout[o] = f.out(key[q], b[q]);
-            vout[o] = vals ? vals[i] : vbase + u32(i);
-            if (vals2) vout2[o] = vals2[i];
+            kb[b[q]][o] = f.out(key[q], b[q]);
+            vb[b[q]][o] = vals ? vals[i] : vbase + u32(i);
+            if (vals2) v2b[b[q]][o] = vals2[i];
         }
     }
 }

@@ -144,34 +144,99 @@ static int allgather_u64(DistCtx& d, const u64* mine, int words, std::vector<u64
     return d.comm->allgather_host(mine, all.data(), sizeof(u64) * words);
 }
 
+// Partition m (key, value[, value2]) elements by destination rank and deliver them.
+//   kin / vin / vin2     the elements (vin == nullptr: value i = vbase + i)
+//   kstage / vstage / v2stage   local staging, one segment per bucket (bucket order).  When send_vals is false the first
+//                        value does not travel: it stays in vstage, in the order in which the keys were sent.
+//   krecv / vrecv / v2recv      receive buffers (in the scratch arena), filled in source-rank order
+//   matrix               out: matrix[r * P + p] = elements rank r sent to rank p
+// Peer-memory transport: the count matrix and the receive-buffer offsets are all-gathered first, then ONE kernel does the
+// partition and the all-to-all: bucket b's elements are stored straight into rank b's receive buffer over NVLink (the
+// staging buffers are not touched for what travels).  Otherwise: partition into the staging buffers, then NCCL.
 template <class K, class F>
-static int bucket_partition(DistCtx& d, const K* kin, const u32* vin, u32 vbase, u64 m, F f, K* kout, u32* vout, u64* cnt_out,
-                            const u32* vin2 = nullptr, u32* vout2 = nullptr) {
+static int exchange_by_bucket(DistCtx& d, const K* kin, const u32* vin, u32 vbase, const u32* vin2, u64 m, F f, K* kstage, u32* vstage,
+                              u32* v2stage, K* krecv, u32* vrecv, u32* v2recv, bool send_vals, std::vector<u64>& matrix, u64* R_out) {
     cudaStream_t st = d.c.stream;
+    const int P = d.P, rank = d.rank;
     TDC_CUDA(cudaMemsetAsync(d.d_counts, 0, sizeof(ull) * 2 * DIST_MAX_RANKS, st));
     if (m) {
         const u32 grid = u32(std::min<u64>(u64(d.c.sm_count) * 8, div_up(m, BP_THREADS)));
         auto bucket_count = bucket_count_kernel<K, F>;
-        TDC_LAUNCH(bucket_count, grid, BP_THREADS, 0, st, kin, m, f, d.P, d.d_counts);
+        TDC_LAUNCH(bucket_count, grid, BP_THREADS, 0, st, kin, m, f, P, d.d_counts);
         TDC_KCHECK();
     }
-    TDC_CUDA(cudaMemcpyAsync(d.h_counts, d.d_counts, sizeof(ull) * d.P, cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaMemcpyAsync(d.h_counts, d.d_counts, sizeof(ull) * P, cudaMemcpyDeviceToHost, st));
     TDC_CUDA(cudaStreamSynchronize(st));
-    ull run = 0;
-    for (int p = 0; p < d.P; p++) {
-        cnt_out[p] = d.h_counts[p];
-        d.h_counts[DIST_MAX_RANKS + p] = run;
-        run += d.h_counts[p];
+    // counts + where my receive buffers are (arena offsets); this all-gather is also the "ready to receive" barrier
+    const int W = DIST_MAX_RANKS + 3;
+    u64 mine[DIST_MAX_RANKS + 3] = {0};
+    for (int p = 0; p < P; p++) mine[p] = d.h_counts[p];
+    const uint8_t* ab = d.c.arena.base;
+    mine[DIST_MAX_RANKS + 0] = u64(reinterpret_cast<const uint8_t*>(krecv) - ab);
+    mine[DIST_MAX_RANKS + 1] = vrecv ? u64(reinterpret_cast<const uint8_t*>(vrecv) - ab) : 0;
+    mine[DIST_MAX_RANKS + 2] = v2recv ? u64(reinterpret_cast<const uint8_t*>(v2recv) - ab) : 0;
+    std::vector<u64> all(size_t(P) * W);
+    TDC_TRY(d.comm->allgather_host(mine, all.data(), sizeof(u64) * W));
+    matrix.assign(size_t(P) * P, 0);
+    for (int r = 0; r < P; r++)
+        for (int p = 0; p < P; p++) matrix[size_t(r) * P + p] = all[size_t(r) * W + p];
+    u64 worst = 0;
+    for (int p = 0; p < P; p++) {
+        u64 R = 0;
+        for (int r = 0; r < P; r++) R += matrix[size_t(r) * P + p];
+        worst = std::max(worst, R);
+        if (p == rank) *R_out = R;
     }
-    TDC_CUDA(cudaMemcpyAsync(d.d_counts + DIST_MAX_RANKS, d.h_counts + DIST_MAX_RANKS, sizeof(ull) * d.P, cudaMemcpyHostToDevice, st));
+    if (worst > d.cap) {  // every rank sees the same matrix and takes the same decision
+        set_error("exchange: a rank would receive %llu elements, capacity %llu (skewed keys)", (unsigned long long)worst, (unsigned long long)d.cap);
+        return TDCGPU_ERR_NOMEM;
+    }
+    BucketDst dst;
+    u64 start = 0, sent = 0;
+    for (int p = 0; p < DIST_MAX_RANKS; p++) { dst.k[p] = nullptr; dst.v[p] = nullptr; dst.v2[p] = nullptr; }
+    for (int p = 0; p < P; p++) {
+        u64 remote_off = 0;
+        for (int r = 0; r < rank; r++) remote_off += matrix[size_t(r) * P + p];
+        if (d.p2p) {
+            uint8_t* pa = static_cast<uint8_t*>(d.peer_arena[p]);
+            dst.k[p] = pa + all[size_t(p) * W + DIST_MAX_RANKS + 0] + remote_off * sizeof(K);
+            dst.v[p] = send_vals ? reinterpret_cast<u32*>(pa + all[size_t(p) * W + DIST_MAX_RANKS + 1]) + remote_off : vstage + start;
+            dst.v2[p] = vin2 ? reinterpret_cast<u32*>(pa + all[size_t(p) * W + DIST_MAX_RANKS + 2]) + remote_off : nullptr;
+        } else {
+            dst.k[p] = kstage + start;
+            dst.v[p] = vstage + start;
+            dst.v2[p] = vin2 ? v2stage + start : nullptr;
+        }
+        start += mine[p];
+        if (p != rank) sent += mine[p];
+    }
     if (m) {
-        auto bucket_scatter = bucket_scatter_kernel<K, F>;
-        TDC_LAUNCH(bucket_scatter, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, d.P, d.d_counts + DIST_MAX_RANKS, kout, vout, vin2, vout2);
-        prof_add_bytes("bucket_scatter", double(m) * 2 * (sizeof(K) + 4 + (vin2 ? 4 : 0)));
-        TDC_KCHECK();
+        if (d.p2p) {  // same kernel; the name tells the profile that its stores are the exchange
+            auto bucket_scatter_push = bucket_scatter_kernel<K, F>;
+            TDC_LAUNCH(bucket_scatter_push, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, P, d.d_counts + DIST_MAX_RANKS, dst, vin2);
+            prof_add_bytes("bucket_scatter_push", double(m) * 2 * (sizeof(K) + 4 + (vin2 ? 4 : 0)));
+        } else {
+            auto bucket_scatter = bucket_scatter_kernel<K, F>;
+            TDC_LAUNCH(bucket_scatter, u32(div_up(m, BP_TILE)), BP_THREADS, 0, st, kin, vin, vbase, m, f, P, d.d_counts + DIST_MAX_RANKS, dst, vin2);
+            prof_add_bytes("bucket_scatter", double(m) * 2 * (sizeof(K) + 4 + (vin2 ? 4 : 0)));
+        }
     }
-    TDC_CUDA(cudaStreamSynchronize(st));  // h_counts is reused by the next call
-    return 0;
+    TDC_KCHECK();
+    const size_t per_elem = sizeof(K) + (send_vals ? 4 : 0) + (vin2 ? 4 : 0);
+    if (d.p2p) {
+        d.p2p_bytes += sent * per_elem;
+        TDC_CUDA(cudaStreamSynchronize(st));
+        u64 token = 1;
+        std::vector<u64> bar(P);
+        return d.comm->allgather_host(&token, bar.data(), sizeof(u64));  // every rank's stores have landed
+    }
+    const void* sends[3] = {kstage, nullptr, nullptr};
+    void* recvs[3] = {krecv, nullptr, nullptr};
+    size_t esz[3] = {sizeof(K), 4, 4};
+    int na = 1;
+    if (send_vals) { sends[na] = vstage; recvs[na] = vrecv; na++; }
+    if (vin2) { sends[na] = v2stage; recvs[na] = v2recv; na++; }
+    return a2a_multi(d, na, sends, recvs, esz, matrix.data());
 }
 
 // dst_shard[idx - owner*block] = val on the owner of idx (and dst2 / val2 alike when given: one partition and one
@@ -180,23 +245,14 @@ static int dist_scatter(DistCtx& d, const u32* idx, const u32* val, u64 m, u32* 
                         u32* dst2 = nullptr) {
     OwnerFn f;
     f.block = d.block;
-    u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
-    TDC_TRY((bucket_partition<u32, OwnerFn>(d, idx, val, 0, m, f, bufs[0], bufs[1], scnt, val2, val2 ? bufs[6] : nullptr)));
-    TDC_TRY(exchange_matrix(d, scnt, d.xchg));
     u64 R = 0;
-    for (int p = 0; p < d.P; p++) { rcnt[p] = d.xchg[size_t(p) * d.P + d.rank]; R += rcnt[p]; }
-    if (R > d.cap) { set_error("dist_scatter: %llu updates exceed the shard capacity", (unsigned long long)R); return TDCGPU_ERR_INTERNAL; }
-    {
-        const void* sends[3] = {bufs[0], bufs[1], val2 ? bufs[6] : nullptr};
-        void* recvs[3] = {bufs[2], bufs[3], val2 ? bufs[7] : nullptr};
-        const size_t esz[3] = {4, 4, 4};
-        TDC_TRY(a2a_multi(d, val2 ? 3 : 2, sends, recvs, esz, d.xchg.data()));
-    }
+    TDC_TRY((exchange_by_bucket<u32, OwnerFn>(d, idx, val, 0, val2, m, f, bufs[0], bufs[1], val2 ? bufs[6] : nullptr, bufs[2], bufs[3],
+                                              val2 ? bufs[7] : nullptr, true, d.xchg, &R)));
     u32* si[2] = {bufs[2], bufs[4]};
     u32* sv[2] = {bufs[3], bufs[5]};
     TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si, sv, R, dst_shard, d.pos_cnt, R == d.pos_cnt));
     if (val2) {
-        // bufs[0]/bufs[1] have been sent: free as the scratch pair of the second scatter (the received indices are intact)
+        // bufs[0]/bufs[1] are free again: scratch pair of the second scatter (the received indices are intact)
         u32* si2[2] = {bufs[2], bufs[0]};
         u32* sv2[2] = {bufs[7], bufs[1]};
         TDC_TRY(partitioned_scatter(d.c.sortws, d.c.stream, si2, sv2, R, dst2, d.pos_cnt, R == d.pos_cnt));
@@ -308,30 +364,20 @@ static int dist_build_sa(DistCtx& d) {
         std::sort(all.begin(), all.end());
         for (int i = 0; i + 1 < P; i++) sf.spl[i] = all[size_t(i + 1) * NS];
     }
-    u64 scnt[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
-    TDC_TRY((bucket_partition<u64, SplitterFn>(d, K[0], nullptr, u32(d.pos_lo), d.pos_cnt, sf, K[1], V[1], scnt)));
-    TDC_TRY(exchange_matrix(d, scnt, d.xchg));
+    // ALL-TO-ALL #1: keys and suffix ids to the rank that owns their bucket.  Peer-memory transport: received straight
+    // into K[1] / V[1] (K[0] is still being read by the partition); NCCL: staged in K[1] / V[1], received into K[0] / V[0].
+    u64* krecv = d.p2p ? K[1] : K[0];
+    u32* vrecv = d.p2p ? V[1] : V[0];
+    u64 mr = 0;
+    TDC_TRY((exchange_by_bucket<u64, SplitterFn>(d, K[0], nullptr, u32(d.pos_lo), nullptr, d.pos_cnt, sf, K[1], V[1], nullptr, krecv,
+                                                 vrecv, nullptr, true, d.xchg, &mr)));
     d.slot_cnts.assign(P, 0);
     for (int r = 0; r < P; r++)
         for (int p = 0; p < P; p++) d.slot_cnts[r] += d.xchg[size_t(p) * P + r];
     d.slot_lo = 0;
-    for (int r = 0; r < P; r++) {
-        if (d.slot_cnts[r] > cap) {
-            set_error("dist suffix array: bucket of rank %d holds %llu suffixes, capacity %llu (skewed keys)", r,
-                      (unsigned long long)d.slot_cnts[r], (unsigned long long)cap);
-            return TDCGPU_ERR_NOMEM;
-        }
-        if (r < d.rank) d.slot_lo += d.slot_cnts[r];
-    }
+    for (int r = 0; r < d.rank; r++) d.slot_lo += d.slot_cnts[r];
     d.slot_cnt = d.slot_cnts[d.rank];
-    for (int p = 0; p < P; p++) rcnt[p] = d.xchg[size_t(p) * P + d.rank];
-    {
-        const void* sends[2] = {K[1], V[1]};  // ALL-TO-ALL #1: keys and suffix ids
-        void* recvs[2] = {K[0], V[0]};
-        const size_t esz[2] = {8, 4};
-        TDC_TRY(a2a_multi(d, 2, sends, recvs, esz, d.xchg.data()));
-    }
-    const u64 mr = d.slot_cnt;
+    if (d.p2p) { std::swap(K[0], K[1]); std::swap(V[0], V[1]); }  // the received pairs are the sort's input, slot 0
     int res = 0;
     TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, K, V, mr, 0, int(sigbits), false, &res));
     u64 m = 0, g = 0;
@@ -363,12 +409,9 @@ static int dist_build_sa(DistCtx& d) {
         u32* Vact = V[res ^ 1];
         // rank[suffix + h] from its owner: request / reply
         if (m) TDC_LAUNCH(add_offset_kernel, u32(div_up(m, 256)), 256, 0, st, Vact, m, u32(h), S[0]);
-        TDC_TRY((bucket_partition<u32, OwnerFn>(d, S[0], nullptr, 0u, m, of, S[1], S[2], scnt)));
-        TDC_TRY(exchange_matrix(d, scnt, d.xchg));
-        u64 R = 0;
-        for (int p = 0; p < P; p++) { rcnt[p] = d.xchg[size_t(p) * P + d.rank]; R += rcnt[p]; }
-        if (R > cap) { set_error("dist suffix array: request overflow"); return TDCGPU_ERR_INTERNAL; }
-        TDC_TRY(a2a_elems(d, S[1], S[3], 4, d.xchg.data()));
+        u64 R = 0;  // requests (owner-local positions) travel to S[3] of the owner; the origin slots stay here, in S[2]
+        TDC_TRY((exchange_by_bucket<u32, OwnerFn>(d, S[0], nullptr, 0u, nullptr, m, of, S[1], S[2], nullptr, S[3], nullptr, nullptr, false,
+                                                  d.xchg, &R)));
         if (R) TDC_LAUNCH(gather_u32_kernel, u32(div_up(R, 256)), 256, 0, st, d.d_rank, S[3], R, S[0]);
         {
             std::vector<u64> back(size_t(P) * P);  // the replies travel the transposed way
