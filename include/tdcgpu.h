@@ -81,6 +81,31 @@ int tdcgpu_lzss_lcp_factorize(tdcgpu_ctx* ctx, uint32_t threshold, uint64_t* cou
 /* Copy the factor list (position order, FactorBuffer::is_sorted() holds) to a caller buffer of `cap` records. */
 int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t cap, int to_device);
 
+/* ---- lzss::encode_text on the device (compressors/lzss/LZSSCoding.hpp:18-92) -------------------------------------
+ * For coders that write integers as plain binary of bits_for(range) bits (the tdc::Encoder default, Coder.hpp:63-80)
+ * and every literal as one fixed code word: BitCoder (coders/BitCoder.hpp) and HuffmanCoder
+ * (coders/HuffmanCoder.hpp:519-570).  The factor list of the last tdcgpu_lzss_lcp_factorize call and the text stay on
+ * the device; only the literal histogram comes back before, and the finished bit stream after.
+ *
+ * Histogram of the literals lzss::TextLiterals iterates (lzss/LZSSLiterals.hpp:10-56: every text position outside a
+ * factor, incl. the final 0) — what huff::count_alphabet_literals counts (coders/HuffmanCoder.hpp:37-49) — and
+ * fdist_max, the longest literal run (LZSSCoding.hpp:29-41). */
+int tdcgpu_lzss_literal_histogram(tdcgpu_ctx* ctx, uint64_t hist[256], uint64_t* fdist_max);
+
+/* Encode n, flen_min, flen_max, fdist_max and the factor/literal items exactly as lzss::encode_text does
+ * (LZSSCoding.hpp:46-91), bits MSB first (io/BitOStream.hpp:79-102).  codes[c]/lens[c]: the coder's word for literal c
+ * (low lens[c] bits of codes[c], lens[c] <= 64; BitCoder: c in 8 bits; HuffmanCoder: codewords[map_to_effective[c]],
+ * coders/HuffmanCoder.hpp:309-322).  The coder's own header already occupies `lead_bits` (0..7) bits of the current
+ * byte `lead_byte` (its high bits); the device stream starts with that partial byte so that it can be appended to the
+ * header's whole bytes.  *nbits = stream length in bits incl. lead_bits. */
+int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t lens[256], uint32_t lead_bits,
+                       uint8_t lead_byte, uint64_t* nbits);
+
+/* Copy the stream to `dst` (cap bytes).  finalize != 0 appends what BitOStream::~BitOStream writes
+ * (io/BitOStream.hpp:53-64: the number of bits used in the last byte goes into its low 3 bits, or into an extra byte when
+ * fewer than 3 bits are free).  *nbytes = bytes written (ceil(nbits / 8), + at most 1 when finalized). */
+int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device);
+
 /* One-shot host-buffer convenience used by the C++ provider shims: text in, arrays out (NULL = not wanted).
  * Same semantics as constructing TextDS<>(env, view, flags) and reading the providers. */
 int tdcgpu_textds_build_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp,

@@ -31,6 +31,8 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
     c.num_factors = 0;
     c.flen_min = 0xffffffffu;
     c.flen_max = 0;
+    c.have_factors = true;
+    c.enc.prepared = c.enc.encoded = false;
     if (n <= 1) return 0;
 
     c.arena.reset();

@@ -25,7 +25,8 @@ struct PhaseTime {
 struct Arena {
     uint8_t* base = nullptr;
     size_t cap = 0, off = 0;
-    void reset() { off = 0; }
+    u64 gen = 0;  // bumped by every reset: state carved before a reset is stale afterwards (EncodeState)
+    void reset() { off = 0; gen++; }
     template <class T>
     T* take(size_t count) {
         size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
@@ -34,6 +35,23 @@ struct Arena {
         off += bytes;
         return p;
     }
+};
+
+// Device-side lzss::encode_text (lzss_encode.cu): masks and scans derived from the factor list, then the bit stream.
+// Everything lives in the scratch arena and is valid only while arena.gen == gen.
+struct EncodeState {
+    u64 gen = 0;
+    bool prepared = false, encoded = false;
+    u32 *S = nullptr, *E = nullptr, *scan_s = nullptr, *scan_e = nullptr, *tile_bits = nullptr;
+    u64* tile_off = nullptr;
+    u64* d_code = nullptr;       // 256 code words
+    uint8_t* d_len = nullptr;    // 256 code lengths
+    uint8_t* out = nullptr;      // bit stream, MSB first
+    u64 out_cap = 0;             // bytes
+    u32 ntiles = 0;
+    u32 fdist_max = 0;
+    u64 hist[256];
+    u64 nbits = 0;
 };
 
 struct Ctx {
@@ -56,6 +74,8 @@ struct Ctx {
     Factor* d_factors = nullptr;
     u64 factors_cap = 0, num_factors = 0;
     u32 flen_min = 0xffffffffu, flen_max = 0;
+    bool have_factors = false;  // factorize_lzss_lcp has run on the current text
+    EncodeState enc;
 
     // scratch
     Arena arena;
@@ -91,6 +111,9 @@ int build_lcp_direct(Ctx& c);  // LCP without Phi/PLCP (texts with short common 
 static const u32 LCP_UNKNOWN = 0xffffffffu;  // LCP slot of a pair the initial keys could not separate
 // lzss_factorize.cu
 int factorize_lzss_lcp(Ctx& c, u32 threshold);
+// lzss_encode.cu
+int encode_prepare(Ctx& c);  // masks, scans, literal histogram, fdist_max of the current factor list
+int encode_lzss(Ctx& c, const u64* codes, const uint8_t* lens, u32 lead_bits, u32 lead_byte);
 
 struct PhaseTimer {  // CUDA-event timing of one phase on the context's stream
     Ctx& c;

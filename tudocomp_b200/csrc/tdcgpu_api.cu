@@ -278,6 +278,8 @@ int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_dev
     c.have = 0;
     c.max_lcp = 0;
     c.num_factors = 0;
+    c.have_factors = false;
+    c.enc.prepared = c.enc.encoded = false;
     c.phases.clear();
     TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
     TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, TEXT_PAD + 16, c.stream));
@@ -338,6 +340,56 @@ int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t ca
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors,
                              to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_lzss_literal_histogram(tdcgpu_ctx* ctx, uint64_t hist[256], uint64_t* fdist_max) {
+    API_GUARD(ctx);
+    c.phases.clear();
+    {
+        PhaseTimer t(c, "Encode: literal histogram");
+        TDC_TRY(encode_prepare(c));
+    }
+    if (hist) memcpy(hist, c.enc.hist, sizeof(uint64_t) * 256);
+    if (fdist_max) *fdist_max = c.enc.fdist_max;
+    return 0;
+}
+
+int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t lens[256], uint32_t lead_bits,
+                       uint8_t lead_byte, uint64_t* nbits) {
+    API_GUARD(ctx);
+    if (!codes || !lens) { set_error("null code table"); return TDCGPU_ERR_ARG; }
+    c.phases.clear();
+    {
+        PhaseTimer t(c, "Encode: bit stream");
+        TDC_TRY(encode_lzss(c, codes, lens, lead_bits, lead_byte));
+    }
+    if (nbits) *nbits = c.enc.nbits;
+    return 0;
+}
+
+int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
+    API_GUARD(ctx);
+    if (!c.enc.encoded || c.enc.gen != c.arena.gen) { set_error("no encoded stream (call tdcgpu_lzss_encode first)"); return TDCGPU_ERR_STATE; }
+    const u64 nbits = c.enc.nbits, whole = nbits / 8;
+    const u32 used = u32(nbits % 8);
+    // BitOStream::~BitOStream (io/BitOStream.hpp:53-64): `used` goes into the low 3 bits of the current byte if they are
+    // free (used <= 5; an untouched byte is written as 0), otherwise the byte is flushed and `used` follows in its own byte
+    const u64 total = finalize ? whole + (used <= 5 ? 1 : 2) : whole + (used ? 1 : 0);
+    if (nbytes) *nbytes = total;
+    if (total > cap) { set_error("encode buffer too small: %llu > %llu", (unsigned long long)total, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    const u64 body = whole + (used ? 1 : 0);
+    TDC_CUDA(cudaMemcpyAsync(dst, c.enc.out, body, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (finalize) {
+        uint8_t tail[2] = {0, 0};
+        if (used) TDC_CUDA(cudaMemcpyAsync(&tail[0], c.enc.out + whole, 1, cudaMemcpyDeviceToHost, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));
+        u64 ntail;
+        if (used <= 5) { tail[0] |= uint8_t(used); ntail = 1; } else { tail[1] = uint8_t(used); ntail = 2; }
+        TDC_CUDA(cudaMemcpyAsync(dst + whole, tail, ntail, to_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, c.stream));
+    }
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
