@@ -212,6 +212,57 @@ int64_t tdcref_lzss_lcp_compress(const uint8_t* text, uint64_t n, uint32_t thres
     return int64_t(res.size());
 }
 
+// What HuffmanCoder::Encoder's constructor does with the literal counts (coders/HuffmanCoder.hpp:526-548), driven by a
+// histogram instead of a literal iterator: header bits as written by the reference's own BitOStream /
+// huff::huffmantable_encode, and the code word of every literal as huff::huffman_encode would write it (:309-322).
+// header receives the whole header bytes plus the partial last byte; *header_bits = exact bit count.
+// coder: 0=bit (no header, literals in 8 bits, Coder.hpp:63-66 via LiteralRange), 1=huff.
+int tdcref_literal_coder(int coder, const uint64_t hist[256], uint8_t* header, uint64_t cap, uint64_t* header_bits,
+                         uint64_t codes[256], uint8_t lens[256]) {
+    return guarded([&] {
+        std::vector<uint8_t> head;
+        for (int c = 0; c < 256; c++) { codes[c] = uint64_t(c); lens[c] = 8; }
+        {
+            Output ho = Output::from_memory(head);
+            BitOStream bos(ho);
+            if (coder == 1) {
+                len_compact_t* C = new len_compact_t[ULITERAL_MAX + 1];
+                for (int c = 0; c < 256; c++) C[c] = len_compact_t(hist[c]);
+                const len_t alphabet_size = huff::effective_alphabet_size(C);
+                if (alphabet_size <= 1) {
+                    delete[] C;
+                    bos.write_bit(0);
+                } else {
+                    huff::extended_huffmantable table = huff::gen_huffmantable(C);  // deletes C
+                    bos.write_bit(1);
+                    huff::huffmantable_encode(bos, table);
+                    for (int c = 0; c < 256; c++) { codes[c] = 0; lens[c] = 0; }
+                    for (size_t i = 0; i < table.alphabet_size; i++) {
+                        codes[table.ordered_map_from_effective[i]] = table.codewords[i];
+                        lens[table.ordered_map_from_effective[i]] = table.ordered_codelengths[i];
+                    }
+                }
+            } else if (coder != 0) {
+                throw std::runtime_error("unknown coder id");
+            }
+        }  // ~BitOStream appends its tail (io/BitOStream.hpp:53-64); undo it to get the exact bit count
+        const uint8_t last = head.back();
+        const unsigned used = last & 7u;
+        uint64_t bits;
+        if (used <= 5) {
+            bits = 8 * uint64_t(head.size() - 1) + used;
+            head.back() = uint8_t(last & ~7u);
+        } else {
+            bits = 8 * uint64_t(head.size() - 2) + used;
+            head.pop_back();
+        }
+        if (bits % 8 == 0 && !head.empty() && head.size() * 8 > bits) head.pop_back();
+        if (head.size() > cap) throw std::runtime_error("header buffer too small");
+        if (!head.empty()) std::memcpy(header, head.data(), head.size());
+        *header_bits = bits;
+    });
+}
+
 // Decompress a raw lzss_lcp archive with the reference decoder (round-trip checker).  Output = text incl. trailing 0.
 int64_t tdcref_lzss_lcp_decompress(const uint8_t* arc, uint64_t len, int coder, uint8_t* out, uint64_t cap) {
     std::vector<uint8_t> res;

@@ -180,6 +180,101 @@ int tdcoracle_lzss_decode(const uint32_t* triples, uint64_t z, const uint8_t* te
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * lzss::encode_text — include/tudocomp/compressors/lzss/LZSSCoding.hpp:18-92 — for coders that keep the Encoder
+ * defaults for integers (binary in bits_for(max - min) bits, include/tudocomp/Coder.hpp:63-80) and write one fixed
+ * code word per literal (BitCoder: 8 bits; HuffmanCoder: include/tudocomp/coders/HuffmanCoder.hpp:309-322, 562-568).
+ * Bits go out MSB first (include/tudocomp/io/BitOStream.hpp:79-102).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static uint32_t bits_for_u64(uint64_t v) { /* include/tudocomp/util.hpp:194: bits_for(0) == 1 */
+    uint32_t b = 1;
+    while (v >>= 1) b++;
+    return b;
+}
+
+typedef struct {
+    uint8_t* out;
+    uint64_t cap, nbits;
+    int overflow;
+} bitsink;
+
+static void sink_bit(bitsink* s, int bit) { /* BitOStream::write_bit, io/BitOStream.hpp:79-90 */
+    uint64_t byte = s->nbits >> 3;
+    if (byte >= s->cap) { s->overflow = 1; s->nbits++; return; }
+    if ((s->nbits & 7) == 0) s->out[byte] = 0;
+    if (bit) s->out[byte] |= (uint8_t)(1u << (7 - (s->nbits & 7)));
+    s->nbits++;
+}
+static void sink_int(bitsink* s, uint64_t v, uint32_t bits) { /* BitOStream::write_int, io/BitOStream.hpp:98-102 */
+    for (int i = (int)bits - 1; i >= 0; i--) sink_bit(s, i < 64 ? (int)((v >> i) & 1u) : 0);
+}
+
+/* Literals as lzss::TextLiterals yields them (lzss/LZSSLiterals.hpp:10-56): every position outside a factor. */
+void tdcoracle_literal_histogram(const uint8_t* text, uint32_t n, const uint32_t* triples, uint64_t z, uint64_t hist[256]) {
+    uint64_t p = 0;
+    memset(hist, 0, 256 * sizeof(uint64_t));
+    for (uint64_t k = 0; k < z; k++) {
+        uint32_t pos = triples[3 * k], len = triples[3 * k + 2];
+        while (p < pos) hist[text[p++]]++;
+        p += len;
+    }
+    while (p < n) hist[text[p++]]++;
+}
+
+/* The stream continues a coder header of `lead_bits` (0..7) bits held in the high bits of `lead_byte`.
+ * finalize: append BitOStream::~BitOStream's tail (io/BitOStream.hpp:53-64).  Returns bytes written, < 0 if cap is
+ * too small; *nbits_out = stream bits incl. lead_bits (before the tail). */
+int64_t tdcoracle_lzss_encode(const uint8_t* text, uint32_t n, const uint32_t* triples, uint64_t z, const uint64_t codes[256],
+                              const uint8_t lens[256], uint32_t lead_bits, uint8_t lead_byte, int finalize, uint8_t* out,
+                              uint64_t cap, uint64_t* nbits_out) {
+    uint32_t flen_min, flen_max, fdist_max;
+    tdcoracle_factor_stats(triples, z, n, &flen_min, &flen_max, &fdist_max);
+    const uint32_t bn = bits_for_u64(n), bf = bits_for_u64(fdist_max);
+    const uint32_t bl = bits_for_u64((uint64_t)flen_max - (uint64_t)flen_min); /* size_t arithmetic as in Range::delta */
+    bitsink s = {out, cap, 0, 0};
+    for (uint32_t i = 0; i < lead_bits; i++) sink_bit(&s, (lead_byte >> (7 - i)) & 1);
+    sink_int(&s, n, 32);         /* coder.encode(n, len_r)          :47 */
+    sink_int(&s, flen_min, bn);  /* coder.encode(flen_min, text_r)  :48 (INDEX_MAX truncated when there is no factor) */
+    sink_int(&s, flen_max, bn);  /* :49 */
+    sink_int(&s, fdist_max, bn); /* :50 */
+    uint64_t p = 0;
+    for (uint64_t k = 0; k < z; k++) {
+        uint32_t pos = triples[3 * k], src = triples[3 * k + 1], len = triples[3 * k + 2];
+        if (pos == p) {
+            sink_bit(&s, 0); /* :58-60 */
+        } else {
+            sink_bit(&s, 1); /* :62-68 */
+            sink_int(&s, pos - p, bf);
+        }
+        while (p < pos) { uint8_t c = text[p++]; sink_int(&s, codes[c], lens[c]); } /* :71-73 */
+        sink_int(&s, src, bn);                /* :77 */
+        sink_int(&s, len - flen_min, bl);     /* :78 */
+        p += len;
+    }
+    if (p < n) { /* :82-85 */
+        sink_bit(&s, 1);
+        sink_int(&s, n - p, bf);
+    }
+    while (p < n) { uint8_t c = text[p++]; sink_int(&s, codes[c], lens[c]); } /* :87-90 */
+    if (nbits_out) *nbits_out = s.nbits;
+    uint64_t bytes = (s.nbits + 7) / 8;
+    if (finalize) {
+        const uint32_t used = (uint32_t)(s.nbits & 7);
+        const uint64_t whole = s.nbits >> 3;
+        if (used <= 5) {
+            if (whole >= cap) return -1;
+            if (used == 0) out[whole] = 0;
+            out[whole] |= (uint8_t)used;
+            bytes = whole + 1;
+        } else {
+            if (whole + 1 >= cap) return -1;
+            out[whole + 1] = (uint8_t)used;
+            bytes = whole + 2;
+        }
+    }
+    return s.overflow ? -1 : (int64_t)bytes;
+}
+
 /* One call for the whole TextDS as TextDS::require orders it (include/tudocomp/ds/TextDS.hpp:247-292).
  * Any output may be NULL; scratch is allocated as needed. */
 int tdcoracle_textds(const uint8_t* t, uint32_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp, uint32_t* phi,

@@ -29,6 +29,7 @@ class Oracle:
         self.lib = ctypes.CDLL(path)
         self.lib.tdcoracle_lzss_lcp_factorize.restype = ctypes.c_int64
         self.lib.tdcoracle_plcp.restype = ctypes.c_uint32
+        self.lib.tdcoracle_lzss_encode.restype = ctypes.c_int64
 
     def textds(self, t):
         n = t.size
@@ -56,6 +57,26 @@ class Oracle:
         self.lib.tdcoracle_factor_stats(_P(tr), ctypes.c_uint64(len(tr)), ctypes.c_uint32(n), ctypes.byref(a),
                                         ctypes.byref(b), ctypes.byref(c))
         return int(a.value), int(b.value), int(c.value)
+
+    def literal_histogram(self, text, triples):
+        tr = np.ascontiguousarray(triples, np.uint32)
+        hist = np.zeros(256, np.uint64)
+        self.lib.tdcoracle_literal_histogram(_P(text), ctypes.c_uint32(text.size), _P(tr), ctypes.c_uint64(len(tr)), _P(hist))
+        return hist
+
+    def encode(self, text, triples, codes, lens, lead_bits=0, lead_byte=0, finalize=True):
+        """lzss::encode_text restated: returns (bytes, nbits)."""
+        tr = np.ascontiguousarray(triples, np.uint32)
+        codes = np.ascontiguousarray(codes, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        cap = 13 * text.size + 64
+        out = np.zeros(cap, np.uint8)
+        nbits = ctypes.c_uint64()
+        m = self.lib.tdcoracle_lzss_encode(_P(text), ctypes.c_uint32(text.size), _P(tr), ctypes.c_uint64(len(tr)), _P(codes),
+                                           _P(lens), ctypes.c_uint32(lead_bits), ctypes.c_uint8(lead_byte),
+                                           ctypes.c_int(1 if finalize else 0), _P(out), ctypes.c_uint64(cap), ctypes.byref(nbits))
+        assert m >= 0
+        return out[:m].copy(), int(nbits.value)
 
     def decode(self, triples, text):
         tr = np.ascontiguousarray(triples, np.uint32)
@@ -107,6 +128,19 @@ class Reference:
                                               ctypes.c_uint64(cap), ctypes.byref(secs))
         assert 0 <= m <= cap, self.lib.tdcref_last_error()
         return out[:m].copy(), secs.value
+
+    def literal_coder(self, coder, hist):
+        """The coder's header bits and literal code words for a literal histogram, from the reference's own
+        HuffmanCoder / BitOStream code: (header bytes incl. the partial last byte, header_bits, codes[256], lens[256])."""
+        hist = np.ascontiguousarray(hist, np.uint64)
+        head = np.zeros(4096, np.uint8)
+        bits = ctypes.c_uint64()
+        codes = np.zeros(256, np.uint64)
+        lens = np.zeros(256, np.uint8)
+        rc = self.lib.tdcref_literal_coder(coder, _P(hist), _P(head), ctypes.c_uint64(head.size), ctypes.byref(bits), _P(codes), _P(lens))
+        assert rc == 0, self.lib.tdcref_last_error()
+        nb = (int(bits.value) + 7) // 8
+        return head[:nb].copy(), int(bits.value), codes, lens
 
     def decompress(self, arc, coder, n):
         out = np.zeros(n + 16, np.uint8)

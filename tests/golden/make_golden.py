@@ -32,6 +32,20 @@ def main():
             f, hdr = ref.factors(t, thr)
             out[f"{name}/factors{thr}"] = f
             out[f"{name}/hdr{thr}"] = np.array(hdr, np.uint64)
+        # the coder side of the archives below, from the reference's own HuffmanCoder: literal histogram of the
+        # threshold-3 parse (counted on the reference's factor list), header bits and code words
+        f3 = out[f"{name}/factors3"]
+        covered = np.zeros(t.size + 1, np.int64)
+        np.add.at(covered, f3[:, 0].astype(np.int64), 1)
+        np.add.at(covered, (f3[:, 0].astype(np.int64) + f3[:, 2]), -1)
+        lit = np.cumsum(covered[:-1]) == 0
+        hist = np.bincount(t[lit], minlength=256).astype(np.uint64)
+        out[f"{name}/lit_hist3"] = hist
+        head, hbits, codes, lens = ref.literal_coder(1, hist)
+        out[f"{name}/huff_head"] = head
+        out[f"{name}/huff_head_bits"] = np.array([hbits], np.uint64)
+        out[f"{name}/huff_codes"] = codes
+        out[f"{name}/huff_lens"] = lens
         for coder, cname in ((0, "bit"), (1, "huff"), (2, "ascii")):
             arc, _ = ref.compress(t, 3, coder)
             out[f"{name}/arc_{cname}"] = arc if small else np.frombuffer(__import__("hashlib").sha256(arc.tobytes()).digest(), np.uint8)

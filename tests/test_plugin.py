@@ -46,6 +46,38 @@ def test_gpu_driver_fails_loudly_without_device(tmp_path):
     assert (tmp_path / "o.tdc").read_bytes().startswith(b"lzss_lcp(coder=ascii)%30:6:12:6:16:hello ")
 
 
+@pytest.mark.sim
+def test_plugin_logic_over_the_simulator_library(tmp_path):
+    """CPU check of the C++ plugin code itself (GpuTextDS.hpp: array hand-over, device factor list, device-side
+    encode_text with the reference's Huffman table): the GPU-only driver is run with tests/sim's interpreter build of the
+    SAME C ABI in place of libtdcgpu.so (LD_LIBRARY_PATH wins over the binary's RUNPATH).  Test infrastructure only —
+    the product library stays the nvcc build; archives must equal the unmodified reference driver's byte for byte."""
+    _need_bins()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    simdir = tmp_path / "simlib"
+    simdir.mkdir()
+    os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
+    cases = {"markov": synth.markov_text(20000, 5)[:-1].tobytes(), "dna": synth.dna(12000, 6)[:-1].tobytes(),
+             "binary_with_escapes": bytes(np.random.default_rng(3).integers(0, 256, 4000, dtype=np.uint8)),
+             "run": b"a" * 3000, "empty": b""}
+    for name, data in cases.items():
+        src = tmp_path / f"{name}.bin"
+        src.write_bytes(data)
+        for algo in ("lzss_lcp(coder=huff)", "lzss_lcp(coder=bit,threshold=5)", "lzss_lcp(coder=ascii)", "bwt"):
+            a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc")
+            assert _run(REF, algo, str(src), a).returncode == 0
+            r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", b, "--force"], capture_output=True, text=True, env=env)
+            assert r.returncode == 0, (name, algo, r.stderr)
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, algo)
+    # the host-side encode_text (A/B switch) gives the same bytes
+    r = subprocess.run([GPU_ONLY, "-a", "lzss_lcp(coder=huff)", str(tmp_path / "markov.bin"), "-o", str(tmp_path / "h.tdc"), "--force"],
+                       capture_output=True, text=True, env=dict(env, TDCGPU_HOST_ENCODE="1"))
+    assert r.returncode == 0, r.stderr
+    assert _run(REF, "lzss_lcp(coder=huff)", str(tmp_path / "markov.bin"), str(tmp_path / "ref.tdc")).returncode == 0
+    assert open(tmp_path / "h.tdc", "rb").read() == open(tmp_path / "ref.tdc", "rb").read()
+
+
 def _inputs(tmp_path):
     cases = {
         "markov": synth.markov_text(300000, 5)[:-1].tobytes(),
@@ -113,5 +145,21 @@ def test_gpu_textds_arrays_through_stats(tmp_path):
     r = subprocess.run([GPU_ONLY, "-a", "lzss_lcp(coder=bit)", str(src), "-o", str(tmp_path / "o"), "--force", "--stats"],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    for title in ("Construct Text DS", "Factorize", "Encode", "factors", "threshold"):
+    for title in ("Construct Text DS", "Factorize", "Encode", "factors", "threshold", "gpu_ms:Encode: bit stream"):
         assert title in r.stdout, title
+
+
+@pytest.mark.gpu
+def test_host_and_device_encode_agree(tmp_path):
+    """TDCGPU_HOST_ENCODE=1 keeps the reference's encode_text on the host (factor list copied back); the default encodes
+    on the device.  Same bytes."""
+    _need_bins()
+    src = tmp_path / "m.txt"
+    src.write_bytes(synth.markov_text(400000, 9)[:-1].tobytes())
+    for coder in ("huff", "bit"):
+        a, b = str(tmp_path / "dev.tdc"), str(tmp_path / "host.tdc")
+        assert _run(GPU_ONLY, f"lzss_lcp(coder={coder})", str(src), a).returncode == 0
+        r = subprocess.run([GPU_ONLY, "-a", f"lzss_lcp(coder={coder})", str(src), "-o", b, "--force"], capture_output=True, text=True,
+                           env=dict(os.environ, TDCGPU_HOST_ENCODE="1"))
+        assert r.returncode == 0, r.stderr
+        assert open(a, "rb").read() == open(b, "rb").read(), coder

@@ -19,6 +19,7 @@ EXPORTS = [
     "tdcgpu_phase_count", "tdcgpu_phase_name", "tdcgpu_phase_ms", "tdcgpu_sa_stats", "tdcgpu_sync",
     "tdcgpu_event_record", "tdcgpu_event_elapsed_ms", "tdcgpu_launch_count", "tdcgpu_profile_enable",
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
+    "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -49,6 +50,9 @@ class TdcGpuLib:
         L.tdcgpu_lzss_lcp_factorize.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint32),
                                                 C.POINTER(C.c_uint32)]
         L.tdcgpu_lzss_lcp_get_factors.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.tdcgpu_lzss_literal_histogram.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        L.tdcgpu_lzss_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.POINTER(C.c_uint64)]
+        L.tdcgpu_lzss_encode_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         L.tdcgpu_textds_build_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5 + [C.POINTER(C.c_uint32)]
         L.tdcgpu_bwt_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
         L.tdcgpu_phase_count.argtypes = [C.c_void_p]
@@ -164,6 +168,37 @@ class Context:
         out = np.empty(count, dtype=FACTOR_DTYPE)
         self.lib.check(self.lib.lib.tdcgpu_lzss_lcp_get_factors(self._h, _host_ptr(out), count, 0))
         return out
+
+    # -- lzss::encode_text on the device ---------------------------------------------------------------------------
+    def literal_histogram(self):
+        """(hist[256] of the literals outside factors, fdist_max) of the last factorize call."""
+        hist = np.zeros(256, np.uint64)
+        fd = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_lzss_literal_histogram(self._h, _host_ptr(hist), C.byref(fd)))
+        return hist, int(fd.value)
+
+    def encode(self, codes: np.ndarray, lens: np.ndarray, lead_bits: int = 0, lead_byte: int = 0) -> int:
+        """Encode the factor list + literals as lzss::encode_text does; returns the stream length in bits."""
+        codes = np.ascontiguousarray(codes, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        assert codes.size == 256 and lens.size == 256
+        nbits = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_lzss_encode(self._h, _host_ptr(codes), _host_ptr(lens), lead_bits, lead_byte,
+                                                       C.byref(nbits)))
+        return int(nbits.value)
+
+    def encoded(self, nbits: int, finalize: bool = True) -> np.ndarray:
+        out = np.empty(nbits // 8 + 2, np.uint8)
+        nb = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_lzss_encode_get(self._h, _host_ptr(out), out.size, 1 if finalize else 0,
+                                                           C.byref(nb), 0))
+        return out[:int(nb.value)]
+
+    def encoded_into(self, host_ptr: int, cap: int, finalize: bool = True) -> int:
+        nb = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_lzss_encode_get(self._h, C.c_void_p(host_ptr), cap, 1 if finalize else 0,
+                                                           C.byref(nb), 0))
+        return int(nb.value)
 
     # -- stats -----------------------------------------------------------------------------------------------------
     def phases(self):

@@ -388,7 +388,8 @@ int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int fina
         TDC_CUDA(cudaStreamSynchronize(c.stream));
         u64 ntail;
         if (used <= 5) { tail[0] |= uint8_t(used); ntail = 1; } else { tail[1] = uint8_t(used); ntail = 2; }
-        TDC_CUDA(cudaMemcpyAsync(dst + whole, tail, ntail, to_device ? cudaMemcpyHostToDevice : cudaMemcpyHostToHost, c.stream));
+        if (to_device) TDC_CUDA(cudaMemcpyAsync(dst + whole, tail, ntail, cudaMemcpyHostToDevice, c.stream));
+        else memcpy(dst + whole, tail, ntail);
     }
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;

@@ -23,11 +23,16 @@
 // TextDS (ds/TextDS.hpp:132-138).  Single-threaded like the reference; StatPhase is only touched from the caller.
 #pragma once
 
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include <tudocomp/Algorithm.hpp>
+#include <tudocomp/coders/BitCoder.hpp>
+#include <tudocomp/coders/HuffmanCoder.hpp>
 #include <tudocomp/compressors/BWTCompressor.hpp>
 #include <tudocomp/compressors/LZSSLCPCompressor.hpp>
 #include <tudocomp/ds/ArrayDS.hpp>
@@ -54,6 +59,79 @@ inline void log_phases(tdcgpu_ctx* ctx) {
     for (int i = 0; i < tdcgpu_phase_count(ctx); i++) {
         StatPhase::log((std::string("gpu_ms:") + tdcgpu_phase_name(ctx, i)).c_str(), tdcgpu_phase_ms(ctx, i));
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-side lzss::encode_text (compressors/lzss/LZSSCoding.hpp:18-92): which coders can hand their literal code words
+// to the device, and how their own stream header is produced.  Everything coder-specific below is the reference's own
+// code (huff::gen_huffmantable, huff::huffmantable_encode, BitOStream); only the literal COUNTS come from the device.
+// ---------------------------------------------------------------------------------------------------------------------
+struct LiteralCodeTable {
+    uint64_t codes[256];
+    uint8_t lens[256];
+};
+
+template <typename coder_t>
+struct DeviceLiteralCoder {
+    static constexpr bool supported = false;  // e.g. ASCIICoder (variable-length decimal integers): host encode_text
+    static void header(io::BitOStream&, const uint64_t*, LiteralCodeTable&) {}
+};
+
+/// BitCoder: no header; literals use the Encoder default for LiteralRange = 8 bits (Coder.hpp:63-66, Range.hpp:89-93).
+template <>
+struct DeviceLiteralCoder<BitCoder> {
+    static constexpr bool supported = true;
+    static void header(io::BitOStream&, const uint64_t*, LiteralCodeTable& t) {
+        for (int c = 0; c < 256; c++) { t.codes[c] = uint64_t(c); t.lens[c] = 8; }
+    }
+};
+
+/// HuffmanCoder: mirrors HuffmanCoder::Encoder's constructor (coders/HuffmanCoder.hpp:526-548) with the literal counts
+/// taken from the device instead of huff::count_alphabet_literals (:37-49); code words as huff::huffman_encode writes
+/// them (:309-322), raw 8 bits when the effective alphabet has a single symbol (:562-568).
+template <>
+struct DeviceLiteralCoder<HuffmanCoder> {
+    static constexpr bool supported = true;
+    static void header(io::BitOStream& out, const uint64_t* hist, LiteralCodeTable& t) {
+        for (int c = 0; c < 256; c++) { t.codes[c] = uint64_t(c); t.lens[c] = 8; }
+        len_compact_t* C = new len_compact_t[ULITERAL_MAX + 1];
+        for (size_t c = 0; c <= ULITERAL_MAX; c++) C[c] = len_compact_t(hist[c]);
+        if (huff::effective_alphabet_size(C) <= 1) {
+            delete[] C;
+            out.write_bit(0);
+            return;
+        }
+        huff::extended_huffmantable table = huff::gen_huffmantable(C);  // takes ownership of C
+        out.write_bit(1);
+        huff::huffmantable_encode(out, table);
+        for (int c = 0; c < 256; c++) { t.codes[c] = 0; t.lens[c] = 0; }
+        for (size_t i = 0; i < table.alphabet_size; i++) {
+            t.codes[table.ordered_map_from_effective[i]] = table.codewords[i];
+            t.lens[table.ordered_map_from_effective[i]] = table.ordered_codelengths[i];
+        }
+    }
+};
+
+/// Strip what BitOStream::~BitOStream appended (io/BitOStream.hpp:53-64) from a finished scratch stream:
+/// returns the exact number of payload bits; `bytes` keeps the whole bytes plus the partial last byte.
+inline uint64_t strip_bitstream_tail(std::vector<uint8_t>& bytes) {
+    const uint8_t last = bytes.back();
+    const unsigned used = last & 7u;
+    uint64_t bits;
+    if (used <= 5) {
+        bits = 8 * uint64_t(bytes.size() - 1) + used;
+        bytes.back() = uint8_t(last & ~7u);
+        if (used == 0) bytes.pop_back();
+    } else {
+        bits = 8 * uint64_t(bytes.size() - 2) + used;
+        bytes.pop_back();
+    }
+    return bits;
+}
+
+inline bool host_encode_forced() {
+    const char* e = std::getenv("TDCGPU_HOST_ENCODE");  // A/B switch: run the reference's encode_text on the host
+    return e && *e && *e != '0';
 }
 }  // namespace gpu_detail
 
@@ -210,6 +288,7 @@ public:
             return text_t(env().env_for_option("textds"), view, text_t::SA | text_t::ISA | text_t::LCP);
         });
 
+        const bool device_encode = gpu_detail::DeviceLiteralCoder<coder_t>::supported && !gpu_detail::host_encode_forced();
         lzss::FactorBuffer factors;
         StatPhase::wrap("Factorize", [&] {
             const len_t threshold = env().option("threshold").as_integer();
@@ -218,16 +297,45 @@ public:
             uint32_t mn = 0, mx = 0;
             gpu_detail::check(tdcgpu_lzss_lcp_factorize(text.device(), threshold, &z, &mn, &mx), "factorize");
             gpu_detail::log_phases(text.device());
-            std::unique_ptr<tdcgpu_factor[]> buf(new tdcgpu_factor[z ? z : 1]);
-            gpu_detail::check(tdcgpu_lzss_lcp_get_factors(text.device(), buf.get(), z, 0), "get_factors");
-            for (uint64_t k = 0; k < z; k++) factors.emplace_back(buf[k].pos, buf[k].src, buf[k].len);
+            if (!device_encode) {  // the host encoder needs the list; the device encoder reads it where it is
+                std::unique_ptr<tdcgpu_factor[]> buf(new tdcgpu_factor[z ? z : 1]);
+                gpu_detail::check(tdcgpu_lzss_lcp_get_factors(text.device(), buf.get(), z, 0), "get_factors");
+                for (uint64_t k = 0; k < z; k++) factors.emplace_back(buf[k].pos, buf[k].src, buf[k].len);
+            }
             StatPhase::log("threshold", threshold);
-            StatPhase::log("factors", factors.size());
+            StatPhase::log("factors", size_t(z));
         });
 
         StatPhase::wrap("Encode", [&] {
-            typename coder_t::Encoder coder(env().env_for_option("coder"), output, lzss::TextLiterals<text_t>(text, factors));
-            lzss::encode_text(coder, text, factors);
+            if (!device_encode) {
+                typename coder_t::Encoder coder(env().env_for_option("coder"), output, lzss::TextLiterals<text_t>(text, factors));
+                lzss::encode_text(coder, text, factors);
+                return;
+            }
+            // 1. literal counts from the device -> the coder's own header and code words (reference code, host)
+            uint64_t hist[256];
+            gpu_detail::check(tdcgpu_lzss_literal_histogram(text.device(), hist, nullptr), "literal histogram");
+            gpu_detail::log_phases(text.device());
+            gpu_detail::LiteralCodeTable table;
+            std::vector<uint8_t> head;
+            {
+                Output scratch = Output::from_memory(head);
+                io::BitOStream bits(scratch);
+                gpu_detail::DeviceLiteralCoder<coder_t>::header(bits, hist, table);
+            }
+            const uint64_t head_bits = gpu_detail::strip_bitstream_tail(head);
+            const uint32_t lead_bits = uint32_t(head_bits % 8);
+            const uint8_t lead_byte = lead_bits ? head[head_bits / 8] : uint8_t(0);
+            // 2. the body of lzss::encode_text on the device, continuing the header's partial byte
+            uint64_t nbits = 0, nbytes = 0;
+            gpu_detail::check(tdcgpu_lzss_encode(text.device(), table.codes, table.lens, lead_bits, lead_byte, &nbits), "encode");
+            gpu_detail::log_phases(text.device());
+            std::vector<uint8_t> body(nbits / 8 + 2);
+            gpu_detail::check(tdcgpu_lzss_encode_get(text.device(), body.data(), body.size(), 1, &nbytes, 0), "encode");
+            auto os = output.as_stream();
+            os.write(reinterpret_cast<const char*>(head.data()), std::streamsize(head_bits / 8));
+            os.write(reinterpret_cast<const char*>(body.data()), std::streamsize(nbytes));
+            StatPhase::log("archive_bytes", size_t(head_bits / 8 + nbytes));
         });
     }
 
