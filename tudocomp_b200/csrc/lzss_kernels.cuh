@@ -126,7 +126,7 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
 #define LPF_CHUNK_CFG 16
 #endif
 static const int LPF_CHUNK = LPF_CHUNK_CFG;  // ranks per thread (16 or 32)
-#ifdef TDC_CUSIM
+#if defined(TDC_CUSIM) && !defined(LPF_THREADS_CFG)
 static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
 #ifndef LPF_THREADS_CFG
@@ -201,14 +201,22 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside, LpfDis
     u32* sQ = sNL + LPF_THREADS;                            // [2 * LPF_TILE / 16] open (index << 1 | side) after the merges
     u32* sQn = sQ + 2 * LPF_TILE / 16;                      // [1] queue length
     const u32 base = blockIdx.x * LPF_TILE;
-    for (u32 j = threadIdx.x; j < LPF_TILE; j += LPF_THREADS) {
-        const u32 i = base + j;
-        sA[lpf_phys(j)] = i < n ? T.a[0][i] : LPF_INF;
-        sU[lpf_phys(j)] = i < n ? T.l[0][i] : LPF_INF;
+    constexpr u32 CH = u32(LPF_CHUNK);
+    // Every warp loads the 32 chunks its own lanes will work on, so that steps 1 and the first five merge levels only
+    // need warp-level synchronisation: with block barriers after every level the barrier was the top stall reason
+    // (9.7 stalled warps per issue, profiles/r1i_summary.md) because the upper levels keep 1-2 warps busy.
+    {
+        const u32 wbase = warp_id() * 32u * CH;
+#pragma unroll 4
+        for (u32 k = 0; k < CH; k++) {
+            const u32 j = wbase + k * 32u + lane_id();
+            const u32 i = base + j;
+            sA[lpf_phys(j)] = i < n ? T.a[0][i] : LPF_INF;
+            sU[lpf_phys(j)] = i < n ? T.l[0][i] : LPF_INF;
+        }
     }
     if (threadIdx.x == 0) *sQn = 0;
-    __syncthreads();
-    constexpr u32 CH = u32(LPF_CHUNK);
+    __syncwarp();
     const u32 cs = threadIdx.x * CH;  // this thread's chunk [cs, cs + CH)
     const u32 sw = (cs >> 5) & 31u;   // swizzle of the chunk: phys(cs + s) = (cs + s) ^ sw
 #define LPF_AT(arr, s) arr[(cs + (s)) ^ sw]
@@ -260,11 +268,14 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside, LpfDis
         } while (s < CH);
         sNL[threadIdx.x] = lmin;
     }
-    __syncthreads();
+    __syncwarp();
     // ---- 2. merge tree ----
+    // The node made of chunks [ca, ca + 2 * half) is merged by thread ca (the thread of its first chunk): nodes of up to
+    // 32 chunks live inside one warp and are ordered by __syncwarp, only the last log2(warps) levels need the block.
     for (u32 half = 1; half < u32(LPF_THREADS); half <<= 1) {  // half = chunks per child node
-        if (threadIdx.x * 2 * half < u32(LPF_THREADS)) {
-            const u32 ca = threadIdx.x * 2 * half, cb = ca + half;  // first chunks of the left / right child
+        if (half >= 32) __syncthreads();
+        if ((threadIdx.x & (2 * half - 1)) == 0) {
+            const u32 ca = threadIdx.x, cb = ca + half;  // first chunks of the left / right child
             u32 a = cb * CH - 1, b = cb * CH;                        // heads: last rank of A, first rank of B
             u32 va = sA[lpf_phys(a)], vb = sA[lpf_phys(b)];
             while (a != LPF_NONE && b != LPF_NONE) {
@@ -298,8 +309,9 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside, LpfDis
             }
             sNL[ca] = min(la, lb);
         }
-        __syncthreads();
+        if (half < 16) __syncwarp();
     }
+    __syncthreads();
     // ---- 3. the tile's own prefix / suffix minima continue in the global tree ----
     {
         u32 open_up = 0, open_dn = 0;
