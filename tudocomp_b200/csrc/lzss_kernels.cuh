@@ -130,7 +130,7 @@ static const int LPF_CHUNK = LPF_CHUNK_CFG;  // ranks per thread (16 or 32)
 static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
 #ifndef LPF_THREADS_CFG
-#define LPF_THREADS_CFG 128
+#define LPF_THREADS_CFG 64  // 2 warps x 32 chunks: one block-level merge; measured best (profiles/r1l_summary.md)
 #endif
 static const int LPF_THREADS = LPF_THREADS_CFG;  // chunks per tile (power of two)
 #endif
