@@ -33,7 +33,30 @@ gpu_textds = [AlgorithmConfig(name="GpuTextDS", header="../tudocomp_gpu/GpuTextD
 
 textds = {"mixed": cpu_textds + gpu_textds, "only": gpu_textds, "none": cpu_textds}[mode]
 
+# lcpcomp (etc/registry_config.py:135-169) with the strategies / decoders that build offline: BoostHeap and
+# PLCPStrategy need Boost.  The reference only allows an uncompressed (writable) LCP provider here; GpuArray is a
+# DynamicIntVector at width 32 unless `compress` narrows it, and the strategies overwrite entries in place either way.
+lcpcomp_coders = [
+    AlgorithmConfig(name="ASCIICoder", header="coders/ASCIICoder.hpp"),
+    AlgorithmConfig(name="SLECoder", header="coders/SLECoder.hpp"),
+    AlgorithmConfig(name="HuffmanCoder", header="coders/HuffmanCoder.hpp"),
+]
+lcpcomp_comp = [
+    AlgorithmConfig(name="lcpcomp::MaxHeapStrategy", header="compressors/lcpcomp/compress/MaxHeapStrategy.hpp"),
+    AlgorithmConfig(name="lcpcomp::MaxLCPStrategy", header="compressors/lcpcomp/compress/MaxLCPStrategy.hpp"),
+    AlgorithmConfig(name="lcpcomp::ArraysComp", header="compressors/lcpcomp/compress/ArraysComp.hpp"),
+    AlgorithmConfig(name="lcpcomp::PLCPPeaksStrategy", header="compressors/lcpcomp/compress/PLCPPeaksStrategy.hpp"),
+]
+lcpcomp_dec = [
+    AlgorithmConfig(name="lcpcomp::ScanDec", header="compressors/lcpcomp/decompress/ScanDec.hpp"),
+    AlgorithmConfig(name="lcpcomp::CompactDec", header="compressors/lcpcomp/decompress/CompactDec.hpp"),
+]  # (DecodeForwardQueueListBuffer / MultimapBuffer left out only to keep the offline build short: 24 instantiations per textds)
+lcp_uncompressed = [AlgorithmConfig(name="LCPFromPLCP", header="ds/LCPFromPLCP.hpp")]
+lcpcomp_cpu_textds = [AlgorithmConfig(name="TextDS", header="ds/TextDS.hpp", sub=[sa, phi, plcp, lcp_uncompressed, isa])]
+lcpcomp_textds = {"mixed": lcpcomp_cpu_textds + gpu_textds, "only": gpu_textds, "none": lcpcomp_cpu_textds}[mode]
+
 tdc.compressors = [
+    AlgorithmConfig(name="LCPCompressor", header="compressors/LCPCompressor.hpp", sub=[lcpcomp_coders, lcpcomp_comp, lcpcomp_dec, lcpcomp_textds]),
     AlgorithmConfig(name="RunLengthEncoder", header="compressors/RunLengthEncoder.hpp"),
     AlgorithmConfig(name="LiteralEncoder", header="compressors/LiteralEncoder.hpp", sub=[coders]),
     AlgorithmConfig(name="LZSSLCPCompressor", header="compressors/LZSSLCPCompressor.hpp", sub=[coders, textds]),
