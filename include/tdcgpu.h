@@ -66,6 +66,16 @@ int tdcgpu_textds_build(tdcgpu_ctx* ctx, uint32_t flags);
  * DynamicIntVector at width 32 (ds/BitPackingVector.hpp:259-271). */
 int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device);
 
+/* The same structure bit-packed on the device to `width` bits per element, in the layout of the reference's
+ * DynamicIntVector / BitPackingVector (ds/BitPackingVector.hpp:62-98, 259-271): element i occupies bits [i*width,
+ * (i+1)*width) of a little-endian stream of 64-bit words, values truncated to their low `width` bits
+ * (sdsl::bits::write_int semantics).  This is what the providers' compress() leaves behind with compress=delayed|compressed
+ * (bits_for(n) for SA/ISA/Phi, bits_for(max_lcp) for PLCP/LCP: ds/SADivSufSort.hpp:53-63, LCPFromPLCP.hpp:56-66); doing
+ * it here replaces the serial re-pack of BitPackingVector::resize (ds/BitPackingVector.hpp:478-540) and shrinks the
+ * device-to-host copy from 4n to n*width/8 bytes.  dst holds cap_words >= ceil(n*width/64) words; unused high bits of the
+ * last word are 0.  1 <= width <= 32.  Uses (and thereby invalidates) the context's scratch. */
+int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, uint64_t* dst, uint64_t cap_words, int to_device);
+
 /* Device pointer of a built structure (valid until the next set_text/destroy); NULL if not built. */
 const void* tdcgpu_textds_device_ptr(tdcgpu_ctx* ctx, uint32_t which);
 

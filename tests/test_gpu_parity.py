@@ -168,3 +168,20 @@ def test_one_shot_host_entry_points():
     assert lib.lib.tdcgpu_bwt_host(0, t.ctypes.data, n, out.ctypes.data) == 0
     assert np.array_equal(out, np.where(sa == 0, t[n - 1], t[(sa.astype(np.int64) - 1) % n]))
     assert np.array_equal(tdc.bwt(t), out)
+
+
+def test_bit_packed_arrays(ctx):
+    """tdcgpu_textds_get_packed against the DynamicIntVector layout computed with numpy (ds/BitPackingVector.hpp:62-98)."""
+    def pack(a, w):
+        m = np.uint64((1 << w) - 1)
+        bits = (((a.astype(np.uint64) & m)[:, None] >> np.arange(w, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8).ravel()
+        bits = np.concatenate([bits, np.zeros((-bits.size) % 64, np.uint8)])
+        return np.packbits(bits, bitorder="little").view(np.uint64)
+
+    t = synth.markov_text(1 << 20, 61)
+    ctx.set_text(t)
+    ctx.build(ALL)
+    for fl in (tdc.SA, tdc.ISA, tdc.LCP, tdc.PLCP, tdc.PHI):
+        a = ctx.get(fl)
+        for w in (5, 21, int(t.size).bit_length(), 32):
+            assert np.array_equal(ctx.get_packed(fl, w), pack(a, w)), (fl, w)

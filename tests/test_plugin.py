@@ -70,6 +70,16 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
             r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", b, "--force"], capture_output=True, text=True, env=env)
             assert r.returncode == 0, (name, algo, r.stderr)
             assert open(a, "rb").read() == open(b, "rb").read(), (name, algo)
+    # lcpcomp: the reference's own strategies consume the GPU text index through require_* / release_*
+    # (arrays come back bit-packed by the device, compress=delayed); mixed registry, so compare under --raw
+    for name in ("markov", "binary_with_escapes", "empty"):
+        src = str(tmp_path / f"{name}.bin")
+        for opts in ("coder=huff", "coder=ascii,comp=heap", "coder=huff,comp=max_lcp", "coder=huff,comp=plcppeaks,dec=compact"):
+            a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc")
+            assert _run(REF, f"lcpcomp({opts})", src, a, ["--raw"]).returncode == 0
+            r = subprocess.run([GPU, "-a", f"lcpcomp({opts},textds=gpu)", src, "-o", b, "--force", "--raw"], capture_output=True, text=True, env=env)
+            assert r.returncode == 0, (name, opts, r.stderr)
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, opts)
     # the host-side encode_text (A/B switch) gives the same bytes
     r = subprocess.run([GPU_ONLY, "-a", "lzss_lcp(coder=huff)", str(tmp_path / "markov.bin"), "-o", str(tmp_path / "h.tdc"), "--force"],
                        capture_output=True, text=True, env=dict(env, TDCGPU_HOST_ENCODE="1"))
@@ -147,6 +157,20 @@ def test_gpu_textds_arrays_through_stats(tmp_path):
     assert r.returncode == 0, r.stderr
     for title in ("Construct Text DS", "Factorize", "Encode", "factors", "threshold", "gpu_ms:Encode: bit stream"):
         assert title in r.stdout, title
+
+
+@pytest.mark.gpu
+def test_lcpcomp_with_gpu_text_index(tmp_path):
+    """lcpcomp's strategies (compressors/lcpcomp/compress/*.hpp) on arrays built by the GPU, byte-identical
+    raw archives, and the reference driver decodes them."""
+    _need_bins()
+    for name, src in _inputs(tmp_path).items():
+        for opts in ("coder=huff", "coder=huff,comp=heap", "coder=ascii,comp=max_lcp", "coder=huff,comp=plcppeaks,dec=compact"):
+            a, b = str(tmp_path / f"{name}.lcpcomp.ref"), str(tmp_path / f"{name}.lcpcomp.gpu")
+            assert _run(REF, f"lcpcomp({opts})", src, a, ["--raw"]).returncode == 0
+            r = _run(GPU, f"lcpcomp({opts},textds=gpu)", src, b, ["--raw"])
+            assert r.returncode == 0, r.stderr
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, opts)
 
 
 @pytest.mark.gpu

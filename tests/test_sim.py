@@ -107,3 +107,27 @@ def test_sim_key_layouts(simlib, oracle):
                     assert c.max_lcp() == ds["max_lcp"], (name, ksym)
     finally:
         os.environ.pop("TDCGPU_SA_SYMBOLS", None)
+
+
+def _pack_reference(a, w):
+    """DynamicIntVector layout (ds/BitPackingVector.hpp:62-98): element i at bits [i*w, (i+1)*w), 64-bit LE words."""
+    m = np.uint64((1 << w) - 1)
+    bits = (((a.astype(np.uint64) & m)[:, None] >> np.arange(w, dtype=np.uint64)) & np.uint64(1)).astype(np.uint8).ravel()
+    bits = np.concatenate([bits, np.zeros((-bits.size) % 64, np.uint8)])
+    return np.packbits(bits, bitorder="little").view(np.uint64)
+
+
+def test_sim_bit_packed_arrays(simlib):
+    """tdcgpu_textds_get_packed: every array at several widths, incl. truncating ones (the stale PLCP[n-1])."""
+    from tudocomp_b200 import synth
+    for name, t in (("markov", synth.markov_text(5000, 1)), ("run", synth.with_sentinel(np.full(777, 97, np.uint8))),
+                    ("sentinel_only", np.zeros(1, np.uint8))):
+        with _abi.Context(simlib) as c:
+            c.set_text(t)
+            c.build(_abi.SA | _abi.ISA | _abi.LCP | _abi.PLCP | _abi.PHI)
+            for which in (_abi.SA, _abi.ISA, _abi.LCP, _abi.PLCP, _abi.PHI):
+                a = c.get(which)
+                for w in (1, 7, 13, 17, 31, 32, int(t.size).bit_length()):
+                    assert np.array_equal(c.get_packed(which, w), _pack_reference(a, w)), (name, which, w)
+            with pytest.raises(_abi.TdcGpuError):
+                c.get_packed(_abi.SA, 33)

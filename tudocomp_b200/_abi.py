@@ -19,7 +19,7 @@ EXPORTS = [
     "tdcgpu_phase_count", "tdcgpu_phase_name", "tdcgpu_phase_ms", "tdcgpu_sa_stats", "tdcgpu_sync",
     "tdcgpu_event_record", "tdcgpu_event_elapsed_ms", "tdcgpu_launch_count", "tdcgpu_profile_enable",
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
-    "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get",
+    "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -44,6 +44,7 @@ class TdcGpuLib:
         L.tdcgpu_set_text.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
         L.tdcgpu_textds_build.argtypes = [C.c_void_p, C.c_uint32]
         L.tdcgpu_textds_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
+        L.tdcgpu_textds_get_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
         L.tdcgpu_textds_device_ptr.argtypes = [C.c_void_p, C.c_uint32]
         L.tdcgpu_textds_device_ptr.restype = C.c_void_p
         L.tdcgpu_textds_max_lcp.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
@@ -145,6 +146,12 @@ class Context:
     def get(self, which: int) -> np.ndarray:
         out = np.empty(self.n, dtype=np.uint8 if which == BWT else np.uint32)
         self.lib.check(self.lib.lib.tdcgpu_textds_get(self._h, which, _host_ptr(out), 0))
+        return out
+
+    def get_packed(self, which: int, width: int) -> np.ndarray:
+        """The array bit-packed to `width` bits per element (DynamicIntVector layout): uint64 words."""
+        out = np.empty((self.n * width + 63) // 64, dtype=np.uint64)
+        self.lib.check(self.lib.lib.tdcgpu_textds_get_packed(self._h, which, width, _host_ptr(out), out.size, 0))
         return out
 
     def get_into_device(self, which: int, dev_ptr: int) -> None:

@@ -190,6 +190,22 @@ static int do_build(Ctx& c, u32 flags) {
     return 0;
 }
 
+// One thread per 64-bit output word: gathers the <= 64/width + 2 elements that overlap it.  Reads of neighbouring
+// threads overlap and stay in L1/L2, writes are coalesced: 4 B read + width/8 B written per element.
+static __global__ void __launch_bounds__(256)
+pack_bits_kernel(const u32* __restrict__ a, u64 n, u32 w, u64* __restrict__ out, u64 nwords) {
+    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= nwords) return;
+    const u64 lo = j * 64, hi = lo + 64;
+    const u32 mask = w >= 32 ? 0xffffffffu : ((1u << w) - 1u);
+    u64 acc = 0;
+    for (u64 e = lo / w; e < n && e * w < hi; e++) {
+        const u64 v = u64(a[e] & mask), start = e * w;
+        acc |= start >= lo ? (v << (start - lo)) : (v >> (lo - start));
+    }
+    out[j] = acc;
+}
+
 static void* array_ptr(Ctx& c, u32 which, size_t* elem) {
     *elem = 4;
     switch (which) {
@@ -300,6 +316,26 @@ int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device)
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
     TDC_CUDA(cudaMemcpyAsync(dst, src, elem * c.n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, uint64_t* dst, uint64_t cap_words, int to_device) {
+    API_GUARD(ctx);
+    size_t elem;
+    void* src = array_ptr(c, which, &elem);
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
+    if (elem != 4 || width < 1 || width > 32) { set_error("get_packed: 32-bit arrays only, 1 <= width <= 32"); return TDCGPU_ERR_ARG; }
+    const u64 nwords = div_up(c.n * u64(width), 64);
+    if (cap_words < nwords) { set_error("get_packed: buffer too small: %llu < %llu words", (unsigned long long)cap_words, (unsigned long long)nwords); return TDCGPU_ERR_ARG; }
+    c.arena.reset();  // scratch: whatever the previous phase kept there (e.g. the encoder's masks) is stale from here on
+    u64* packed = c.arena.take<u64>(nwords);
+    if (!packed) { set_error("get_packed: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
+    TDC_LAUNCH(pack_bits_kernel, u32(div_up(nwords, 256)), 256, 0, c.stream, static_cast<const u32*>(src), c.n, width, packed, nwords);
+    prof_add_bytes("pack_bits_kernel", double(c.n) * 4 + double(nwords) * 8);
+    TDC_KCHECK();
+    TDC_CUDA(cudaMemcpyAsync(dst, packed, nwords * sizeof(u64), to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }

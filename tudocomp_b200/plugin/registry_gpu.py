@@ -38,9 +38,8 @@ textds = {"mixed": cpu_textds + gpu_textds, "only": gpu_textds, "none": cpu_text
 # DynamicIntVector at width 32 unless `compress` narrows it, and the strategies overwrite entries in place either way.
 lcpcomp_coders = [
     AlgorithmConfig(name="ASCIICoder", header="coders/ASCIICoder.hpp"),
-    AlgorithmConfig(name="SLECoder", header="coders/SLECoder.hpp"),
     AlgorithmConfig(name="HuffmanCoder", header="coders/HuffmanCoder.hpp"),
-]
+]  # (SLECoder left out only to keep the offline build short)
 lcpcomp_comp = [
     AlgorithmConfig(name="lcpcomp::MaxHeapStrategy", header="compressors/lcpcomp/compress/MaxHeapStrategy.hpp"),
     AlgorithmConfig(name="lcpcomp::MaxLCPStrategy", header="compressors/lcpcomp/compress/MaxLCPStrategy.hpp"),
@@ -54,9 +53,14 @@ lcpcomp_dec = [
 lcp_uncompressed = [AlgorithmConfig(name="LCPFromPLCP", header="ds/LCPFromPLCP.hpp")]
 lcpcomp_cpu_textds = [AlgorithmConfig(name="TextDS", header="ds/TextDS.hpp", sub=[sa, phi, plcp, lcp_uncompressed, isa])]
 lcpcomp_textds = {"mixed": lcpcomp_cpu_textds + gpu_textds, "only": gpu_textds, "none": lcpcomp_cpu_textds}[mode]
-
-tdc.compressors = [
+# LCPCompressor::meta() hard-codes TextDS<> as the default of its `textds` option (compressors/LCPCompressor.hpp:91), so a
+# registry without the CPU TextDS cannot hold it: lcpcomp is registered in the reference subset and in the mixed registry
+# (select the GPU index with `lcpcomp(..., textds=gpu)`), not in the GPU-only one.
+lcpcomp = [] if mode == "only" else [
     AlgorithmConfig(name="LCPCompressor", header="compressors/LCPCompressor.hpp", sub=[lcpcomp_coders, lcpcomp_comp, lcpcomp_dec, lcpcomp_textds]),
+]
+
+tdc.compressors = lcpcomp + [
     AlgorithmConfig(name="RunLengthEncoder", header="compressors/RunLengthEncoder.hpp"),
     AlgorithmConfig(name="LiteralEncoder", header="compressors/LiteralEncoder.hpp", sub=[coders]),
     AlgorithmConfig(name="LZSSLCPCompressor", header="compressors/LZSSLCPCompressor.hpp", sub=[coders, textds]),
