@@ -116,6 +116,31 @@ int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t
  * fewer than 3 bits are free).  *nbytes = bytes written (ceil(nbits / 8), + at most 1 when finalized). */
 int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device);
 
+/* ---- byte-stream stages behind the BWT in `bwt:mtf:rle:encode(huff)` (BASELINE config 3) -------------------------
+ * Stateless with respect to the text index: they only use the context's stream and a scratch buffer of their own.
+ * on_device != 0: in/out are device pointers on the context's device; otherwise host pointers.
+ *
+ * mtf_encode (compressors/MTFCompressor.hpp:46-56): out[i] = index of in[i] in the move-to-front table (initially
+ * 0..255) before it is moved to the front; n bytes out. */
+int tdcgpu_mtf_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int on_device);
+
+/* rle_encode (compressors/RunLengthEncoder.hpp:15-31, util/vbyte.hpp:27-37): a run of L >= 2 equal bytes c becomes
+ * c c vbyte(L - 2 + offset), single bytes are copied; runs of bytes >= 0x80 are not merged, exactly like the reference, whose
+ * run counter compares an int with a signed char (:24).  *out_n = bytes produced (<= cap, else TDCGPU_ERR_ARG; a device
+ * output buffer must hold the worst case n * (1 + vbyte_len(offset + n)) + 16).  n < 2^32 - 16. */
+int tdcgpu_rle_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t offset, uint8_t* out, uint64_t cap, uint64_t* out_n,
+                      int on_device);
+
+/* LiteralEncoder<coder>::compress (compressors/LiteralEncoder.hpp:23-32) for BitCoder / HuffmanCoder, in three steps like
+ * the lzss encoder above: begin = stage the input on the device and count its bytes (what huff::count_alphabet_literals
+ * sees through ViewLiterals, coders/HuffmanCoder.hpp:37-49, Literal.hpp:55-70); the caller derives the coder's header and
+ * code words (reference code); encode = every byte by its code word behind the header's `lead_bits` bits; get = the stream
+ * (finalize: BitOStream's tail).  A device input must stay valid until tdcgpu_literal_encode returns. */
+int tdcgpu_literal_encode_begin(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, int on_device, uint64_t hist[256]);
+int tdcgpu_literal_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t lens[256], uint32_t lead_bits, uint8_t lead_byte,
+                          uint64_t* nbits);
+int tdcgpu_literal_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device);
+
 /* One-shot host-buffer convenience used by the C++ provider shims: text in, arrays out (NULL = not wanted).
  * Same semantics as constructing TextDS<>(env, view, flags) and reading the providers. */
 int tdcgpu_textds_build_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp,

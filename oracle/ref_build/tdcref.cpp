@@ -26,6 +26,9 @@
 #include <tudocomp/coders/HuffmanCoder.hpp>
 #include <tudocomp/compressors/BWTCompressor.hpp>
 #include <tudocomp/compressors/LZSSLCPCompressor.hpp>
+#include <tudocomp/compressors/LiteralEncoder.hpp>
+#include <tudocomp/compressors/MTFCompressor.hpp>
+#include <tudocomp/compressors/RunLengthEncoder.hpp>
 #include <tudocomp/ds/TextDS.hpp>
 #include <tudocomp/ds/bwt.hpp>
 #include <tudocomp/io.hpp>
@@ -261,6 +264,24 @@ int tdcref_literal_coder(int coder, const uint64_t hist[256], uint8_t* header, u
         if (!head.empty()) std::memcpy(header, head.data(), head.size());
         *header_bits = bits;
     });
+}
+
+// One stream stage of `bwt:mtf:rle:encode(huff)` through the reference's own Compressor classes (no sentinel / escaping:
+// these stages declare no input restrictions).  stage: 0 = MTFCompressor, 1 = RunLengthEncoder(offset),
+// 2 = LiteralEncoder<BitCoder>, 3 = LiteralEncoder<HuffmanCoder>.  Returns the output length.
+int64_t tdcref_stream_stage(int stage, const uint8_t* in, uint64_t n, uint64_t offset, uint8_t* out, uint64_t cap, double* secs) {
+    std::vector<uint8_t> res;
+    int rc = guarded([&] {
+        View v(in, n);
+        if (stage == 0) res = run_compress<MTFCompressor>(v, "", secs);
+        else if (stage == 1) res = run_compress<RunLengthEncoder>(v, "offset=" + std::to_string(offset), secs);
+        else if (stage == 2) res = run_compress<LiteralEncoder<BitCoder>>(v, "", secs);
+        else if (stage == 3) res = run_compress<LiteralEncoder<HuffmanCoder>>(v, "", secs);
+        else throw std::runtime_error("unknown stage id");
+    });
+    if (rc) return rc;
+    if (out && res.size() <= cap) std::memcpy(out, res.data(), res.size());
+    return int64_t(res.size());
 }
 
 // Decompress a raw lzss_lcp archive with the reference decoder (round-trip checker).  Output = text incl. trailing 0.

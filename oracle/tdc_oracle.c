@@ -275,6 +275,87 @@ int64_t tdcoracle_lzss_encode(const uint8_t* text, uint32_t n, const uint32_t* t
     return s.overflow ? -1 : (int64_t)bytes;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The stream stages behind the BWT in `bwt:mtf:rle:encode(huff)`.
+ * ------------------------------------------------------------------------------------------------------------------ */
+/* mtf_encode — include/tudocomp/compressors/MTFCompressor.hpp:17-30, 46-56: table starts as 0..255; each byte is looked
+ * up linearly, its index is emitted and it moves to the front. */
+void tdcoracle_mtf_encode(const uint8_t* in, uint64_t n, uint8_t* out) {
+    uint8_t table[256];
+    for (int i = 0; i < 256; i++) table[i] = (uint8_t)i;
+    for (uint64_t p = 0; p < n; p++) {
+        const uint8_t v = in[p];
+        int i = 0;
+        while (table[i] != v) i++;
+        for (int j = i; j > 0; j--) table[j] = table[j - 1];
+        table[0] = v;
+        out[p] = (uint8_t)i;
+    }
+}
+
+/* rle_encode — include/tudocomp/compressors/RunLengthEncoder.hpp:15-31 with write_vbyte
+ * (include/tudocomp/util/vbyte.hpp:27-37): the first byte of a run is copied; a second equal byte is copied and followed
+ * by vbyte(number of further equal bytes + offset).  Returns the output length, or -1 if cap is too small.
+ * Quirk reproduced on purpose: the compressor instantiates char_type = char (std::istream), and the run counter compares
+ * `is.peek() == c` (:24), i.e. an int in 0..255 with a signed char: for bytes >= 0x80 it is never true, so such a run is
+ * never merged — every further byte of it is written as  c vbyte(0 + offset).  (At end of input peek() is EOF = -1, which
+ * does equal the char 0xFF: the reference then spins forever on inputs that END in 0xFF 0xFF; here such a tail is encoded
+ * like any other run of a byte >= 0x80.) */
+int64_t tdcoracle_rle_encode(const uint8_t* in, uint64_t n, uint64_t offset, uint8_t* out, uint64_t cap) {
+    uint64_t o = 0, i = 0;
+    if (n == 0) return 0;
+#define PUT(b) do { if (o >= cap) return -1; out[o++] = (uint8_t)(b); } while (0)
+    uint8_t prev = in[i++];
+    PUT(prev);
+    while (i < n) {
+        const uint8_t c = in[i++];
+        if (prev == c) {
+            uint64_t run = 0;
+            while (c < 0x80 && i < n && in[i] == c) { run++; i++; }
+            PUT(c);
+            uint64_t v = run + offset;
+            do {
+                uint8_t byte = (uint8_t)(v & 0x7f);
+                v >>= 7;
+                if (v > 0) byte |= 0x80;
+                PUT(byte);
+            } while (v > 0);
+        } else {
+            PUT(c);
+        }
+        prev = c;
+    }
+#undef PUT
+    return (int64_t)o;
+}
+
+/* LiteralEncoder::compress — include/tudocomp/compressors/LiteralEncoder.hpp:23-32: after the coder's own header every
+ * byte is written with its code word; then BitOStream's tail.  Same conventions as tdcoracle_lzss_encode. */
+int64_t tdcoracle_literal_encode(const uint8_t* in, uint64_t n, const uint64_t codes[256], const uint8_t lens[256],
+                                 uint32_t lead_bits, uint8_t lead_byte, int finalize, uint8_t* out, uint64_t cap,
+                                 uint64_t* nbits_out) {
+    bitsink s = {out, cap, 0, 0};
+    for (uint32_t i = 0; i < lead_bits; i++) sink_bit(&s, (lead_byte >> (7 - i)) & 1);
+    for (uint64_t p = 0; p < n; p++) sink_int(&s, codes[in[p]], lens[in[p]]);
+    if (nbits_out) *nbits_out = s.nbits;
+    uint64_t bytes = (s.nbits + 7) / 8;
+    if (finalize) {
+        const uint32_t used = (uint32_t)(s.nbits & 7);
+        const uint64_t whole = s.nbits >> 3;
+        if (used <= 5) {
+            if (whole >= cap) return -1;
+            if (used == 0) out[whole] = 0;
+            out[whole] |= (uint8_t)used;
+            bytes = whole + 1;
+        } else {
+            if (whole + 1 >= cap) return -1;
+            out[whole + 1] = (uint8_t)used;
+            bytes = whole + 2;
+        }
+    }
+    return s.overflow ? -1 : (int64_t)bytes;
+}
+
 /* One call for the whole TextDS as TextDS::require orders it (include/tudocomp/ds/TextDS.hpp:247-292).
  * Any output may be NULL; scratch is allocated as needed. */
 int tdcoracle_textds(const uint8_t* t, uint32_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp, uint32_t* phi,

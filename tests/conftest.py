@@ -30,6 +30,8 @@ class Oracle:
         self.lib.tdcoracle_lzss_lcp_factorize.restype = ctypes.c_int64
         self.lib.tdcoracle_plcp.restype = ctypes.c_uint32
         self.lib.tdcoracle_lzss_encode.restype = ctypes.c_int64
+        self.lib.tdcoracle_rle_encode.restype = ctypes.c_int64
+        self.lib.tdcoracle_literal_encode.restype = ctypes.c_int64
 
     def textds(self, t):
         n = t.size
@@ -78,6 +80,31 @@ class Oracle:
         assert m >= 0
         return out[:m].copy(), int(nbits.value)
 
+    def mtf_encode(self, data):
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.zeros(data.size, np.uint8)
+        self.lib.tdcoracle_mtf_encode(_P(data), ctypes.c_uint64(data.size), _P(out))
+        return out
+
+    def rle_encode(self, data, offset=0):
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.zeros(12 * data.size + 16, np.uint8)
+        m = self.lib.tdcoracle_rle_encode(_P(data), ctypes.c_uint64(data.size), ctypes.c_uint64(offset), _P(out), ctypes.c_uint64(out.size))
+        assert m >= 0
+        return out[:m].copy()
+
+    def literal_encode(self, data, codes, lens, lead_bits=0, lead_byte=0, finalize=True):
+        data = np.ascontiguousarray(data, np.uint8)
+        codes = np.ascontiguousarray(codes, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        out = np.zeros(8 * data.size + 64, np.uint8)
+        nbits = ctypes.c_uint64()
+        m = self.lib.tdcoracle_literal_encode(_P(data), ctypes.c_uint64(data.size), _P(codes), _P(lens), ctypes.c_uint32(lead_bits),
+                                              ctypes.c_uint8(lead_byte), ctypes.c_int(1 if finalize else 0), _P(out),
+                                              ctypes.c_uint64(out.size), ctypes.byref(nbits))
+        assert m >= 0
+        return out[:m].copy(), int(nbits.value)
+
     def decode(self, triples, text):
         tr = np.ascontiguousarray(triples, np.uint32)
         out = np.zeros(text.size, np.uint8)
@@ -95,7 +122,7 @@ class Reference:
             pytest.skip("oracle/_ref/libtdcref.so not built (needs /root/reference; run `make -C oracle ref`)")
         self.lib = ctypes.CDLL(path)
         for f in ("tdcref_lzss_lcp_factors", "tdcref_lzss_lcp_compress", "tdcref_lzss_lcp_decompress", "tdcref_escape",
-                  "tdcref_bwt_compress"):
+                  "tdcref_bwt_compress", "tdcref_stream_stage"):
             getattr(self.lib, f).restype = ctypes.c_int64
         self.lib.tdcref_last_error.restype = ctypes.c_char_p
 
@@ -141,6 +168,15 @@ class Reference:
         assert rc == 0, self.lib.tdcref_last_error()
         nb = (int(bits.value) + 7) // 8
         return head[:nb].copy(), int(bits.value), codes, lens
+
+    def stream_stage(self, stage, data, offset=0):
+        """0 = mtf, 1 = rle(offset), 2 = encode(bit), 3 = encode(huff) through the reference's own Compressor classes"""
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.zeros(12 * data.size + 4096, np.uint8)
+        m = self.lib.tdcref_stream_stage(stage, _P(data) if data.size else None, ctypes.c_uint64(data.size), ctypes.c_uint64(offset),
+                                         _P(out), ctypes.c_uint64(out.size), None)
+        assert 0 <= m <= out.size, self.lib.tdcref_last_error()
+        return out[:m].copy()
 
     def decompress(self, arc, coder, n):
         out = np.zeros(n + 16, np.uint8)

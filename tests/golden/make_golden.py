@@ -57,6 +57,48 @@ def main():
     path = os.path.join(HERE, "reference_vectors.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes,", len(names), "cases")
+    make_stream_stage_vectors(ref)
+
+
+def stream_stage_inputs():
+    """Inputs of the stream stages behind the BWT (mtf / rle / encode): seeded, incl. bytes >= 0x80 in runs (the reference's
+    signed-char run counter), long runs, and a real BWT -> MTF chain."""
+    rng = np.random.default_rng(2024)
+    t = synth.markov_text(20000, 9)
+    cases = {
+        "empty": np.zeros(0, np.uint8), "one": np.array([65], np.uint8), "pair": np.array([65, 65], np.uint8),
+        "run_low": np.full(5000, 97, np.uint8), "run_high": np.full(700, 200, np.uint8),
+        "random": rng.integers(0, 256, 20000, dtype=np.uint8), "two_symbols": rng.integers(65, 67, 20000, dtype=np.uint8),
+        "runs_mixed": np.repeat(rng.integers(0, 256, 900, dtype=np.uint8), rng.integers(1, 40, 900)),
+        "long_runs": np.repeat(rng.integers(0, 100, 30, dtype=np.uint8), rng.integers(1, 3000, 30)),
+        "markov": t,
+    }
+    return cases
+
+
+def make_stream_stage_vectors(ref):
+    out, names = {}, []
+    for name, d in stream_stage_inputs().items():
+        names.append(name)
+        out[f"{name}/in"] = d
+        out[f"{name}/mtf"] = ref.stream_stage(0, d)
+        for off in (0, 1, 300):
+            out[f"{name}/rle{off}"] = ref.stream_stage(1, d, off)
+        out[f"{name}/enc_bit"] = ref.stream_stage(2, d)
+        out[f"{name}/enc_huff"] = ref.stream_stage(3, d)
+        hist = np.bincount(d, minlength=256).astype(np.uint64)
+        head, hbits, codes, lens = ref.literal_coder(1, hist)
+        out[f"{name}/huff_head"], out[f"{name}/huff_head_bits"] = head, np.array([hbits], np.uint64)
+        out[f"{name}/huff_codes"], out[f"{name}/huff_lens"] = codes, lens
+    # the chain of config 3 on a real BWT: bwt -> mtf -> rle
+    t = synth.markov_text(20000, 9)
+    b = ref.bwt(t)
+    out["chain/bwt"], out["chain/mtf"] = b, ref.stream_stage(0, b)
+    out["chain/rle"] = ref.stream_stage(1, out["chain/mtf"], 0)
+    out["names"] = np.array(names)
+    path = os.path.join(HERE, "stream_stage_vectors.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(names), "cases")
 
 
 if __name__ == "__main__":

@@ -64,7 +64,8 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
     for name, data in cases.items():
         src = tmp_path / f"{name}.bin"
         src.write_bytes(data)
-        for algo in ("lzss_lcp(coder=huff)", "lzss_lcp(coder=bit,threshold=5)", "lzss_lcp(coder=ascii)", "bwt"):
+        for algo in ("lzss_lcp(coder=huff)", "lzss_lcp(coder=bit,threshold=5)", "lzss_lcp(coder=ascii)", "bwt",
+                     "bwt:mtf:rle:encode(huff)", "mtf:rle(offset=2):encode(bit)"):  # all four stages of config 3 on the "device"
             a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc")
             assert _run(REF, algo, str(src), a).returncode == 0
             r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", b, "--force"], capture_output=True, text=True, env=env)

@@ -1,0 +1,113 @@
+"""The stream stages behind the BWT in `bwt:mtf:rle:encode(huff)` (BASELINE config 3):
+mtf_encode (MTFCompressor.hpp:46-56), rle_encode (RunLengthEncoder.hpp:15-31), LiteralEncoder (LiteralEncoder.hpp:23-32).
+
+CPU: the oracle restatements against the committed outputs of the unmodified reference (tests/golden/stream_stage_vectors.npz)
+and against oracle/_ref on fresh inputs; the kernels in the tests/sim interpreter.  GPU: the CUDA path through the C ABI
+against the golden outputs, and against the oracle at 16-64 MiB.  Byte-exact."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from tudocomp_b200 import _abi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "stream_stage_vectors.npz")
+SIM = os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so")
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _lead(head, bits):
+    return bits % 8, (int(head[bits // 8]) if bits % 8 else 0)
+
+
+def _huff(gold, name):
+    return gold[f"{name}/huff_head"], int(gold[f"{name}/huff_head_bits"][0]), gold[f"{name}/huff_codes"], gold[f"{name}/huff_lens"]
+
+
+def test_oracle_matches_golden_stage_outputs(oracle, gold):
+    for name in gold["names"]:
+        d = gold[f"{name}/in"]
+        assert np.array_equal(oracle.mtf_encode(d), gold[f"{name}/mtf"]), name
+        for off in (0, 1, 300):
+            assert np.array_equal(oracle.rle_encode(d, off), gold[f"{name}/rle{off}"]), (name, off)
+        body, _ = oracle.literal_encode(d, np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8))
+        assert np.array_equal(body, gold[f"{name}/enc_bit"]), name
+        head, hb, codes, lens = _huff(gold, name)
+        lb, lbyte = _lead(head, hb)
+        body, _ = oracle.literal_encode(d, codes, lens, lb, lbyte)
+        assert np.array_equal(np.concatenate([head[:hb // 8], body]), gold[f"{name}/enc_huff"]), name
+    assert np.array_equal(oracle.mtf_encode(gold["chain/bwt"]), gold["chain/mtf"])
+    assert np.array_equal(oracle.rle_encode(gold["chain/mtf"], 0), gold["chain/rle"])
+
+
+def test_oracle_matches_reference_on_fresh_inputs(oracle, reference):
+    rng = np.random.default_rng(77)
+    for name, d in (("random", rng.integers(0, 256, 30000, dtype=np.uint8)), ("dna", synth.dna(30000, 5)[:-1]),
+                    ("runs", np.repeat(rng.integers(0, 256, 500, dtype=np.uint8), rng.integers(1, 200, 500)))):
+        assert np.array_equal(oracle.mtf_encode(d), reference.stream_stage(0, d)), name
+        assert np.array_equal(oracle.rle_encode(d, 7), reference.stream_stage(1, d, 7)), name
+
+
+def _device_checks(lib, oracle, gold, names, device=0):
+    with _abi.Context(lib, device) as c:
+        for name in names:
+            d = gold[f"{name}/in"]
+            assert np.array_equal(c.mtf_encode(d), gold[f"{name}/mtf"]), name
+            for off in (0, 1, 300):
+                assert np.array_equal(c.rle_encode(d, off), gold[f"{name}/rle{off}"]), (name, off)
+            assert np.array_equal(c.literal_histogram_of(d), np.bincount(d, minlength=256).astype(np.uint64)), name
+            assert np.array_equal(c.literal_encode(np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8)), gold[f"{name}/enc_bit"]), name
+            head, hb, codes, lens = _huff(gold, name)
+            lb, lbyte = _lead(head, hb)
+            c.literal_histogram_of(d)
+            body = c.literal_encode(codes, lens, lb, lbyte)
+            assert np.array_equal(np.concatenate([head[:hb // 8], body]), gold[f"{name}/enc_huff"]), name
+        assert np.array_equal(c.mtf_encode(gold["chain/bwt"]), gold["chain/mtf"])
+        assert np.array_equal(c.rle_encode(gold["chain/mtf"], 0), gold["chain/rle"])
+
+
+@pytest.mark.sim
+def test_sim_stream_stages(oracle, gold):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    lib = _abi.TdcGpuLib(SIM)
+    small = [n for n in gold["names"] if gold[f"{n}/in"].size <= 5000] + ["two_symbols", "runs_mixed"]
+    _device_checks(lib, oracle, gold, small)
+    with _abi.Context(lib) as c:
+        with pytest.raises(_abi.TdcGpuError):
+            c.literal_encode(np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8))  # nothing staged
+
+
+@pytest.mark.gpu
+def test_gpu_stream_stages_golden(oracle, gold):
+    import tudocomp_b200 as tdc
+    _device_checks(tdc.load(), oracle, gold, list(gold["names"]))
+
+
+@pytest.mark.gpu
+def test_gpu_stream_stages_large(oracle):
+    """16-64 MiB: a real BWT (from the GPU) through mtf -> rle -> encode against the oracle; random bytes (MTF worst case)."""
+    import tudocomp_b200 as tdc
+    lib = tdc.load()
+    rng = np.random.default_rng(9)
+    with _abi.Context(lib, 0) as c:
+        t = synth.repetitive(1 << 24, 3, block=1 << 16, p=0.01)
+        c.set_text(t)
+        c.build(tdc.SA | tdc.BWT)
+        inputs = {"bwt_repetitive_16m": c.get(tdc.BWT), "random_16m": rng.integers(0, 256, 1 << 24, dtype=np.uint8),
+                  "runs_64m": np.repeat(rng.integers(0, 256, 1 << 16, dtype=np.uint8), 1024)}
+        for name, d in inputs.items():
+            m = c.mtf_encode(d)
+            assert np.array_equal(m, oracle.mtf_encode(d)), name
+            r = c.rle_encode(m, 0)
+            assert np.array_equal(r, oracle.rle_encode(m, 0)), name
+            hist = c.literal_histogram_of(r)
+            assert np.array_equal(hist, np.bincount(r, minlength=256).astype(np.uint64)), name
+            codes, lens = np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8)
+            want, _ = oracle.literal_encode(r, codes, lens)
+            assert np.array_equal(c.literal_encode(codes, lens), want), name

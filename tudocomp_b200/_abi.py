@@ -20,6 +20,7 @@ EXPORTS = [
     "tdcgpu_event_record", "tdcgpu_event_elapsed_ms", "tdcgpu_launch_count", "tdcgpu_profile_enable",
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
     "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
+    "tdcgpu_mtf_encode", "tdcgpu_rle_encode", "tdcgpu_literal_encode_begin", "tdcgpu_literal_encode", "tdcgpu_literal_encode_get",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -45,6 +46,11 @@ class TdcGpuLib:
         L.tdcgpu_textds_build.argtypes = [C.c_void_p, C.c_uint32]
         L.tdcgpu_textds_get.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int]
         L.tdcgpu_textds_get_packed.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.c_int]
+        L.tdcgpu_mtf_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        L.tdcgpu_rle_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+        L.tdcgpu_literal_encode_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+        L.tdcgpu_literal_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.POINTER(C.c_uint64)]
+        L.tdcgpu_literal_encode_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         L.tdcgpu_textds_device_ptr.argtypes = [C.c_void_p, C.c_uint32]
         L.tdcgpu_textds_device_ptr.restype = C.c_void_p
         L.tdcgpu_textds_max_lcp.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
@@ -206,6 +212,38 @@ class Context:
         self.lib.check(self.lib.lib.tdcgpu_lzss_encode_get(self._h, C.c_void_p(host_ptr), cap, 1 if finalize else 0,
                                                            C.byref(nb), 0))
         return int(nb.value)
+
+    # -- byte-stream stages behind the BWT -------------------------------------------------------------------------
+    def mtf_encode(self, data: np.ndarray) -> np.ndarray:
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.empty(data.size, np.uint8)
+        self.lib.check(self.lib.lib.tdcgpu_mtf_encode(self._h, _host_ptr(data), data.size, _host_ptr(out), 0))
+        return out
+
+    def rle_encode(self, data: np.ndarray, offset: int = 0) -> np.ndarray:
+        data = np.ascontiguousarray(data, np.uint8)
+        out = np.empty(12 * data.size + 32, np.uint8)
+        m = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_rle_encode(self._h, _host_ptr(data), data.size, offset, _host_ptr(out), out.size, C.byref(m), 0))
+        return out[:int(m.value)].copy()
+
+    def literal_histogram_of(self, data: np.ndarray) -> np.ndarray:
+        """LiteralEncoder step 1: stage `data` on the device, return its byte histogram."""
+        data = np.ascontiguousarray(data, np.uint8)
+        hist = np.zeros(256, np.uint64)
+        self.lib.check(self.lib.lib.tdcgpu_literal_encode_begin(self._h, _host_ptr(data), data.size, 0, _host_ptr(hist)))
+        return hist
+
+    def literal_encode(self, codes: np.ndarray, lens: np.ndarray, lead_bits: int = 0, lead_byte: int = 0, finalize: bool = True) -> np.ndarray:
+        """LiteralEncoder steps 2+3 on the staged data: the bit stream (with BitOStream's tail when finalize)."""
+        codes = np.ascontiguousarray(codes, np.uint64)
+        lens = np.ascontiguousarray(lens, np.uint8)
+        nbits = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_literal_encode(self._h, _host_ptr(codes), _host_ptr(lens), lead_bits, lead_byte, C.byref(nbits)))
+        out = np.empty(int(nbits.value) // 8 + 2, np.uint8)
+        nb = C.c_uint64()
+        self.lib.check(self.lib.lib.tdcgpu_literal_encode_get(self._h, _host_ptr(out), out.size, 1 if finalize else 0, C.byref(nb), 0))
+        return out[:int(nb.value)].copy()
 
     # -- stats -----------------------------------------------------------------------------------------------------
     def phases(self):

@@ -87,6 +87,16 @@ struct Ctx {
     uint8_t* h_stage = nullptr;
     size_t h_stage_cap = 0;
 
+    // byte-stream stages (stream_codecs.cu): one grow-only device buffer, independent of the text-index arrays
+    Arena stream_arena;
+    struct LiteralStage {  // tdcgpu_literal_encode_begin .. _get: the staged input and the encoded stream
+        u64 gen = 0, n = 0, nbits = 0;
+        const uint8_t* d_in = nullptr;
+        uint8_t* d_out = nullptr;
+        u64 out_cap = 0;
+        bool staged = false, encoded = false;
+    } lit;
+
     cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
     std::vector<u64> h_samples;  // host copy of the sorted prefix sample (key-length cost model)
@@ -111,6 +121,17 @@ int build_lcp_direct(Ctx& c);  // LCP without Phi/PLCP (texts with short common 
 static const u32 LCP_UNKNOWN = 0xffffffffu;  // LCP slot of a pair the initial keys could not separate
 // lzss_factorize.cu
 int factorize_lzss_lcp(Ctx& c, u32 threshold);
+// stream_codecs.cu — device pointers in, device pointers out; scratch from c.stream_arena (after the caller's buffers)
+int stream_arena_reserve(Ctx& c, size_t bytes);
+size_t mtf_scratch_bytes(u64 n);
+int mtf_encode_device(Ctx& c, const uint8_t* d_in, u64 n, uint8_t* d_out);
+size_t rle_scratch_bytes(u64 n);
+u64 rle_max_output(u64 n, u64 offset);
+int rle_encode_device(Ctx& c, const uint8_t* d_in, u64 n, u64 offset, uint8_t* d_out, u64* out_n);
+size_t literal_scratch_bytes(u64 n);
+int stream_histogram_device(Ctx& c, const uint8_t* d_in, u64 n, u64 hist[256]);
+int literal_encode_device(Ctx& c, const uint8_t* d_in, u64 n, const u64* codes, const uint8_t* lens, u32 lead_bits, u32 lead_byte,
+                          u64* nbits);
 // lzss_encode.cu
 int encode_prepare(Ctx& c);  // masks, scans, literal histogram, fdist_max of the current factor list
 int encode_lzss(Ctx& c, const u64* codes, const uint8_t* lens, u32 lead_bits, u32 lead_byte);

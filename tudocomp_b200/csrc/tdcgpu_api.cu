@@ -277,6 +277,8 @@ void tdcgpu_destroy(tdcgpu_ctx* ctx) {
     free_arrays(c);
     sort_workspace_free(c.sortws);
     if (c.d_factors) cudaFree(c.d_factors);
+    if (c.stream_arena.base) cudaFree(c.stream_arena.base);
+    if (c.lit.d_out) cudaFree(c.lit.d_out);
     if (c.d_scalars) cudaFree(c.d_scalars);
     if (c.h_scalars) cudaFreeHost(c.h_scalars);
     for (auto& e : c.user_events)
@@ -405,22 +407,21 @@ int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t
     return 0;
 }
 
-int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
-    API_GUARD(ctx);
-    if (!c.enc.encoded || c.enc.gen != c.arena.gen) { set_error("no encoded stream (call tdcgpu_lzss_encode first)"); return TDCGPU_ERR_STATE; }
-    const u64 nbits = c.enc.nbits, whole = nbits / 8;
+// Copy a device bit stream of `nbits` bits out; finalize appends BitOStream::~BitOStream's tail (io/BitOStream.hpp:53-64):
+// the number of bits used in the current byte goes into its low 3 bits if they are free (used <= 5; an untouched byte is
+// written as 0), otherwise the byte is flushed and the count follows in a byte of its own.
+static int copy_bitstream_out(Ctx& c, const uint8_t* d_stream, u64 nbits, uint8_t* dst, u64 cap, int finalize, u64* nbytes, int to_device) {
+    const u64 whole = nbits / 8;
     const u32 used = u32(nbits % 8);
-    // BitOStream::~BitOStream (io/BitOStream.hpp:53-64): `used` goes into the low 3 bits of the current byte if they are
-    // free (used <= 5; an untouched byte is written as 0), otherwise the byte is flushed and `used` follows in its own byte
     const u64 total = finalize ? whole + (used <= 5 ? 1 : 2) : whole + (used ? 1 : 0);
     if (nbytes) *nbytes = total;
     if (total > cap) { set_error("encode buffer too small: %llu > %llu", (unsigned long long)total, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     const u64 body = whole + (used ? 1 : 0);
-    TDC_CUDA(cudaMemcpyAsync(dst, c.enc.out, body, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (body) TDC_CUDA(cudaMemcpyAsync(dst, d_stream, body, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
     if (finalize) {
         uint8_t tail[2] = {0, 0};
-        if (used) TDC_CUDA(cudaMemcpyAsync(&tail[0], c.enc.out + whole, 1, cudaMemcpyDeviceToHost, c.stream));
+        if (used) TDC_CUDA(cudaMemcpyAsync(&tail[0], d_stream + whole, 1, cudaMemcpyDeviceToHost, c.stream));
         TDC_CUDA(cudaStreamSynchronize(c.stream));
         u64 ntail;
         if (used <= 5) { tail[0] |= uint8_t(used); ntail = 1; } else { tail[1] = uint8_t(used); ntail = 2; }
@@ -429,6 +430,108 @@ int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int fina
     }
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
+}
+
+int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
+    API_GUARD(ctx);
+    if (!c.enc.encoded || c.enc.gen != c.arena.gen) { set_error("no encoded stream (call tdcgpu_lzss_encode first)"); return TDCGPU_ERR_STATE; }
+    return copy_bitstream_out(c, c.enc.out, c.enc.nbits, dst, cap, finalize, nbytes, to_device);
+}
+
+// in/out staging of the stream stages: [in (n) | out (out_cap) | scratch]
+static int stream_stage_in(Ctx& c, const uint8_t* in, u64 n, u64 out_cap, size_t scratch, int on_device, const uint8_t** d_in, uint8_t** d_out) {
+    TDC_TRY(stream_arena_reserve(c, size_t(on_device ? 0 : n + out_cap + 512) + scratch + 4096));
+    if (on_device) { *d_in = in; return 0; }
+    uint8_t* di = c.stream_arena.take<uint8_t>(n + 16);
+    *d_out = c.stream_arena.take<uint8_t>(out_cap + 16);
+    if (!di || !*d_out) { set_error("stream scratch too small"); return TDCGPU_ERR_NOMEM; }
+    if (n) TDC_CUDA(cudaMemcpyAsync(di, in, n, cudaMemcpyHostToDevice, c.stream));
+    *d_in = di;
+    return 0;
+}
+
+int tdcgpu_mtf_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* out, int on_device) {
+    API_GUARD(ctx);
+    if (n == 0) return 0;
+    if (!in || !out) { set_error("null buffer"); return TDCGPU_ERR_ARG; }
+    c.phases.clear();
+    const uint8_t* d_in = nullptr;
+    uint8_t* d_out = out;
+    TDC_TRY(stream_stage_in(c, in, n, n, mtf_scratch_bytes(n), on_device, &d_in, &d_out));
+    {
+        PhaseTimer t(c, "MTF");
+        TDC_TRY(mtf_encode_device(c, d_in, n, d_out));
+    }
+    if (!on_device) TDC_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, c.stream));
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_rle_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t offset, uint8_t* out, uint64_t cap, uint64_t* out_n,
+                      int on_device) {
+    API_GUARD(ctx);
+    if (out_n) *out_n = 0;
+    if (n == 0) return 0;
+    if (!in || !out) { set_error("null buffer"); return TDCGPU_ERR_ARG; }
+    c.phases.clear();
+    const u64 worst = rle_max_output(n, offset);
+    if (on_device && cap < worst) { set_error("rle: a device output buffer must hold the worst case (%llu bytes)", (unsigned long long)worst); return TDCGPU_ERR_ARG; }
+    const uint8_t* d_in = nullptr;
+    uint8_t* d_out = out;
+    TDC_TRY(stream_stage_in(c, in, n, worst, rle_scratch_bytes(n), on_device, &d_in, &d_out));
+    u64 produced = 0;
+    {
+        PhaseTimer t(c, "RLE");
+        TDC_TRY(rle_encode_device(c, d_in, n, offset, d_out, &produced));
+    }
+    if (out_n) *out_n = produced;
+    if (!on_device) {
+        if (produced > cap) { set_error("rle: output buffer too small: %llu > %llu", (unsigned long long)produced, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
+        TDC_CUDA(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, c.stream));
+    }
+    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    return 0;
+}
+
+int tdcgpu_literal_encode_begin(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, int on_device, uint64_t hist[256]) {
+    API_GUARD(ctx);
+    if (n && !in) { set_error("null buffer"); return TDCGPU_ERR_ARG; }
+    if (!hist) { set_error("null histogram"); return TDCGPU_ERR_ARG; }
+    c.phases.clear();
+    c.lit.staged = c.lit.encoded = false;
+    const uint8_t* d_in = nullptr;
+    uint8_t* d_unused = nullptr;
+    TDC_TRY(stream_stage_in(c, in, n, 0, literal_scratch_bytes(n), on_device, &d_in, &d_unused));
+    {
+        PhaseTimer t(c, "Literal histogram");
+        TDC_TRY(stream_histogram_device(c, d_in, n, hist));
+    }
+    c.lit.d_in = d_in;
+    c.lit.n = n;
+    c.lit.gen = c.stream_arena.gen;
+    c.lit.staged = true;
+    return 0;
+}
+
+int tdcgpu_literal_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t lens[256], uint32_t lead_bits, uint8_t lead_byte,
+                          uint64_t* nbits) {
+    API_GUARD(ctx);
+    if (!codes || !lens) { set_error("null code table"); return TDCGPU_ERR_ARG; }
+    if (!c.lit.staged || c.lit.gen != c.stream_arena.gen) { set_error("no staged input (call tdcgpu_literal_encode_begin first)"); return TDCGPU_ERR_STATE; }
+    c.phases.clear();
+    {
+        PhaseTimer t(c, "Literal encode");
+        TDC_TRY(literal_encode_device(c, c.lit.d_in, c.lit.n, codes, lens, lead_bits, lead_byte, &c.lit.nbits));
+    }
+    c.lit.encoded = true;
+    if (nbits) *nbits = c.lit.nbits;
+    return 0;
+}
+
+int tdcgpu_literal_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
+    API_GUARD(ctx);
+    if (!c.lit.encoded) { set_error("no encoded stream (call tdcgpu_literal_encode first)"); return TDCGPU_ERR_STATE; }
+    return copy_bitstream_out(c, c.lit.d_out, c.lit.nbits, dst, cap, finalize, nbytes, to_device);
 }
 
 int tdcgpu_textds_build_host(int device, const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp,

@@ -60,11 +60,23 @@ lcpcomp = [] if mode == "only" else [
     AlgorithmConfig(name="LCPCompressor", header="compressors/LCPCompressor.hpp", sub=[lcpcomp_coders, lcpcomp_comp, lcpcomp_dec, lcpcomp_textds]),
 ]
 
-tdc.compressors = lcpcomp + [
-    AlgorithmConfig(name="RunLengthEncoder", header="compressors/RunLengthEncoder.hpp"),
-    AlgorithmConfig(name="LiteralEncoder", header="compressors/LiteralEncoder.hpp", sub=[coders]),
+# The stream stages behind the BWT (config 3, `bwt:mtf:rle:encode(huff)`): in the GPU-only registry the same names resolve
+# to the GPU classes of tudocomp_gpu/GpuStreamStages.hpp (same Meta, same bytes); elsewhere to the reference's.
+if mode == "only":
+    stream_stages = [
+        AlgorithmConfig(name="GpuRunLengthEncoder", header="../tudocomp_gpu/GpuStreamStages.hpp"),
+        AlgorithmConfig(name="GpuLiteralEncoder", header="../tudocomp_gpu/GpuStreamStages.hpp", sub=[coders]),
+        AlgorithmConfig(name="GpuMTFCompressor", header="../tudocomp_gpu/GpuStreamStages.hpp"),
+    ]
+else:
+    stream_stages = [
+        AlgorithmConfig(name="RunLengthEncoder", header="compressors/RunLengthEncoder.hpp"),
+        AlgorithmConfig(name="LiteralEncoder", header="compressors/LiteralEncoder.hpp", sub=[coders]),
+        AlgorithmConfig(name="MTFCompressor", header="compressors/MTFCompressor.hpp"),
+    ]
+
+tdc.compressors = lcpcomp + stream_stages + [
     AlgorithmConfig(name="LZSSLCPCompressor", header="compressors/LZSSLCPCompressor.hpp", sub=[coders, textds]),
-    AlgorithmConfig(name="MTFCompressor", header="compressors/MTFCompressor.hpp"),
     AlgorithmConfig(name="NoopCompressor", header="compressors/NoopCompressor.hpp"),
     AlgorithmConfig(name="BWTCompressor", header="compressors/BWTCompressor.hpp", sub=[textds]),
     AlgorithmConfig(name="ChainCompressor", header="../tudocomp_driver/ChainCompressor.hpp"),
