@@ -59,12 +59,22 @@ struct Voidify { template <class T> void operator&(T&&) {} };
 #define DCHECK_GE(a, b) CHECK_GE(a, b)
 #endif
 
+// LOG evaluates its operands (glog would format and emit them); DLOG / DVLOG compile to dead code under NDEBUG exactly
+// like glog's own definitions (`true ? (void)0 : LogMessageVoidify() & LOG(...)`), and VLOG is guarded by VLOG_IS_ON:
+// their operands are NOT evaluated.  (An earlier version of this shim evaluated them, which made e.g.
+// ChainCompressor's `DLOG(INFO) << vec_to_debug_string(between_buf)` format every intermediate buffer: 75 ns per byte and
+// chain link that a real Release build of the reference does not pay.)
 #define LOG(sev) TDC_SHIM_NULL()
-#define DLOG(sev) TDC_SHIM_NULL()
-#define VLOG(lvl) TDC_SHIM_NULL()
-#define DVLOG(lvl) TDC_SHIM_NULL()
 #define LOG_IF(sev, c) TDC_SHIM_NULL()
 #define VLOG_IS_ON(lvl) false
+#define VLOG(lvl) TDC_SHIM_DEAD(0)
+#ifdef NDEBUG
+#define DLOG(sev) TDC_SHIM_DEAD(0)
+#define DVLOG(lvl) TDC_SHIM_DEAD(0)
+#else
+#define DLOG(sev) TDC_SHIM_NULL()
+#define DVLOG(lvl) TDC_SHIM_NULL()
+#endif
 
 static int FLAGS_logtostderr __attribute__((unused)) = 1;
 static int FLAGS_v __attribute__((unused)) = 0;

@@ -73,7 +73,7 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
             assert open(a, "rb").read() == open(b, "rb").read(), (name, algo)
     # lcpcomp: the reference's own strategies consume the GPU text index through require_* / release_*
     # (arrays come back bit-packed by the device, compress=delayed); mixed registry, so compare under --raw
-    for name in ("markov", "binary_with_escapes", "empty"):
+    for name in ("markov", "empty"):
         src = str(tmp_path / f"{name}.bin")
         for opts in ("coder=huff", "coder=ascii,comp=heap", "coder=huff,comp=max_lcp", "coder=huff,comp=plcppeaks,dec=compact"):
             a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc")

@@ -86,7 +86,7 @@ def test_sim_key_layouts(simlib, oracle):
     from tudocomp_b200 import synth
     rng = np.random.default_rng(77)
     cases = []
-    for sigma in (1, 2, 3, 4, 7, 8, 16, 100, 128, 254, 255):
+    for sigma in (1, 2, 3, 4, 8, 100, 255):
         body = rng.integers(1, sigma + 1, 2500, dtype=np.uint16).astype(np.uint8)
         cases.append((f"sigma{sigma}", synth.with_sentinel(body)))
         tail = np.concatenate([body[:700], np.full(40, 1, np.uint8)])  # ...AAAA$ : padded keys would tie

@@ -161,7 +161,7 @@ mtf_tile_kernel(const uint8_t* __restrict__ in, u64 n, uint8_t* __restrict__ til
                         const uint8_t cur = slots[k * MTF_THREADS + t];
                         slots[k * MTF_THREADS + t] = prev;
                         prev = cur;
-                    } while (prev != c);
+                    } while (prev != c && k < 255);  // (the table is a permutation; the bound only guards against a hang)
                     slots[t] = c;
                 }
                 dst[j] = uint8_t(k);
