@@ -32,7 +32,7 @@ struct OwnerFn {  // position-sharded arrays: owner = position / block, the owne
 };
 
 static const int BP_THREADS = 256;
-static const int BP_IPT = 4;
+static const int BP_IPT = 8;
 static const int BP_TILE = BP_THREADS * BP_IPT;
 
 template <class K, class F>
@@ -64,15 +64,22 @@ struct BucketDst {
 };
 
 // vals == nullptr: the value of element i is vbase + i.  vals2: optional second value travelling with the first.
+// The tile is staged in shared memory in bucket order and written out run by run, so that a warp's stores to a peer are
+// whole consecutive lines (with one store per thread straight from registers, a warp hit all P buckets at once and the
+// NVLink writes were 32-byte fragments: the push was 40 % of the 8-GPU step, profiles/r1m_summary.md).
 template <class K, class F>
 static __global__ void __launch_bounds__(BP_THREADS)
 bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, u32 vbase, u64 m, F f, int nbuckets,
                       ull* __restrict__ cursor, BucketDst dst, const u32* __restrict__ vals2) {
     __shared__ u32 cnt[DIST_MAX_RANKS];
+    __shared__ u32 start[DIST_MAX_RANKS + 1];
     __shared__ ull gbase[DIST_MAX_RANKS];
     __shared__ K* kb[DIST_MAX_RANKS];
     __shared__ u32* vb[DIST_MAX_RANKS];
     __shared__ u32* v2b[DIST_MAX_RANKS];
+    __shared__ K s_key[BP_TILE];
+    __shared__ u32 s_val[BP_TILE];
+    __shared__ u32 s_val2[BP_TILE];
     if (threadIdx.x < DIST_MAX_RANKS) {
         cnt[threadIdx.x] = 0;
         kb[threadIdx.x] = static_cast<K*>(dst.k[threadIdx.x]);
@@ -99,16 +106,38 @@ bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, 
     }
     __syncthreads();
     if (threadIdx.x < u32(nbuckets)) gbase[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], ull(cnt[threadIdx.x])) : 0;
+    if (threadIdx.x == 0) {
+        u32 run = 0;
+        for (int bb = 0; bb < DIST_MAX_RANKS; bb++) {
+            start[bb] = run;
+            if (bb < nbuckets) run += cnt[bb];
+        }
+        start[DIST_MAX_RANKS] = run;
+    }
     __syncthreads();
+    // ---- stage in bucket order ----
 #pragma unroll
     for (int q = 0; q < BP_IPT; q++) {
         const u64 i = t0 + u64(q) * BP_THREADS + threadIdx.x;
         if (i < m) {
-            const u64 o = gbase[b[q]] + lr[q];
-            kb[b[q]][o] = f.out(key[q], b[q]);
-            vb[b[q]][o] = vals ? vals[i] : vbase + u32(i);
-            if (vals2) v2b[b[q]][o] = vals2[i];
+            const u32 p = start[b[q]] + lr[q];
+            s_key[p] = f.out(key[q], b[q]);
+            s_val[p] = vals ? vals[i] : vbase + u32(i);
+            if (vals2) s_val2[p] = vals2[i];
         }
+    }
+    __syncthreads();
+    // ---- runs out: consecutive threads, consecutive addresses of the same bucket ----
+    const u32 total = start[DIST_MAX_RANKS];
+    for (u32 j = threadIdx.x; j < total; j += BP_THREADS) {
+        u32 bj = 0;
+#pragma unroll
+        for (int x = 1; x < DIST_MAX_RANKS; x++)
+            if (x < nbuckets && start[x] <= j) bj = u32(x);  // starts are non-decreasing: the last one not above j
+        const u64 o = gbase[bj] + (j - start[bj]);
+        kb[bj][o] = s_key[j];
+        vb[bj][o] = s_val[j];
+        if (vals2) v2b[bj][o] = s_val2[j];
     }
 }
 

@@ -15,23 +15,27 @@ namespace tdc {
 // unseen symbols in their initial (ascending) order.  Hence the effect of a block of text on ANY incoming table T is
 //         T' = R ++ (T \ R),      R = the block's distinct symbols ordered by last occurrence, most recent first,
 // an associative operator.  Three kernels:
-//   1. mtf_tile_kernel<false>: every thread builds R for its chunk (one backward pass), one warp folds the chunks of the
-//      tile (starting from 0..255) into the tile's own (R, |R|);
+//   1. mtf_tile_kernel<false>: every thread builds R for its chunk (one backward pass); every warp folds its 32 chunks
+//      (starting from 0..255), one warp folds the warps' results into the tile's own (R, |R|);
 //   2. mtf_scan_kernel: one warp folds the tiles in order: incoming table of every tile;
-//   3. mtf_tile_kernel<true>: chunk lists again, folded from the tile's incoming table, which leaves every thread the
-//      exact table at the start of its chunk; then each thread runs the reference's loop on its own chunk with its own
-//      table in shared memory (cost per byte ~ the emitted rank, which is small on BWT output).
+//   3. mtf_tile_kernel<true>: chunk lists and warp results again; the warp results folded from the tile's incoming table
+//      give every warp its incoming table, from which it folds its chunks once more — that leaves every thread the exact
+//      table at the start of its chunk (32 + warps + 32 sequential fold steps instead of one per chunk of the tile);
+//      then each thread runs the reference's loop on its own chunk with its own table in shared memory (cost per byte
+//      ~ the emitted rank, which is small on BWT output).
 // Tables live in shared memory symbol-index-major (entry k of thread t at k * MTF_THREADS + t).
 // =====================================================================================================================
 #ifdef TDC_CUSIM
-static const u32 MTF_THREADS = 32;   // small tiles so that the CPU tests cross many chunk and tile boundaries
+static const u32 MTF_THREADS = 64;   // small tiles so that the CPU tests cross many chunk, warp and tile boundaries
 static const u32 MTF_CHUNK = 16;
 #else
 static const u32 MTF_THREADS = 256;
 static const u32 MTF_CHUNK = 1024;   // bytes per thread (multiple of 16)
 #endif
 static const u32 MTF_TILE = MTF_THREADS * MTF_CHUNK;
-static inline size_t mtf_smem_bytes() { return size_t(256) * MTF_THREADS + 512 + 64 + 2 * MTF_THREADS; }
+static const u32 MTF_WARPS = MTF_THREADS / 32;
+static const u32 MTF_FOLD_BYTES = 256 + 256 + 64;  // table, scratch table, two 8-word bitmaps: one fold context
+static inline size_t mtf_smem_bytes() { return size_t(256) * MTF_THREADS + size_t(MTF_WARPS + 1) * MTF_FOLD_BYTES + 2 * MTF_THREADS + 4 * MTF_WARPS + 64; }
 
 // One warp: T := R ++ (T \ R).  T: 256 bytes (plain layout) in shared memory; this lane holds R entries
 // [8 * lane, 8 * lane + 8) in r[], rc = |R|; bitmap: 8 shared words; tmp: 256 shared bytes.
@@ -72,11 +76,13 @@ mtf_tile_kernel(const uint8_t* __restrict__ in, u64 n, uint8_t* __restrict__ til
                 const uint8_t* __restrict__ incoming, uint8_t* __restrict__ out, bool vec16) {  // vec16: in and out are 16-byte aligned
     TDC_DYN_SMEM(smem_raw);
     uint8_t* slots = smem_raw;                                            // [256][MTF_THREADS]: chunk lists, then chunk tables
-    uint8_t* T = slots + 256 * MTF_THREADS;                               // [256] running table of the fold
-    uint8_t* tmp = T + 256;                                               // [256]
-    u32* bitmap = reinterpret_cast<u32*>(tmp + 256);                      // [8] (+ 8 spare)
-    unsigned short* cnts = reinterpret_cast<unsigned short*>(bitmap + 16);  // [MTF_THREADS] |R| of every chunk
-    const u32 t = threadIdx.x, lane = lane_id();
+    uint8_t* folds = slots + 256 * MTF_THREADS;                           // [MTF_WARPS + 1] fold contexts (last: the tile's)
+    unsigned short* cnts = reinterpret_cast<unsigned short*>(folds + (MTF_WARPS + 1) * MTF_FOLD_BYTES);  // [MTF_THREADS] |R| of every chunk
+    u32* warp_rc = reinterpret_cast<u32*>(cnts + MTF_THREADS);            // [MTF_WARPS] distinct symbols of every warp's chunks
+    const u32 t = threadIdx.x, lane = lane_id(), w = warp_id();
+    uint8_t* T = folds + w * MTF_FOLD_BYTES;                              // this warp's running table
+    uint8_t* tmp = T + 256;
+    u32* bitmap = reinterpret_cast<u32*>(tmp + 256);                      // [8] scratch of mtf_compose, [8] union of symbol sets
     const u64 tile_base = u64(blockIdx.x) * MTF_TILE;
     const u64 c0 = tile_base + u64(t) * MTF_CHUNK;                        // this thread's chunk [c0, c1)
     const u64 c1 = min(c0 + MTF_CHUNK, n);
@@ -101,39 +107,76 @@ mtf_tile_kernel(const uint8_t* __restrict__ in, u64 n, uint8_t* __restrict__ til
     }
     __syncthreads();
 
-    // ---- B. one warp folds the chunks in order ----
-    if (warp_id() == 0) {
+    // ---- B1. every warp folds its own 32 chunks from 0..255: (R_w, |R_w|) = the warp's effect on any table ----
+    {
 #pragma unroll
-        for (u32 j = 0; j < 8; j++) T[lane * 8 + j] = APPLY ? incoming[u64(blockIdx.x) * 256 + lane * 8 + j] : uint8_t(lane * 8 + j);
-        if (!APPLY && lane < 8) bitmap[8 + lane] = 0;  // union of the chunks' symbol sets
+        for (u32 j = 0; j < 8; j++) T[lane * 8 + j] = uint8_t(lane * 8 + j);
+        if (lane < 8) bitmap[8 + lane] = 0;
         __syncwarp();
-        for (u32 k = 0; k < MTF_THREADS; k++) {
+        for (u32 k = w * 32; k < w * 32 + 32; k++) {
             const u32 rc = cnts[k];
             uint8_t r[8];
 #pragma unroll
-            for (u32 j = 0; j < 8; j++) r[j] = (lane * 8 + j < rc) ? slots[(lane * 8 + j) * MTF_THREADS + k] : uint8_t(0);
-            __syncwarp();
-            if (APPLY) {
-                // the table at the start of chunk k replaces the chunk's list in its slot
-#pragma unroll
-                for (u32 j = 0; j < 8; j++) slots[(lane * 8 + j) * MTF_THREADS + k] = T[lane * 8 + j];
-            } else {
-#pragma unroll
-                for (u32 j = 0; j < 8; j++)
-                    if (lane * 8 + j < rc) atomicOr(&bitmap[8 + (r[j] >> 5)], 1u << (r[j] & 31u));
+            for (u32 j = 0; j < 8; j++) {
+                r[j] = (lane * 8 + j < rc) ? slots[(lane * 8 + j) * MTF_THREADS + k] : uint8_t(0);
+                if (lane * 8 + j < rc) atomicOr(&bitmap[8 + (r[j] >> 5)], 1u << (r[j] & 31u));
             }
             __syncwarp();
             mtf_compose(T, r, rc, bitmap, tmp);
         }
+        u32 c = lane < 8 ? u32(__popc(bitmap[8 + lane])) : 0u;
+        c = warp_sum(c);
+        if (lane == 0) warp_rc[w] = c;
+    }
+    __syncthreads();
+    // ---- B2. one warp folds the warps' results in order (from the tile's incoming table when applying) ----
+    if (w == 0) {
+        uint8_t* TT = folds + MTF_WARPS * MTF_FOLD_BYTES;
+        uint8_t* ttmp = TT + 256;
+        u32* tbitmap = reinterpret_cast<u32*>(ttmp + 256);
+#pragma unroll
+        for (u32 j = 0; j < 8; j++) TT[lane * 8 + j] = APPLY ? incoming[u64(blockIdx.x) * 256 + lane * 8 + j] : uint8_t(lane * 8 + j);
+        if (lane < 8) tbitmap[8 + lane] = 0;
+        __syncwarp();
+        for (u32 ww = 0; ww < MTF_WARPS; ww++) {
+            uint8_t* Tw = folds + ww * MTF_FOLD_BYTES;
+            const u32 rc = warp_rc[ww];
+            uint8_t r[8];
+#pragma unroll
+            for (u32 j = 0; j < 8; j++) r[j] = Tw[lane * 8 + j];  // its first rc entries are the warp's recency list
+            if (!APPLY && lane < 8) tbitmap[8 + lane] |= reinterpret_cast<const u32*>(Tw + 512)[8 + lane];
+            __syncwarp();
+            if (APPLY) {
+                // the table at the start of warp ww's chunks replaces the warp's result
+#pragma unroll
+                for (u32 j = 0; j < 8; j++) Tw[lane * 8 + j] = TT[lane * 8 + j];
+                __syncwarp();
+            }
+            mtf_compose(TT, r, rc, tbitmap, ttmp);
+        }
         if (!APPLY) {
 #pragma unroll
-            for (u32 j = 0; j < 8; j++) tile_R[u64(blockIdx.x) * 256 + lane * 8 + j] = T[lane * 8 + j];
-            u32 c = lane < 8 ? u32(__popc(bitmap[8 + lane])) : 0u;
+            for (u32 j = 0; j < 8; j++) tile_R[u64(blockIdx.x) * 256 + lane * 8 + j] = TT[lane * 8 + j];
+            u32 c = lane < 8 ? u32(__popc(tbitmap[8 + lane])) : 0u;
             c = warp_sum(c);
             if (lane == 0) tile_rc[blockIdx.x] = c;
         }
     }
     if (!APPLY) return;
+    __syncthreads();
+    // ---- B3. every warp folds its chunks again, now from its incoming table: the table at the start of chunk k replaces
+    //          the chunk's list in its slot ----
+    for (u32 k = w * 32; k < w * 32 + 32; k++) {
+        const u32 rc = cnts[k];
+        uint8_t r[8];
+#pragma unroll
+        for (u32 j = 0; j < 8; j++) r[j] = (lane * 8 + j < rc) ? slots[(lane * 8 + j) * MTF_THREADS + k] : uint8_t(0);
+        __syncwarp();
+#pragma unroll
+        for (u32 j = 0; j < 8; j++) slots[(lane * 8 + j) * MTF_THREADS + k] = T[lane * 8 + j];
+        __syncwarp();
+        mtf_compose(T, r, rc, bitmap, tmp);
+    }
     __syncthreads();
 
     // ---- C. the reference's loop (MTFCompressor.hpp:17-30) on this thread's chunk with its own table ----
