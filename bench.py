@@ -553,7 +553,7 @@ def main():
                            "encode_kernels_ms_per_step": round(enc_ms, 3),
                            "encode_algorithmic_GBps": (enc_bytes / 1e9 / (enc_ms / 1e3)) if enc_ms else None,
                            "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof_arc.items(), key=lambda kv: -kv[1]["ms"])}}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             sample_body = min(n_body, 1 << CPU_SAMPLE_LOG2)
             sample = text[: sample_body + 1].copy()
             sample[-1] = 0
