@@ -147,12 +147,38 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     u32* digit_start = warp_cnt + RS_WARPS * RS_RADIX;                          // [256]
     u32* gbase = digit_start + RS_RADIX;                                        // [256]
     u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch
+#ifdef RS_VALS_ASYNC
+    u32* svals_in = misc + 40;                                                  // TILE incoming values (tile order)
+#endif
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const u32 tile = blockIdx.x;
     const u64 tile_base = u64(tile) * TILE;
     const u32 count = u32(min(u64(TILE), m - tile_base));
 
+#ifdef RS_VALS_ASYNC
+    // EXPERIMENT (off by default, A/B with tools/sortbench.cu -DRS_VALS_ASYNC): the tile's values start travelling to
+    // shared memory right away with cp.async — no registers held across the ranking and the look-back (prefetching them
+    // into registers measured 20 % slower), and the staging step below finds them on chip instead of paying a second
+    // exposed global-load latency per tile.  16-byte chunks; the partial last tile clamps the source size (zero fill).
+    if (!IOTA) {
+        for (u32 c16 = tid; c16 < u32(TILE / 4); c16 += RS_THREADS) {
+            const u32 e0 = c16 * 4;
+            if (e0 < count) {
+#ifdef TDC_CUSIM
+                for (u32 e = e0; e < min(e0 + 4, count); e++) svals_in[e] = vin[tile_base + e];
+#else
+                const u32 bytes = min(16u, (count - e0) * 4u);
+                const u32 dst = u32(__cvta_generic_to_shared(svals_in + e0));
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(vin + tile_base + e0), "r"(bytes) : "memory");
+#endif
+            }
+        }
+#ifndef TDC_CUSIM
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+    }
+#endif
     // ---- load (warp-striped: coalesced, and index order == (k, lane) order inside a warp) ----
     K key[IPT];
     u32 rank[IPT];
@@ -241,6 +267,9 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
         gbase[tid] = bucket_start[tid] + exclusive - ex;
     }
+#if defined(RS_VALS_ASYNC) && !defined(TDC_CUSIM)
+    if (!IOTA) asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's chunks have landed; the barrier publishes them
+#endif
     __syncthreads();
 
     // ---- stage in shared memory in digit order ----
@@ -250,7 +279,11 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
         const u64 idx = wbase + u32(k) * 32 + lane;
         skeys[p] = key[k];
+#ifdef RS_VALS_ASYNC
+        if (idx < m) svals[p] = IOTA ? u32(idx) : svals_in[u32(idx - tile_base)];
+#else
         if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];  // (prefetching these before the look-back measured 20 % slower)
+#endif
     }
     __syncthreads();
 
@@ -278,7 +311,11 @@ static __global__ void rs_iota_kernel(u32* v, u64 m) {
 template <class K>
 static inline size_t rs_smem_bytes() {
     constexpr int TILE = RS_THREADS * RsCfg<K>::IPT;
-    return sizeof(K) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
+    size_t bytes = sizeof(K) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
+#ifdef RS_VALS_ASYNC
+    bytes += 4 * TILE;
+#endif
+    return bytes;
 }
 template <class K>
 static inline u64 rs_tiles(u64 m) {
