@@ -1,7 +1,7 @@
 """Seeded differential fuzz of the kernels added behind the factoriser (device-side encode_text, bit-packed arrays, mtf /
 rle / literal encoder) in the tests/sim interpreter: random sizes around the tile / chunk / word boundaries, random
 alphabets (incl. bytes >= 0x80 in runs), random thresholds, offsets, coders and widths — against the oracle, and every
-few iterations the oracle against the unmodified reference (oracle/_ref).  CPU only; ~40 s (30 seeded iterations)."""
+few iterations the oracle against the unmodified reference (oracle/_ref).  CPU only; ~40 s (20 seeded iterations)."""
 import os
 import subprocess
 
@@ -39,7 +39,7 @@ def test_fuzz_new_kernels_against_oracle_and_reference(oracle, reference):
     lib = _abi.TdcGpuLib(SIM)
     rng = np.random.default_rng(20261017)
     with _abi.Context(lib) as c:
-        for it in range(30):
+        for it in range(20):
             d = _input(rng, int(rng.choice(SIZES)))
             off = int(rng.choice([0, 1, 127, 128, 5000, 1 << 20]))
             tag = (it, d.size, off)
