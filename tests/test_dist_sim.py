@@ -17,10 +17,11 @@ def simbuilt():
     subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
 
 
-def _run_world(world, case, timeout=900):
-    port = 29700 + (os.getpid() % 1500) + world
+def _run_world(world, case, timeout=900, env=None):
+    port = 29700 + (os.getpid() % 1500) + world + (7 if env else 0)
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "sim_dist.py"), str(r), str(world), str(port), case],
-                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=dict(os.environ, **(env or {})))
+             for r in range(world)]
     outs = []
     for p in procs:
         try:
@@ -51,3 +52,8 @@ def test_two_ranks_gloo_reference_strings(simbuilt):
 
 def test_three_ranks_gloo_reference_strings(simbuilt):
     _run_world(3, "strings")
+
+
+def test_two_ranks_slice_upload_experiment(simbuilt):
+    """TDCGPU_DIST_SLICE_UPLOAD=1 (off by default): every rank uploads its n/P slice and the peers exchange the rest."""
+    _run_world(2, "strings", env={"TDCGPU_DIST_SLICE_UPLOAD": "1"})

@@ -28,6 +28,8 @@
 
 #include "../../include/tdcgpu.h"
 #include "dist_comm.h"
+#include <cstdlib>
+
 #include "dist_kernels.cuh"
 
 namespace tdc {
@@ -860,6 +862,26 @@ int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on
     c.max_lcp = 0;
     c.num_factors = 0;
     c.phases.clear();
+    // EXPERIMENT (TDCGPU_DIST_SLICE_UPLOAD=1, off by default until measured on >= 2 GPUs): every rank uploads only its own
+    // n/P slice over PCIe and receives the other slices from its peers over NVLink, instead of n bytes over PCIe per rank
+    // (the end-to-end figure of the sharded path is bounded by exactly that copy, profiles/r1m_summary.md).
+    const char* slice_env = std::getenv("TDCGPU_DIST_SLICE_UPLOAD");
+    if (!on_device && d.P > 1 && slice_env && *slice_env && *slice_env != '0') {
+        if (d.pos_cnt) TDC_CUDA(cudaMemcpyAsync(c.d_text + d.pos_lo, text + d.pos_lo, d.pos_cnt, cudaMemcpyHostToDevice, c.stream));
+        TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));
+        u64 soff[DIST_MAX_RANKS], scnt[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
+        for (int p = 0; p < d.P; p++) {
+            const u64 lo = std::min<u64>(n, u64(p) * d.block), cnt = std::min<u64>(n - lo, d.block);
+            soff[p] = d.pos_lo;
+            scnt[p] = p == d.rank ? 0 : d.pos_cnt;  // my slice to every peer
+            roff[p] = lo;
+            rcnt[p] = p == d.rank ? 0 : cnt;        // every peer's slice to its place in my copy
+        }
+        TDC_TRY(d.comm->alltoallv(c.d_text, soff, scnt, c.d_text, roff, rcnt, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));
+        return 0;
+    }
     TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
     TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
