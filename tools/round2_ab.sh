@@ -1,8 +1,10 @@
 #!/usr/bin/env bash
 # First GPU call of the next round: A/B of experiments that are compiled out by default.
-#   RS_VALS_ASYNC   radix pass: values prefetched to shared memory with cp.async (radix_sort.cuh)
+#   RS_VALS_ASYNC               radix pass: values prefetched to shared memory with cp.async (radix_sort.cuh)
+#   TDCGPU_DIST_SLICE_UPLOAD=1  sharded path: every rank uploads n/P bytes, the peers exchange the rest (dist_textds.cu)
 # Build here (nvcc cross-compiles):   bash tools/round2_ab.sh build
 # Run on the GPU box:                 gpurun -- 'bash tools/round2_ab.sh run'
+#                                     gpurun --gpus 2 -- 'bash tools/round2_ab.sh run2'   (e2e of the sharded path, both ways)
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
 mkdir -p build/sb
@@ -11,6 +13,17 @@ if [ "${1:-build}" = build ]; then
   $NV -DRS_VALS_ASYNC tools/sortbench.cu -o build/sb/sb_vals_async
   $NV -DRS_VALS_ASYNC -DRS_IPT64_CFG=12 -DRS_MIN_CTAS_CFG=4 tools/sortbench.cu -o build/sb/sb_vals_async_12x4 || true
   ls -la build/sb
+elif [ "$1" = run2 ]; then
+  mkdir -p gpurun_out/ab
+  TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
+  timeout 300 $TR --master-port 29571 bench.py --gpus 2 --mode dist --steps 2 --warmup 1 --verify --no-cpu-baseline > gpurun_out/ab/dist2_full_upload.json 2> gpurun_out/ab/dist2_full_upload.err
+  TDCGPU_DIST_SLICE_UPLOAD=1 timeout 300 $TR --master-port 29572 bench.py --gpus 2 --mode dist --steps 2 --warmup 1 --verify --no-cpu-baseline > gpurun_out/ab/dist2_slice_upload.json 2> gpurun_out/ab/dist2_slice_upload.err
+  python - <<'PY'
+import json
+for f in ("full", "slice"):
+    d = json.loads([l for l in open(f"gpurun_out/ab/dist2_{f}_upload.json") if l.startswith("{")][0])
+    print(f, "resident", round(d["ms_per_step"], 1), "ms  e2e", round(d["e2e"]["ms_per_step"], 1), "ms  verify", d["verify"]["ok"])
+PY
 else
   mkdir -p gpurun_out/ab
   for b in build/sb/sb_*; do for lg in 28 30; do timeout 120 $b $lg 48 | sed "s#^#$(basename $b): #" | tee -a gpurun_out/ab/sortbench.txt; done; done
