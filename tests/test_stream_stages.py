@@ -111,3 +111,63 @@ def test_gpu_stream_stages_large(oracle):
             codes, lens = np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8)
             want, _ = oracle.literal_encode(r, codes, lens)
             assert np.array_equal(c.literal_encode(codes, lens), want), name
+
+
+@pytest.mark.sim
+def test_sim_device_pointer_variants(oracle):
+    """The on_device / to_device flavours of the entry points (device pointers in, device pointers out).  In the interpreter
+    build device memory is host memory, so the same buffers serve as "device" pointers: this checks the staging logic
+    (no copy-in, caller-owned output, tail bytes written through the device path), not the CUDA copies themselves."""
+    import ctypes as C
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    lib = _abi.TdcGpuLib(SIM)
+    L = lib.lib
+    rng = np.random.default_rng(31)
+    d = np.repeat(rng.integers(0, 200, 700, dtype=np.uint8), rng.integers(1, 9, 700))
+    with _abi.Context(lib) as c:
+        h = c._h
+        # mtf: device in, device out
+        out = np.zeros(d.size + 64, np.uint8)
+        lib.check(L.tdcgpu_mtf_encode(h, d.ctypes.data, d.size, out.ctypes.data, 1))
+        assert np.array_equal(out[:d.size], oracle.mtf_encode(d))
+        # rle: a device output buffer must hold the worst case
+        want = oracle.rle_encode(d, 5)
+        small = np.zeros(want.size + 8, np.uint8)
+        m = C.c_uint64()
+        assert L.tdcgpu_rle_encode(h, d.ctypes.data, d.size, 5, small.ctypes.data, small.size, C.byref(m), 1) == -5
+        big = np.zeros(3 * d.size + 64, np.uint8)
+        lib.check(L.tdcgpu_rle_encode(h, d.ctypes.data, d.size, 5, big.ctypes.data, big.size, C.byref(m), 1))
+        assert np.array_equal(big[:m.value], want)
+        # literal encoder: device input, stream fetched to a "device" buffer with and without the tail
+        hist = np.zeros(256, np.uint64)
+        lib.check(L.tdcgpu_literal_encode_begin(h, d.ctypes.data, d.size, 1, hist.ctypes.data))
+        assert np.array_equal(hist, np.bincount(d, minlength=256).astype(np.uint64))
+        codes, lens = np.arange(256, dtype=np.uint64), np.full(256, 7, np.uint8)  # 7-bit words: the stream ends mid-byte
+        nbits = C.c_uint64()
+        lib.check(L.tdcgpu_literal_encode(h, codes.ctypes.data, lens.ctypes.data, 3, 0xA0, C.byref(nbits)))
+        want, wbits = oracle.literal_encode(d, codes & np.uint64(0x7F), lens, 3, 0xA0)
+        assert nbits.value == wbits
+        for fin in (1, 0):
+            buf = np.zeros(want.size + 8, np.uint8)
+            nb = C.c_uint64()
+            lib.check(L.tdcgpu_literal_encode_get(h, buf.ctypes.data, buf.size, fin, C.byref(nb), 1))
+            ref_bytes = want if fin else oracle.literal_encode(d, codes & np.uint64(0x7F), lens, 3, 0xA0, finalize=False)[0]
+            assert np.array_equal(buf[:nb.value], ref_bytes), fin
+        # text index: packed array and encoded lzss stream into "device" buffers
+        t = synth.markov_text(3000, 8)
+        c.set_text(t)
+        c.build(_abi.SA)
+        w = int(t.size).bit_length()
+        host = c.get_packed(_abi.SA, w)
+        dev = np.zeros(host.size, np.uint64)
+        lib.check(L.tdcgpu_textds_get_packed(h, _abi.SA, w, dev.ctypes.data, dev.size, 1))
+        assert np.array_equal(dev, host)
+        c.factorize(3)
+        c.literal_histogram()
+        nbits = c.encode(np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8))
+        host = c.encoded(nbits)
+        dev = np.zeros(host.size + 4, np.uint8)
+        nb = C.c_uint64()
+        lib.check(L.tdcgpu_lzss_encode_get(h, dev.ctypes.data, dev.size, 1, C.byref(nb), 1))
+        assert np.array_equal(dev[:nb.value], host)

@@ -13,6 +13,16 @@ if [ "${1:-build}" = build ]; then
   $NV -DRS_VALS_ASYNC tools/sortbench.cu -o build/sb/sb_vals_async
   $NV -DRS_VALS_ASYNC -DRS_IPT64_CFG=12 -DRS_MIN_CTAS_CFG=4 tools/sortbench.cu -o build/sb/sb_vals_async_12x4 || true
   ls -la build/sb
+  # lpf_tile_kernel configurations as whole-library variants (tools/lpf_variants.py loads build/variants/libtdcgpu_*.so)
+  make -s -C tudocomp_b200/csrc
+  mkdir -p build/variants
+  for cfg in "t32c16 -DLPF_THREADS_CFG=32" "t128c16 -DLPF_THREADS_CFG=128"; do
+    set -- $cfg; name=$1; shift
+    $NV -Xcompiler -fPIC "$@" -c tudocomp_b200/csrc/lzss_factorize.cu -o build/variants/lzss_factorize_$name.o
+    nvcc -shared -o build/variants/libtdcgpu_$name.so build/tdcgpu_api.o build/suffix_array.o build/lcp.o build/variants/lzss_factorize_$name.o \
+      build/lzss_encode.o build/stream_codecs.o build/dist_comm.o build/dist_textds.o -lcudart -ldl
+  done
+  ls -la build/variants/*.so
 elif [ "$1" = run2 ]; then
   mkdir -p gpurun_out/ab
   TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
@@ -27,4 +37,5 @@ PY
 else
   mkdir -p gpurun_out/ab
   for b in build/sb/sb_*; do for lg in 28 30; do timeout 120 $b $lg 48 | sed "s#^#$(basename $b): #" | tee -a gpurun_out/ab/sortbench.txt; done; done
+  timeout 300 python tools/lpf_variants.py 30 | tee gpurun_out/ab/lpf_variants.txt
 fi
