@@ -5,6 +5,7 @@
 # Build here (nvcc cross-compiles):   bash tools/round2_ab.sh build
 # Run on the GPU box:                 gpurun -- 'bash tools/round2_ab.sh run'
 #                                     gpurun --gpus 2 -- 'bash tools/round2_ab.sh run2'   (e2e of the sharded path, both ways)
+#                                     gpurun -- 'bash tools/round2_ab.sh sanitize'        (compute-sanitizer on the new kernels)
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
 mkdir -p build/sb
@@ -23,6 +24,16 @@ if [ "${1:-build}" = build ]; then
       build/lzss_encode.o build/stream_codecs.o build/dist_comm.o build/dist_textds.o -lcudart -ldl
   done
   ls -la build/variants/*.so
+elif [ "$1" = sanitize ]; then
+  # the kernels added late in round 1 (lzss encoder, packed arrays, mtf / rle / literal encoder, warp-local LPF merges) have
+  # not been under compute-sanitizer yet: memcheck + racecheck on small inputs (minutes, not seconds, under the tool)
+  mkdir -p gpurun_out/ab
+  for tool in memcheck racecheck; do
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/ab/sanitize_${tool}_smoke.log 2>&1
+    tail -3 gpurun_out/ab/sanitize_${tool}_smoke.log
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_stream_stages.py -m gpu -k golden -x -q > gpurun_out/ab/sanitize_${tool}_stream.log 2>&1
+    tail -3 gpurun_out/ab/sanitize_${tool}_stream.log
+  done
 elif [ "$1" = run2 ]; then
   mkdir -p gpurun_out/ab
   TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
