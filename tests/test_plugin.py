@@ -11,6 +11,7 @@ from tudocomp_b200 import synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF, GPU, GPU_ONLY = (os.path.join(ROOT, "build", b) for b in ("tdc_ref", "tdc_gpu", "tdc_gpu_only"))
+BLOCK_REF, BLOCK_GPU = (os.path.join(ROOT, "build", b) for b in ("tdc_block_ref", "tdc_block_gpu"))
 
 
 def _need_bins():
@@ -87,6 +88,68 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
     assert r.returncode == 0, r.stderr
     assert _run(REF, "lzss_lcp(coder=huff)", str(tmp_path / "markov.bin"), str(tmp_path / "ref.tdc")).returncode == 0
     assert open(tmp_path / "h.tdc", "rb").read() == open(tmp_path / "ref.tdc", "rb").read()
+
+
+def _block_container(path):
+    """(block_bytes, algo, [archive bytes per block]) of a tdc_block container (tudocomp_b200/plugin/tdc_block.cpp)."""
+    import struct
+    c = open(path, "rb").read()
+    assert c.startswith(b"TDCBLOCK1\n")
+    p = 10
+    blk, nb = struct.unpack_from("<QQ", c, p)
+    p += 16
+    (al,) = struct.unpack_from("<I", c, p)
+    p += 4
+    algo = c[p:p + al].decode()
+    p += al
+    arcs = []
+    for _ in range(nb):
+        (ln,) = struct.unpack_from("<Q", c, p)
+        p += 8
+        arcs.append(c[p:p + ln])
+        p += ln
+    assert p == len(c)
+    return blk, algo, arcs
+
+
+def _need_block_bins():
+    if not all(os.path.exists(p) for p in (REF, BLOCK_REF, BLOCK_GPU)):
+        pytest.skip("tdc_block drivers not built (bash tudocomp_b200/plugin/build_tdc.sh; needs /root/reference)")
+
+
+@pytest.mark.sim
+def test_block_mode_driver_over_the_simulator_library(tmp_path):
+    """Block mode (config 5) end to end on the CPU: tdc_block over the GPU registry (interpreter library in place of
+    libtdcgpu.so) produces the same container as tdc_block over the reference registry, every block equals what the stock
+    reference driver writes with --raw for that slice, forked workers give the same container, and it round-trips."""
+    _need_block_bins()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    simdir = tmp_path / "simlib"
+    simdir.mkdir()
+    os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
+    data = (synth.markov_text(5000, 5)[:-1].tobytes() + bytes(np.random.default_rng(1).integers(0, 256, 1500, dtype=np.uint8))
+            + synth.dna(3000, 6)[:-1].tobytes())
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    algo, blk = "lzss_lcp(coder=huff)", 3000
+    ref_c, gpu_c, ref3_c = (str(tmp_path / n) for n in ("ref.tdcb", "gpu.tdcb", "ref3.tdcb"))
+    assert subprocess.run([BLOCK_REF, "-a", algo, "-b", str(blk), str(src), "-o", ref_c], capture_output=True).returncode == 0
+    r = subprocess.run([BLOCK_GPU, "-a", algo, "-b", str(blk), str(src), "-o", gpu_c], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(ref_c, "rb").read() == open(gpu_c, "rb").read()
+    assert subprocess.run([BLOCK_REF, "-a", algo, "-b", str(blk), "-g", "3", str(src), "-o", ref3_c], capture_output=True).returncode == 0
+    assert open(ref_c, "rb").read() == open(ref3_c, "rb").read()
+    b, a, arcs = _block_container(gpu_c)
+    assert (b, a, len(arcs)) == (blk, algo, -(-len(data) // blk))
+    for i, arc in enumerate(arcs):
+        sl = tmp_path / "slice.bin"
+        sl.write_bytes(data[i * blk:(i + 1) * blk])
+        assert _run(REF, algo, str(sl), str(tmp_path / "slice.tdc"), ["--raw"]).returncode == 0
+        assert open(tmp_path / "slice.tdc", "rb").read() == arc, i
+    back = str(tmp_path / "back.bin")
+    assert subprocess.run([BLOCK_REF, "-d", gpu_c, "-o", back], capture_output=True).returncode == 0
+    assert open(back, "rb").read() == data
 
 
 def _inputs(tmp_path):
@@ -188,3 +251,21 @@ def test_host_and_device_encode_agree(tmp_path):
                            env=dict(os.environ, TDCGPU_HOST_ENCODE="1"))
         assert r.returncode == 0, r.stderr
         assert open(a, "rb").read() == open(b, "rb").read(), coder
+
+
+@pytest.mark.gpu
+def test_block_mode_driver_on_the_gpu(tmp_path):
+    """tdc_block over the GPU registry: same container as over the reference registry, round trip through the reference."""
+    _need_block_bins()
+    data = synth.markov_text(3 << 20, 11)[:-1].tobytes()
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    algo = "lzss_lcp(coder=huff)"
+    ref_c, gpu_c = str(tmp_path / "ref.tdcb"), str(tmp_path / "gpu.tdcb")
+    assert subprocess.run([BLOCK_REF, "-a", algo, "-b", str(1 << 20), str(src), "-o", ref_c], capture_output=True).returncode == 0
+    r = subprocess.run([BLOCK_GPU, "-a", algo, "-b", str(1 << 20), str(src), "-o", gpu_c], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert open(ref_c, "rb").read() == open(gpu_c, "rb").read()
+    back = str(tmp_path / "back.bin")
+    assert subprocess.run([BLOCK_REF, "-d", gpu_c, "-o", back], capture_output=True).returncode == 0
+    assert open(back, "rb").read() == data

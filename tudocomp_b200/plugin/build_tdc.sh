@@ -3,6 +3,7 @@
 #   build/tdc_ref        unmodified reference subset (CPU)            — byte-identity checker
 #   build/tdc_gpu        reference registry + GpuTextDS ("mixed")     — -a "lzss_lcp(huff, gpu)"
 #   build/tdc_gpu_only   GPU text index as the default ("only")       — same -a strings as the reference
+#   build/tdc_block_ref / build/tdc_block_gpu   block mode driver (tdc_block.cpp) over the reference / GPU-only registry
 # The reference sources are compiled where they lie under $REF (nothing is copied); the two missing third-party headers
 # come from oracle/ref_build/shim.  Needs $REF, so it only runs in the build container; the binaries travel in build/.
 set -euo pipefail
@@ -34,4 +35,16 @@ for mode in none mixed only; do
     g++ -o "$ROOT/build/$bin" $objs -ldl
   fi
   echo "built build/$bin"
+  # block mode driver (tdc_block.cpp): the same registry objects with its own main instead of tudocomp_driver.cpp
+  if [ "$mode" != mixed ]; then
+    [ "$mode" = none ] && bbin=tdc_block_ref || bbin=tdc_block_gpu
+    g++ $CXXFLAGS $extra -I$gen -c "$ROOT/tudocomp_b200/plugin/tdc_block.cpp" -o "$gen/tdc_block.o"
+    bobjs=$(echo $objs | tr ' ' '\n' | grep -v tudocomp_driver.o | tr '\n' ' ')
+    if [ "$mode" = only ]; then
+      g++ -o "$ROOT/build/$bbin" $bobjs "$gen/tdc_block.o" -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+    else
+      g++ -o "$ROOT/build/$bbin" $bobjs "$gen/tdc_block.o" -ldl
+    fi
+    echo "built build/$bbin"
+  fi
 done
