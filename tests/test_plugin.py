@@ -138,6 +138,10 @@ def test_block_mode_driver_over_the_simulator_library(tmp_path):
     r = subprocess.run([BLOCK_GPU, "-a", algo, "-b", str(blk), str(src), "-o", gpu_c], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert open(ref_c, "rb").read() == open(gpu_c, "rb").read()
+    # -c: one device context kept alive across the blocks of a worker (TDCGPU_CTX_CACHE=1): same bytes
+    r = subprocess.run([BLOCK_GPU, "-a", algo, "-b", str(blk), "-c", str(src), "-o", gpu_c + ".c"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert open(ref_c, "rb").read() == open(gpu_c + ".c", "rb").read()
     assert subprocess.run([BLOCK_REF, "-a", algo, "-b", str(blk), "-g", "3", str(src), "-o", ref3_c], capture_output=True).returncode == 0
     assert open(ref_c, "rb").read() == open(ref3_c, "rb").read()
     b, a, arcs = _block_container(gpu_c)

@@ -28,8 +28,8 @@ namespace tdc {
 namespace gpu_detail {
 struct StreamCtx {  // one context (stream + scratch) for the duration of a compress() call
     tdcgpu_ctx* ctx = nullptr;
-    StreamCtx() { check(tdcgpu_create(device_from_env(), &ctx), "create"); }
-    ~StreamCtx() { tdcgpu_destroy(ctx); }
+    StreamCtx() : ctx(acquire_ctx()) {}
+    ~StreamCtx() { release_ctx(ctx); }
     StreamCtx(const StreamCtx&) = delete;
     StreamCtx& operator=(const StreamCtx&) = delete;
 };

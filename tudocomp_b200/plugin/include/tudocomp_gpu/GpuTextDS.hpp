@@ -54,6 +54,34 @@ inline int device_from_env() {
     const char* e = std::getenv("TDCGPU_DEVICE");
     return e ? std::atoi(e) : 0;
 }
+// Opt-in (TDCGPU_CTX_CACHE=1, off by default): keep one device context alive between compress() calls of a process instead
+// of creating and destroying one per text — the arrays and the scratch arena (~57 n bytes) are then allocated once for
+// the largest text seen.  Meant for `tdc_block -c` (many blocks per worker) and for chains of GPU stages; tdc itself is
+// single-threaded, so one cached context is enough.  The cached context is deliberately not destroyed at
+// process exit (static destructors may run after the CUDA runtime has shut down).
+inline bool ctx_cache_enabled() {
+    const char* e = std::getenv("TDCGPU_CTX_CACHE");
+    return e && *e && *e != '0';
+}
+inline tdcgpu_ctx*& cached_ctx() {
+    static tdcgpu_ctx* c = nullptr;
+    return c;
+}
+inline tdcgpu_ctx* acquire_ctx() {
+    if (ctx_cache_enabled() && cached_ctx()) {
+        tdcgpu_ctx* c = cached_ctx();
+        cached_ctx() = nullptr;
+        return c;
+    }
+    tdcgpu_ctx* raw = nullptr;
+    check(tdcgpu_create(device_from_env(), &raw), "create");
+    return raw;
+}
+inline void release_ctx(tdcgpu_ctx* c) {
+    if (!c) return;
+    if (ctx_cache_enabled() && !cached_ctx()) cached_ctx() = c;
+    else tdcgpu_destroy(c);
+}
 // log the device-side phase times under the current StatPhase (tudocomp_stat/StatPhase.hpp:217-220)
 inline void log_phases(tdcgpu_ctx* ctx) {
     for (int i = 0; i < tdcgpu_phase_count(ctx); i++) {
@@ -176,7 +204,7 @@ public:
 
 private:
     struct CtxDeleter {
-        void operator()(tdcgpu_ctx* c) const { tdcgpu_destroy(c); }
+        void operator()(tdcgpu_ctx* c) const { gpu_detail::release_ctx(c); }
     };
     View m_text;
     std::unique_ptr<tdcgpu_ctx, CtxDeleter> m_ctx;
@@ -219,9 +247,7 @@ public:
         }
         auto& cm_str = this->env().option("compress").as_string();
         m_cm = cm_str == "delayed" ? CompressMode::delayed : (cm_str == "compressed" ? CompressMode::compressed : CompressMode::plain);
-        tdcgpu_ctx* raw = nullptr;
-        gpu_detail::check(tdcgpu_create(gpu_detail::device_from_env(), &raw), "create");
-        m_ctx.reset(raw);
+        m_ctx.reset(gpu_detail::acquire_ctx());
         gpu_detail::check(tdcgpu_set_text(m_ctx.get(), reinterpret_cast<const uint8_t*>(m_text.data()), m_text.size(), 0), "set_text");
     }
 

@@ -6,7 +6,8 @@
 // With the GPU registry (`tdc_block_gpu`) every block runs on a GPU; blocks are dealt round-robin to `-g N` worker
 // processes, worker k using device k (TDCGPU_DEVICE), with no communication between them.
 //
-//   tdc_block -a "lzss_lcp(coder=huff)" -b 268435456 -g 8 input -o output.tdcb
+//   tdc_block -a "lzss_lcp(coder=huff)" -b 268435456 -g 8 [-c] input -o output.tdcb
+//        -c  keep one device context per worker alive across its blocks (TDCGPU_CTX_CACHE=1, GpuTextDS.hpp)
 //   tdc_block -d output.tdcb -o roundtrip
 //
 // Container: "TDCBLOCK1\n", u64 block_bytes, u64 nblocks, u32 algo_len, algo string, then per block u64 archive_len and
@@ -91,7 +92,7 @@ std::vector<uint8_t> decompress_block(const std::string& algo, const uint8_t* ar
 std::string block_tmp(const std::string& ofile, uint64_t b) { return ofile + ".blk." + std::to_string(b); }
 
 int usage() {
-    std::cerr << "usage: tdc_block -a ALGO [-b BLOCK_BYTES] [-g WORKERS] INPUT -o OUTPUT\n"
+    std::cerr << "usage: tdc_block -a ALGO [-b BLOCK_BYTES] [-g WORKERS] [-c] INPUT -o OUTPUT\n"
                  "       tdc_block -d CONTAINER -o OUTPUT\n";
     return 2;
 }
@@ -110,6 +111,7 @@ int main(int argc, char** argv) {
         else if (a == "-g" && i + 1 < argc) workers = std::atoi(argv[++i]);
         else if (a == "-o" && i + 1 < argc) ofile = argv[++i];
         else if (a == "-d") decompress = true;
+        else if (a == "-c") setenv("TDCGPU_CTX_CACHE", "1", 1);
         else if (!a.empty() && a[0] != '-') input = a;
         else return usage();
     }
