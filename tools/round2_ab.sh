@@ -6,6 +6,7 @@
 # Run on the GPU box:                 gpurun -- 'bash tools/round2_ab.sh run'
 #                                     gpurun --gpus 2 -- 'bash tools/round2_ab.sh run2'   (e2e of the sharded path, both ways)
 #                                     gpurun -- 'bash tools/round2_ab.sh sanitize'        (compute-sanitizer on the new kernels)
+#                                     gpurun --gpus 8 -- 'bash tools/round2_ab.sh block 8 8'  (config 5 via tdc_block, 8 GiB)
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
 mkdir -p build/sb
@@ -34,6 +35,22 @@ elif [ "$1" = sanitize ]; then
     timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_stream_stages.py -m gpu -k golden -x -q > gpurun_out/ab/sanitize_${tool}_stream.log 2>&1
     tail -3 gpurun_out/ab/sanitize_${tool}_stream.log
   done
+elif [ "$1" = block ]; then
+  # config 5 through the real plugin: tdc_block over the GPU registry, 256 MiB blocks, one worker per GPU, with and without the
+  # context cache.  gpurun --gpus N -- 'bash tools/round2_ab.sh block N GIB'
+  mkdir -p gpurun_out/ab
+  N=${2:-1}; GIB=${3:-2}
+  python - <<PY
+import sys; sys.path.insert(0, ".")
+from tudocomp_b200 import synth
+with open("/dev/shm/block_in.txt", "wb") as f:
+    for i in range($GIB):
+        f.write(synth.markov_text(1 << 30, 500 + i)[:-1].tobytes())
+PY
+  for flag in "" "-c"; do
+    ./build/tdc_block_gpu -a "lzss_lcp(coder=huff)" -b 268435456 -g $N $flag /dev/shm/block_in.txt -o /dev/shm/block_out.tdcb 2>&1 | sed "s#^#[-g $N $flag] #" | tee -a gpurun_out/ab/block_mode.txt
+  done
+  rm -f /dev/shm/block_in.txt /dev/shm/block_out.tdcb
 elif [ "$1" = run2 ]; then
   mkdir -p gpurun_out/ab
   TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --nproc-per-node 2"
