@@ -82,6 +82,14 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
             r = subprocess.run([GPU, "-a", f"lcpcomp({opts},textds=gpu)", src, "-o", b, "--force", "--raw"], capture_output=True, text=True, env=env)
             assert r.returncode == 0, (name, opts, r.stderr)
             assert open(a, "rb").read() == open(b, "rb").read(), (name, opts)
+    # the `compress` option of the GPU text index (plain: 32-bit arrays; delayed / compressed: bit-packed on the device)
+    src = str(tmp_path / "markov.bin")
+    assert _run(REF, "lcpcomp(coder=huff)", src, str(tmp_path / "ref.tdc"), ["--raw"]).returncode == 0
+    for cm in ("plain", "compressed"):
+        r = subprocess.run([GPU, "-a", f'lcpcomp(coder=huff,textds=gpu(compress="{cm}"))', src, "-o", str(tmp_path / "sim.tdc"), "--force", "--raw"],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, (cm, r.stderr)
+        assert open(tmp_path / "ref.tdc", "rb").read() == open(tmp_path / "sim.tdc", "rb").read(), cm
     # the host-side encode_text (A/B switch) gives the same bytes
     r = subprocess.run([GPU_ONLY, "-a", "lzss_lcp(coder=huff)", str(tmp_path / "markov.bin"), "-o", str(tmp_path / "h.tdc"), "--force"],
                        capture_output=True, text=True, env=dict(env, TDCGPU_HOST_ENCODE="1"))
