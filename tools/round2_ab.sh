@@ -7,6 +7,7 @@
 #                                     gpurun --gpus 2 -- 'bash tools/round2_ab.sh run2'   (e2e of the sharded path, both ways)
 #                                     gpurun -- 'bash tools/round2_ab.sh sanitize'        (compute-sanitizer on the new kernels)
 #                                     gpurun --gpus 8 -- 'bash tools/round2_ab.sh block 8 8'  (config 5 via tdc_block, 8 GiB)
+#                                     gpurun -- 'bash tools/round2_ab.sh ncu'             (ncu --set full of the sort pass)
 set -e
 NV="nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo"
 mkdir -p build/sb
@@ -34,6 +35,15 @@ elif [ "$1" = sanitize ]; then
     tail -3 gpurun_out/ab/sanitize_${tool}_smoke.log
     timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -m pytest tests/test_stream_stages.py -m gpu -k golden -x -q > gpurun_out/ab/sanitize_${tool}_stream.log 2>&1
     tail -3 gpurun_out/ab/sanitize_${tool}_stream.log
+  done
+elif [ "$1" = ncu ]; then
+  # fresh `ncu --set full` of the sort pass in its current configuration (profiles/traffic.json still holds the 256 x 12
+  # capture).  The micro-benchmark only launches full-size passes, so "-s 3 -c 1" is the 4th pass of the first sort — inside
+  # bench.py the first rs_onesweep launches belong to the 2^16-element sample sort (that is what call 13 captured).
+  mkdir -p gpurun_out/ab
+  for b in sb_base sb_vals_async; do
+    timeout 300 ncu --set full --clock-control none --import-source on -k regex:rs_onesweep_kernel -s 3 -c 1 -o gpurun_out/ab/ncu_$b -f build/sb/$b 30 48 > gpurun_out/ab/ncu_$b.log 2>&1
+    tail -2 gpurun_out/ab/ncu_$b.log
   done
 elif [ "$1" = block ]; then
   # config 5 through the real plugin: tdc_block over the GPU registry, 256 MiB blocks, one worker per GPU, with and without the
