@@ -51,9 +51,15 @@ int tdcgpu_device_count(void);
 int tdcgpu_create(int device, tdcgpu_ctx** out);
 void tdcgpu_destroy(tdcgpu_ctx* ctx);
 
-/* Make `text` (n bytes incl. the trailing 0) the context's text.  on_device != 0: `text` is a device pointer on the
- * context's device (device-to-device copy); otherwise a host pointer (staged through pinned memory).
- * Replaces the View handed to TextDS::TextDS (ds/TextDS.hpp:130-147). */
+/* Make `text` (n bytes incl. the trailing 0) the context's text.  Replaces the View handed to TextDS::TextDS
+ * (ds/TextDS.hpp:130-147).
+ * on_device == 0: `text` is a host pointer.  Pinned memory (cudaHostAlloc / cudaHostRegister) is copied directly; pageable
+ * memory — what the driver's View is, io/RestrictedBuffer.hpp:108-181 — is staged chunk by chunk through the context's
+ * pinned buffers by a few copy threads, so the transfer runs at PCIe speed.  The call returns when the copy is complete:
+ * the caller may reuse its buffer.  A last byte != 0 is rejected here with TDCGPU_ERR_SENTINEL.
+ * on_device != 0: `text` is a device pointer on the context's device (device-to-device copy on the context's stream).
+ * The data must be complete before the call (the context's stream is not ordered after the caller's streams), and the
+ * call returns after the copy has finished, so the source may be overwritten afterwards. */
 int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_device);
 
 /* Build the requested structures on the device (they stay resident).  Replaces TextDS::require
@@ -177,6 +183,29 @@ void tdcgpu_profile_reset(void);
 int tdcgpu_profile_count(void);
 int tdcgpu_profile_entry(int i, const char** name, uint64_t* launches, double* ms, double* bytes);
 
+/* ---- device-side checkers (no reference counterpart in the product path; they assert what the reference's own tests
+ * assert, test/ds_tests.cpp:71-112, and re-run the reference's decision rule, compressors/LZSSLCPCompressor.hpp:60-115) ----
+ * Used by `bench.py --verify`, the GPU tests and the sharded path's verification; build/factorize never call them.
+ * All pointers are DEVICE pointers on the context's device; the text must be readable 16 bytes past n (the contexts'
+ * own text buffers are).  Arrays are the FULL arrays; a rank of a sharded run checks its own slot / position range.
+ *
+ * check_index: slots [slot_lo, slot_lo + slot_cnt).  out[0] = slots with SA[i] out of range or ISA[SA[i]] != i;
+ * out[1] = slots violating the Burkhardt-Kaerkkaeinen order criterion (or SA[0] != n-1); out[2] = slots whose LCP differs
+ * from the directly compared common prefix (d_lcp may be NULL: not checked); out[3] = 0. */
+int tdcgpu_check_index(tdcgpu_ctx* ctx, const uint8_t* d_text, uint64_t n, const uint32_t* d_sa, const uint32_t* d_isa,
+                       const uint32_t* d_lcp, uint64_t slot_lo, uint64_t slot_cnt, uint64_t out[4]);
+/* check_factors: the z factors (position order) are exactly the lzss_lcp(threshold) parse of the positions
+ * [pos_lo, pos_lo + pos_cnt) they cover.  out[0] = malformed records (len < threshold, src >= pos, past the sentinel);
+ * out[1] = order / overlap violations; out[2] = factor starts where the reference's PSV/NSV scan decides another
+ * (src, len); out[3] = positions outside every factor where that scan finds a factor; out[4] = positions whose scan
+ * exceeded 2^22 steps (not decided). */
+int tdcgpu_check_factors(tdcgpu_ctx* ctx, const uint8_t* d_text, uint64_t n, const uint32_t* d_sa, const uint32_t* d_isa,
+                         const uint32_t* d_lcp, const tdcgpu_factor* d_factors, uint64_t z, uint32_t threshold,
+                         uint64_t pos_lo, uint64_t pos_cnt, uint64_t out[5]);
+/* device pointers of the context's resident text (padded) and factor list (NULL before factorize) */
+const uint8_t* tdcgpu_text_device_ptr(tdcgpu_ctx* ctx);
+const tdcgpu_factor* tdcgpu_factors_device_ptr(tdcgpu_ctx* ctx);
+
 /* ---- one text sharded over several GPUs (no reference counterpart: tudocomp is single-threaded) -------------------
  * One rank = one process = one GPU; ranks exchange data with NCCL (all-to-all of rank buckets, see
  * tudocomp_b200/csrc/dist_textds.cu).  Every rank passes the SAME full text; results come back as shards:
@@ -200,6 +229,9 @@ int tdcgpu_dist_max_lcp(tdcgpu_dist* h, uint32_t* max_lcp);
 int tdcgpu_dist_lzss_lcp_factorize(tdcgpu_dist* h, uint32_t threshold, uint64_t* local_count, uint64_t* total_count,
                                    uint32_t* min_len, uint32_t* max_len);
 int tdcgpu_dist_get_factors(tdcgpu_dist* h, tdcgpu_factor* dst, uint64_t cap, int to_device);
+/* device pointers of the rank's resident (replicated, padded) text and of its factor shard */
+const uint8_t* tdcgpu_dist_text_device_ptr(tdcgpu_dist* h);
+const tdcgpu_factor* tdcgpu_dist_factors_device_ptr(tdcgpu_dist* h);
 int tdcgpu_dist_sync(tdcgpu_dist* h);
 int tdcgpu_dist_event_record(tdcgpu_dist* h, int slot);
 int tdcgpu_dist_event_elapsed_ms(tdcgpu_dist* h, int slot_a, int slot_b, float* ms);

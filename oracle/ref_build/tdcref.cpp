@@ -166,6 +166,22 @@ int tdcref_textds(const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, 
     });
 }
 
+// SA, ISA, LCP and the BWT from ONE TextDS (tests/golden/make_size_hashes.py: at 2^30 B every extra SA costs ~15 min).
+int tdcref_index_bwt(const uint8_t* text, uint64_t n, uint32_t* sa, uint32_t* isa, uint32_t* lcp, uint8_t* bwt_out,
+                     uint32_t* max_lcp) {
+    return guarded([&] {
+        View v(text, n);
+        auto t = create_algo<TextDS<>>("compress=\"plain\"", v, ds::SA | ds::ISA | ds::LCP);
+        auto& s = t.require_sa();
+        for (uint64_t i = 0; i < n; i++) { sa[i] = s[i]; bwt_out[i] = bwt::bwt(t, s, i); }
+        auto& a = t.require_isa();
+        for (uint64_t i = 0; i < n; i++) isa[i] = a[i];
+        auto& l = t.require_lcp();
+        for (uint64_t i = 0; i < n; i++) lcp[i] = l[i];
+        if (max_lcp) *max_lcp = l.max_lcp();
+    });
+}
+
 // BWT through bwt::bwt over the reference SA.
 int tdcref_bwt(const uint8_t* text, uint64_t n, uint8_t* out) {
     return guarded([&] {

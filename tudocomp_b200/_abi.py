@@ -21,6 +21,7 @@ EXPORTS = [
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
     "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
     "tdcgpu_mtf_encode", "tdcgpu_rle_encode", "tdcgpu_literal_encode_begin", "tdcgpu_literal_encode", "tdcgpu_literal_encode_get",
+    "tdcgpu_check_index", "tdcgpu_check_factors", "tdcgpu_text_device_ptr", "tdcgpu_factors_device_ptr",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -62,6 +63,13 @@ class TdcGpuLib:
         L.tdcgpu_lzss_encode_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         L.tdcgpu_textds_build_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5 + [C.POINTER(C.c_uint32)]
         L.tdcgpu_bwt_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.tdcgpu_check_index.argtypes = [C.c_void_p] + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.tdcgpu_check_factors.argtypes = [C.c_void_p] + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                         C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
+        L.tdcgpu_text_device_ptr.argtypes = [C.c_void_p]
+        L.tdcgpu_text_device_ptr.restype = C.c_void_p
+        L.tdcgpu_factors_device_ptr.argtypes = [C.c_void_p]
+        L.tdcgpu_factors_device_ptr.restype = C.c_void_p
         L.tdcgpu_phase_count.argtypes = [C.c_void_p]
         L.tdcgpu_phase_name.argtypes = [C.c_void_p, C.c_int]
         L.tdcgpu_phase_name.restype = C.c_char_p
@@ -244,6 +252,31 @@ class Context:
         nb = C.c_uint64()
         self.lib.check(self.lib.lib.tdcgpu_literal_encode_get(self._h, _host_ptr(out), out.size, 1 if finalize else 0, C.byref(nb), 0))
         return out[:int(nb.value)].copy()
+
+    # -- device-side checkers (tdcgpu_check_*; not part of the product path) ----------------------------------------
+    def check_index_ptrs(self, d_text: int, n: int, d_sa: int, d_isa: int, d_lcp: int, slot_lo: int, slot_cnt: int) -> dict:
+        out = (C.c_uint64 * 4)()
+        self.lib.check(self.lib.lib.tdcgpu_check_index(self._h, C.c_void_p(d_text), n, C.c_void_p(d_sa), C.c_void_p(d_isa),
+                                                       C.c_void_p(d_lcp) if d_lcp else None, slot_lo, slot_cnt, out))
+        return dict(zip(("isa_of_sa", "suffix_order", "lcp"), (int(x) for x in out[:3])))
+
+    def check_factors_ptrs(self, d_text: int, n: int, d_sa: int, d_isa: int, d_lcp: int, d_factors: int, z: int, threshold: int,
+                           pos_lo: int, pos_cnt: int) -> dict:
+        out = (C.c_uint64 * 5)()
+        self.lib.check(self.lib.lib.tdcgpu_check_factors(self._h, C.c_void_p(d_text), n, C.c_void_p(d_sa), C.c_void_p(d_isa), C.c_void_p(d_lcp),
+                                                         C.c_void_p(d_factors) if d_factors else None, z, threshold, pos_lo, pos_cnt, out))
+        return dict(zip(("malformed", "order", "factor_rule", "missed_factor", "undecided"), (int(x) for x in out)))
+
+    def check(self, threshold: int = 0, z: int = 0) -> dict:
+        """Full device-side check of the context's own SA / ISA / LCP (and, with threshold > 0, of its factor list)."""
+        L = self.lib.lib
+        t = L.tdcgpu_text_device_ptr(self._h)
+        sa, isa, lcp = (self.device_ptr(w) for w in (SA, ISA, LCP))
+        res = self.check_index_ptrs(t, self.n, sa, isa, lcp, 0, self.n)
+        if threshold:
+            res.update(self.check_factors_ptrs(t, self.n, sa, isa, lcp, L.tdcgpu_factors_device_ptr(self._h) or 0, z, threshold, 0, self.n))
+        res["ok"] = all(v == 0 for v in res.values())
+        return res
 
     # -- stats -----------------------------------------------------------------------------------------------------
     def phases(self):

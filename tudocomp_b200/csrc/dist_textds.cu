@@ -306,10 +306,13 @@ static int dist_build_sa(DistCtx& d) {
         TDC_KCHECK();
     }
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 16, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    c.h_scalars[16 + 256] = 0xff;
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 16 + 256, c.d_text + (n - 1), 1, cudaMemcpyDeviceToHost, st));  // the last text byte
     TDC_CUDA(cudaStreamSynchronize(st));
     const u32* hist = c.h_scalars + 16;
-    if (hist[0] != 1) {
-        set_error("text must contain exactly one 0 byte, at its end (found %u)", hist[0]);
+    if (hist[0] != 1 || (c.h_scalars[16 + 256] & 0xffu) != 0) {  // same contract as the single-GPU builder (TextDS.hpp:132-138)
+        set_error("text must contain exactly one 0 byte, at its end (found %u zero bytes, last byte 0x%02x)", hist[0],
+                  c.h_scalars[16 + 256] & 0xffu);
         return TDCGPU_ERR_SENTINEL;
     }
     PackParams pp;
@@ -842,6 +845,7 @@ void tdcgpu_dist_destroy(tdcgpu_dist* h) {
     if (c.h_scalars) cudaFreeHost(c.h_scalars);
     if (d.d_counts) cudaFree(d.d_counts);
     if (d.h_counts) cudaFreeHost(d.h_counts);
+    host_copier_free(c.copier);
     for (auto& e : c.user_events)
         if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c.stream);
@@ -852,6 +856,10 @@ int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on
     DIST_GUARD(h);
     if (!text || n == 0) { set_error("empty text (the path always sees at least the sentinel)"); return TDCGPU_ERR_ARG; }
     if (n >= (uint64_t(1) << 32) - 1) { set_error("n = %llu: indices are 32-bit", (unsigned long long)n); return TDCGPU_ERR_ARG; }
+    if (!on_device && text[n - 1] != 0) {
+        set_error("Input has no sentinel! (the last text byte must be 0, ds/TextDS.hpp:132-138)");
+        return TDCGPU_ERR_SENTINEL;
+    }
     TDC_TRY(dist_ensure_capacity(d, n));
     d.n = n;
     c.n = n;
@@ -867,8 +875,8 @@ int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on
     // (the end-to-end figure of the sharded path is bounded by exactly that copy, profiles/r1m_summary.md).
     const char* slice_env = std::getenv("TDCGPU_DIST_SLICE_UPLOAD");
     if (!on_device && d.P > 1 && slice_env && *slice_env && *slice_env != '0') {
-        if (d.pos_cnt) TDC_CUDA(cudaMemcpyAsync(c.d_text + d.pos_lo, text + d.pos_lo, d.pos_cnt, cudaMemcpyHostToDevice, c.stream));
         TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
+        if (d.pos_cnt) TDC_TRY(host_copy(c, c.d_text + d.pos_lo, text + d.pos_lo, d.pos_cnt, true));
         TDC_CUDA(cudaStreamSynchronize(c.stream));
         u64 soff[DIST_MAX_RANKS], scnt[DIST_MAX_RANKS], roff[DIST_MAX_RANKS], rcnt[DIST_MAX_RANKS];
         for (int p = 0; p < d.P; p++) {
@@ -882,9 +890,13 @@ int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on
         TDC_CUDA(cudaStreamSynchronize(c.stream));
         return 0;
     }
-    TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
     TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
-    TDC_CUDA(cudaStreamSynchronize(c.stream));
+    if (on_device) {
+        TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, cudaMemcpyDeviceToDevice, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+        TDC_TRY(host_copy(c, c.d_text, text, n, true));
+    }
     return 0;
 }
 
@@ -958,6 +970,11 @@ int tdcgpu_dist_get_factors(tdcgpu_dist* h, tdcgpu_factor* dst, uint64_t cap, in
     TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
+}
+
+const uint8_t* tdcgpu_dist_text_device_ptr(tdcgpu_dist* h) { return h ? h->d.c.d_text : nullptr; }
+const tdcgpu_factor* tdcgpu_dist_factors_device_ptr(tdcgpu_dist* h) {
+    return h ? reinterpret_cast<const tdcgpu_factor*>(h->d.c.d_factors) : nullptr;
 }
 
 int tdcgpu_dist_sync(tdcgpu_dist* h) {

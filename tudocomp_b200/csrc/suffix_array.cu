@@ -106,12 +106,15 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
         TDC_KCHECK();
     }
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 16, d_hist, 256 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    c.h_scalars[16 + 256] = 0xff;
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 16 + 256, c.d_text + (n - 1), 1, cudaMemcpyDeviceToHost, st));  // the last text byte
     TDC_CUDA(cudaStreamSynchronize(st));
     const u32* hist = c.h_scalars + 16;
-    if (hist[0] != 1) {
-        // mirrors TextDS's sentinel requirement (/root/reference/include/tudocomp/ds/TextDS.hpp:132-138) and the
-        // escape-0 input restriction of SADivSufSort (ds/SADivSufSort.hpp:21-26)
-        set_error("text must contain exactly one 0 byte, at its end (found %u)", hist[0]);
+    if (hist[0] != 1 || (c.h_scalars[16 + 256] & 0xffu) != 0) {
+        // mirrors TextDS's sentinel requirement (/root/reference/include/tudocomp/ds/TextDS.hpp:132-138: the LAST byte is
+        // the 0) and the escape-0 input restriction of SADivSufSort (ds/SADivSufSort.hpp:21-26: no other 0)
+        set_error("text must contain exactly one 0 byte, at its end (found %u zero bytes, last byte 0x%02x)", hist[0],
+                  c.h_scalars[16 + 256] & 0xffu);
         return -3;
     }
     PackParams pp;

@@ -54,6 +54,17 @@ struct EncodeState {
     u64 nbits = 0;
 };
 
+// host_copy.cu: pinned double buffers + copy streams of the threads that stage pageable caller memory
+static const int HC_THREADS = 4;
+static const size_t HC_CHUNK = size_t(8) << 20;
+static const size_t HC_MIN_STAGED = size_t(4) << 20;  // smaller copies: one plain cudaMemcpy
+struct HostCopier {
+    bool ready = false;
+    uint8_t* buf[HC_THREADS][2] = {};
+    cudaEvent_t ev[HC_THREADS][2] = {};
+    cudaStream_t stream[HC_THREADS] = {};
+};
+
 struct Ctx {
     int device = 0;
     int sm_count = 148;
@@ -83,14 +94,14 @@ struct Ctx {
     u32* d_scalars = nullptr;  // small device scratch (256 u32)
     u32* h_scalars = nullptr;  // pinned mirror
 
-    // pinned staging for host<->device copies of caller buffers
-    uint8_t* h_stage = nullptr;
-    size_t h_stage_cap = 0;
+    // pinned staging for host<->device copies of pageable caller buffers
+    HostCopier copier;
 
     // byte-stream stages (stream_codecs.cu): one grow-only device buffer, independent of the text-index arrays
     Arena stream_arena;
     struct LiteralStage {  // tdcgpu_literal_encode_begin .. _get: the staged input and the encoded stream
         u64 gen = 0, n = 0, nbits = 0;
+        size_t arena_mark = 0;  // stream_arena.off after staging: every (re-)encode carves its scratch from here
         const uint8_t* d_in = nullptr;
         uint8_t* d_out = nullptr;
         u64 out_cap = 0;
@@ -112,6 +123,9 @@ struct Ctx {
     u32 lcp_route = 0;          // 1 = direct comparison in SA order, 2 = Phi/PLCP route
 };
 
+// host_copy.cu
+int host_copy(Ctx& c, void* dst, const void* src, size_t bytes, bool h2d);  // blocking; pageable memory is staged
+void host_copier_free(HostCopier& hc);
 // suffix_array.cu
 int build_suffix_array(Ctx& c, bool want_lcp);  // fills d_sa and d_isa; want_lcp: seed d_lcp from the initial keys
 // lcp.cu
@@ -145,3 +159,8 @@ struct PhaseTimer {  // CUDA-event timing of one phase on the context's stream
 };
 
 }  // namespace tdc
+
+// the opaque handle of include/tdcgpu.h is a Ctx
+struct tdcgpu_ctx {
+    tdc::Ctx c;
+};

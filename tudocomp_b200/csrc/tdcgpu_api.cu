@@ -223,10 +223,6 @@ static void* array_ptr(Ctx& c, u32 which, size_t* elem) {
 
 using namespace tdc;
 
-struct tdcgpu_ctx {
-    Ctx c;
-};
-
 #define API_GUARD(ctx)                                         \
     if (!(ctx)) { set_error("null context"); return TDCGPU_ERR_ARG; } \
     Ctx& c = (ctx)->c;                                         \
@@ -283,6 +279,7 @@ void tdcgpu_destroy(tdcgpu_ctx* ctx) {
     if (c.h_scalars) cudaFreeHost(c.h_scalars);
     for (auto& e : c.user_events)
         if (e) cudaEventDestroy(e);
+    host_copier_free(c.copier);
     cudaStreamDestroy(c.stream);
     delete ctx;
 }
@@ -291,6 +288,10 @@ int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_dev
     API_GUARD(ctx);
     if (!text || n == 0) { set_error("empty text (the path always sees at least the sentinel)"); return TDCGPU_ERR_ARG; }
     if (n >= (uint64_t(1) << 31)) { set_error("n = %llu: indices are 32-bit, n must be < 2^31", (unsigned long long)n); return TDCGPU_ERR_ARG; }
+    if (!on_device && text[n - 1] != 0) {  // device input: checked by the builder (suffix_array.cu), which reads d_text[n-1]
+        set_error("Input has no sentinel! (the last text byte must be 0, ds/TextDS.hpp:132-138)");
+        return TDCGPU_ERR_SENTINEL;
+    }
     TDC_TRY(ensure_capacity(c, n));
     c.n = n;
     c.have = 0;
@@ -299,9 +300,13 @@ int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_dev
     c.have_factors = false;
     c.enc.prepared = c.enc.encoded = false;
     c.phases.clear();
-    TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c.stream));
     TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, TEXT_PAD + 16, c.stream));
-    if (!on_device) TDC_CUDA(cudaStreamSynchronize(c.stream));  // the caller may reuse its buffer
+    if (on_device) {
+        TDC_CUDA(cudaMemcpyAsync(c.d_text, text, n, cudaMemcpyDeviceToDevice, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));  // the source may be overwritten once the call returns
+    } else {
+        TDC_TRY(host_copy(c, c.d_text, text, n, true));  // blocking: the caller may reuse its buffer
+    }
     return 0;
 }
 
@@ -317,7 +322,8 @@ int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device)
     void* src = array_ptr(c, which, &elem);
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
-    TDC_CUDA(cudaMemcpyAsync(dst, src, elem * c.n, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (!to_device) return host_copy(c, dst, src, elem * c.n, false);
+    TDC_CUDA(cudaMemcpyAsync(dst, src, elem * c.n, cudaMemcpyDeviceToDevice, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -337,7 +343,8 @@ int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, ui
     TDC_LAUNCH(pack_bits_kernel, u32(div_up(nwords, 256)), 256, 0, c.stream, static_cast<const u32*>(src), c.n, width, packed, nwords);
     prof_add_bytes("pack_bits_kernel", double(c.n) * 4 + double(nwords) * 8);
     TDC_KCHECK();
-    TDC_CUDA(cudaMemcpyAsync(dst, packed, nwords * sizeof(u64), to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (!to_device) return host_copy(c, dst, packed, nwords * sizeof(u64), false);
+    TDC_CUDA(cudaMemcpyAsync(dst, packed, nwords * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -373,11 +380,12 @@ int tdcgpu_lzss_lcp_factorize(tdcgpu_ctx* ctx, uint32_t threshold, uint64_t* cou
 
 int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t cap, int to_device) {
     API_GUARD(ctx);
+    if (!c.have_factors) { set_error("no factor list (call tdcgpu_lzss_lcp_factorize first)"); return TDCGPU_ERR_STATE; }
     if (c.num_factors > cap) { set_error("factor buffer too small: %llu > %llu", (unsigned long long)c.num_factors, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
     if (c.num_factors == 0) return 0;
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
-    TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors,
-                             to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (!to_device) return host_copy(c, dst, c.d_factors, sizeof(Factor) * c.num_factors, false);
+    TDC_CUDA(cudaMemcpyAsync(dst, c.d_factors, sizeof(Factor) * c.num_factors, cudaMemcpyDeviceToDevice, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -418,7 +426,8 @@ static int copy_bitstream_out(Ctx& c, const uint8_t* d_stream, u64 nbits, uint8_
     if (total > cap) { set_error("encode buffer too small: %llu > %llu", (unsigned long long)total, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     const u64 body = whole + (used ? 1 : 0);
-    if (body) TDC_CUDA(cudaMemcpyAsync(dst, d_stream, body, to_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c.stream));
+    if (body && to_device) TDC_CUDA(cudaMemcpyAsync(dst, d_stream, body, cudaMemcpyDeviceToDevice, c.stream));
+    if (body && !to_device) TDC_TRY(host_copy(c, dst, d_stream, body, false));
     if (finalize) {
         uint8_t tail[2] = {0, 0};
         if (used) TDC_CUDA(cudaMemcpyAsync(&tail[0], d_stream + whole, 1, cudaMemcpyDeviceToHost, c.stream));
@@ -445,7 +454,7 @@ static int stream_stage_in(Ctx& c, const uint8_t* in, u64 n, u64 out_cap, size_t
     uint8_t* di = c.stream_arena.take<uint8_t>(n + 16);
     *d_out = c.stream_arena.take<uint8_t>(out_cap + 16);
     if (!di || !*d_out) { set_error("stream scratch too small"); return TDCGPU_ERR_NOMEM; }
-    if (n) TDC_CUDA(cudaMemcpyAsync(di, in, n, cudaMemcpyHostToDevice, c.stream));
+    if (n) TDC_TRY(host_copy(c, di, in, n, true));
     *d_in = di;
     return 0;
 }
@@ -462,7 +471,7 @@ int tdcgpu_mtf_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* o
         PhaseTimer t(c, "MTF");
         TDC_TRY(mtf_encode_device(c, d_in, n, d_out));
     }
-    if (!on_device) TDC_CUDA(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, c.stream));
+    if (!on_device) TDC_TRY(host_copy(c, out, d_out, n, false));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -487,7 +496,7 @@ int tdcgpu_rle_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t o
     if (out_n) *out_n = produced;
     if (!on_device) {
         if (produced > cap) { set_error("rle: output buffer too small: %llu > %llu", (unsigned long long)produced, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
-        TDC_CUDA(cudaMemcpyAsync(out, d_out, produced, cudaMemcpyDeviceToHost, c.stream));
+        TDC_TRY(host_copy(c, out, d_out, produced, false));
     }
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
@@ -509,6 +518,7 @@ int tdcgpu_literal_encode_begin(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, 
     c.lit.d_in = d_in;
     c.lit.n = n;
     c.lit.gen = c.stream_arena.gen;
+    c.lit.arena_mark = c.stream_arena.off;
     c.lit.staged = true;
     return 0;
 }
@@ -519,6 +529,7 @@ int tdcgpu_literal_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint
     if (!codes || !lens) { set_error("null code table"); return TDCGPU_ERR_ARG; }
     if (!c.lit.staged || c.lit.gen != c.stream_arena.gen) { set_error("no staged input (call tdcgpu_literal_encode_begin first)"); return TDCGPU_ERR_STATE; }
     c.phases.clear();
+    c.stream_arena.off = c.lit.arena_mark;  // re-encoding the staged input (e.g. with another code table) reuses the scratch
     {
         PhaseTimer t(c, "Literal encode");
         TDC_TRY(literal_encode_device(c, c.lit.d_in, c.lit.n, codes, lens, lead_bits, lead_byte, &c.lit.nbits));
