@@ -163,95 +163,135 @@ def cpu_reference_parallel(blocks, steps: int):
     return kind, times
 
 
-def verify_shard(ctx, text, info, zl, rank, samples=2000):
-    """Size-independent properties on a random sample of this rank's shard (the CPU oracle cannot reach multi-GB texts):
-    SA[j-1] < SA[j] as suffixes and LCP[j] = their common prefix (direct byte comparison on the host text); every sampled
-    factor copies an earlier occurrence (text[src:src+len] == text[pos:pos+len], src < pos) and cannot be extended."""
-    import tudocomp_b200 as tdc
+def gen_text_device(workload: str, n_body: int, seed: int, device: int):
+    """Multi-GB texts of the sharded configuration, generated ON the GPU (torch's Philox generator: the same seed gives
+    the same bytes on every rank) — numpy needs ~10 s per GB.  Returns a uint8 CUDA tensor of n_body + 1 bytes (sentinel)."""
+    import torch
 
-    rng = np.random.default_rng(1234 + rank)
-    sa, lcp = ctx.get(tdc.SA), ctx.get(tdc.LCP)
-    n = text.size
-    bad = []
-
-    def common(a, b, limit=1 << 16):
-        l = 0
-        while l < limit:
-            step = min(4096, n - max(a, b) - l)
-            if step <= 0:
-                break
-            x, y = text[a + l:a + l + step], text[b + l:b + l + step]
-            d = np.nonzero(x != y)[0]
-            if d.size:
-                return l + int(d[0])
-            l += step
-        return l
-
-    if sa.size > 1:
-        for j in rng.integers(1, sa.size, size=min(samples, sa.size - 1)):
-            a, b = int(sa[j - 1]), int(sa[j])
-            l = common(a, b)
-            if l != int(lcp[j]) or not (text[a + l] < text[b + l]):
-                bad.append(("sa/lcp", int(j), a, b, l, int(lcp[j])))
-    f = ctx.factors(zl)
-    if zl:
-        for k in rng.integers(0, zl, size=min(samples, zl)):
-            pos, src, ln = int(f["pos"][k]), int(f["src"][k]), int(f["len"][k])
-            ok = src < pos and ln >= THRESHOLD and common(src, pos, ln + 1) == ln
-            if not ok:
-                bad.append(("factor", int(k), pos, src, ln))
-        if not (np.all(np.diff(f["pos"].astype(np.int64)) > 0) and int(f["pos"][0]) >= info["pos_lo"] and int(f["pos"][-1]) < info["pos_lo"] + info["pos_cnt"]):
-            bad.append(("factor order/range",))
-    return {"ok": not bad, "sampled_slots": int(min(samples, max(sa.size - 1, 0))), "sampled_factors": int(min(samples, zl)), "first_problems": bad[:3]}
+    if workload != "dna":
+        t = torch.from_numpy(gen_text(workload, n_body, seed))
+        return t.to(f"cuda:{device}")
+    g = torch.Generator(device=f"cuda:{device}")
+    g.manual_seed(seed)
+    out = torch.empty(n_body + 1, dtype=torch.uint8, device=f"cuda:{device}")
+    lut = torch.tensor(list(b"ACGT"), dtype=torch.uint8, device=f"cuda:{device}")
+    chunk = 1 << 27
+    for lo in range(0, n_body, chunk):
+        hi = min(n_body, lo + chunk)
+        idx = torch.randint(0, 4, (hi - lo,), generator=g, device=f"cuda:{device}", dtype=torch.int64)
+        out[lo:hi] = lut[idx]
+    out[n_body] = 0
+    return out
 
 
-def main_dist(args, rank, local_rank, world, n_body, seed):
-    """One text of n_body bytes sharded over all ranks (config 4 of BASELINE.json): distributed prefix-doubling SA with
-    NCCL all-to-all exchanges, LCP, lzss_lcp factorisation.  Strong scaling: value = n_body / step time (max over ranks)."""
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
+    return peak, src
+
+
+def kernel_table(prof):
+    return {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+
+def dominant_roofline(prof, dev_ms, peak, peak_src, with_traffic=True):
+    dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
+    if not dom:
+        return None
+    d = prof[dom]
+    plb, plm = d["bytes"] / max(d["launches"], 1), d["ms"] / max(d["launches"], 1)
+    ach = plb / 1e9 / (plm / 1e3) if d["bytes"] else None
+    traffic, traffic_src = None, None
+    if with_traffic:
+        # DRAM bytes per launch: the committed `ncu --set full` capture of this kernel (profiles/traffic.json) gives dram
+        # bytes per algorithmic byte; scaled to the average launch of this run
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+            if tj and plb:
+                traffic = tj["dram_per_algorithmic_byte"] * plb
+                traffic_src = "profiles/traffic.json: " + tj["capture"]
+        except Exception:
+            pass
+    return {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launches": d["launches"],
+            "avg_launch_ms": plm, "algorithmic_bytes_per_launch": plb, "share_of_step": d["ms"] / dev_ms}
+
+
+def golden_case(workload, n_body, seed):
+    """The tests/golden/size_hashes.json entry (fingerprints of the unmodified reference) for exactly this text, if any."""
+    try:
+        hashes = json.load(open(os.path.join(ROOT, "tests", "golden", "size_hashes.json")))
+    except Exception:
+        return None, None
+    for name, c in hashes.items():
+        if c.get("generator") == [workload, n_body, seed] and "factors" in c:
+            return name, c
+    return None, None
+
+
+def sha256_of(a) -> str:
+    import hashlib
+
+    return hashlib.sha256(memoryview(np.ascontiguousarray(a)).cast("B")).hexdigest()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# one text sharded over all ranks (BASELINE config 4)
+# ---------------------------------------------------------------------------------------------------------------------
+def dist_record(args, lib, rank, local_rank, world, dist, n_body, seed, steps, warmup, verify):
+    """One text of n_body bytes sharded over all ranks: distributed prefix-doubling SA with all-to-all exchanges of rank
+    buckets, LCP, lzss_lcp factorisation.  Strong scaling: value = n_body / step time (max over ranks).  Returns the
+    record on rank 0 (None elsewhere).  world == 1 uses the same sharded code path on one rank when it fits, which it
+    does not above ~1.5e9 B (84 B per suffix): then the single-GPU context serves as the N = 1 point."""
     import torch
 
     import tudocomp_b200 as tdc
     from tudocomp_b200 import blockmode
     from tudocomp_b200.dist import DistContext
 
-    dist = None
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    lib = tdc.load()
-    ctx = DistContext.create_nccl(lib, local_rank, dist)
-    text = gen_text(args.workload, n_body, seed)  # the same text on every rank
-    n = int(text.size)
-    h_text = torch.from_numpy(text).pin_memory()
-    d_text = h_text.to(f"cuda:{local_rank}")
+    single = world == 1 and n_body > 1_500_000_000
+    d_text = gen_text_device(args.workload, n_body, seed, local_rank)  # the same text on every rank
+    n = int(d_text.numel())
+    h_text = torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_text.copy_(d_text)
     torch.cuda.synchronize()
+    ctx = tdc.Context(lib, local_rank) if single else DistContext.create_nccl(lib, local_rank, dist if world > 1 else None)
 
     def barrier():
         torch.cuda.synchronize()
         ctx.sync()
-        if dist is not None:
+        if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     def step(host):
+        if single:
+            if host:
+                ctx.set_text_host_ptr(h_text.data_ptr(), n)
+            else:
+                ctx.set_text_device(d_text.data_ptr(), n)
+            ctx.build(tdc.SA | tdc.ISA | tdc.LCP)
+            z, mn, mx = ctx.factorize(THRESHOLD)
+            return z, z, mn, mx
         ctx.set_text_ptr(h_text.data_ptr() if host else d_text.data_ptr(), n, on_device=not host)
         ctx.build()
         return ctx.factorize(THRESHOLD)
 
     zl, zt, mn, mx = step(False)
     h_factors = torch.empty(int(zl * 1.05) + 1024, 3, dtype=torch.int32).pin_memory()
-    for _ in range(args.warmup):
+    for _ in range(max(warmup - 1, 0)):
         step(False)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     lib.profile_reset()
     lib.profile_enable(True)
     barrier()
     launches0 = lib.launch_count()
     ctx.event_record(0)
-    for _ in range(args.steps):
+    for _ in range(steps):
         zl, zt, mn, mx = step(False)
     ctx.event_record(1)
     barrier()
@@ -260,62 +300,48 @@ def main_dist(args, rank, local_rank, world, n_body, seed):
     lib.profile_enable(False)
     prof = lib.profile()
     phases = ctx.phases()
-    stats = ctx.stats()
-    info = ctx.shard_info()
+    stats = ctx.sa_stats() if single else ctx.stats()
+    info = {"slot_lo": 0, "slot_cnt": n, "pos_lo": 0, "pos_cnt": n} if single else ctx.shard_info()
+    verified = None
+    if verify:  # outside the timed regions, on the results of the last resident step
+        try:
+            verified = ctx.check(THRESHOLD, zl) if single else ctx.verify_full(THRESHOLD, zl, local_rank, dist if world > 1 else None)
+            verified["how"] = "every SA/ISA/LCP slot and every parse position, device checkers (csrc/check.cu)"
+        except Exception as e:  # noqa: BLE001  (e.g. the gathered arrays do not fit next to the shards)
+            verified = {"ok": None, "error": f"{type(e).__name__}: {e}"[:300]}
     barrier()
     t1 = time.perf_counter()
     ctx.event_record(2)
-    for _ in range(args.steps):
+    for _ in range(steps):
         zl, zt, mn, mx = step(True)
         ctx.get_factors_into(h_factors.data_ptr(), h_factors.shape[0])
     ctx.event_record(3)
     barrier()
     e2e_ms = max(ctx.event_elapsed_ms(2, 3), 1e3 * (time.perf_counter() - t1))
-    clocks = sampler.stop()
-    ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist)
-    ms_step_e2e = blockmode.reduce_step_time(e2e_ms / args.steps, dist)
-    verified = None
-    if args.verify:
-        verified = verify_shard(ctx, text, info, zl, rank)
-        if dist is not None:
-            flag = torch.tensor([0 if verified["ok"] else 1], device=f"cuda:{local_rank}")
-            dist.all_reduce(flag)
-            verified["all_ranks_ok"] = bool(flag.item() == 0)
-    if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        dom = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
-        roof = None
-        if dom:
-            dd = prof[dom]
-            plb, plm = dd["bytes"] / max(dd["launches"], 1), dd["ms"] / max(dd["launches"], 1)
-            ach = plb / 1e9 / (plm / 1e3) if dd["bytes"] else None
-            roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
-                    "traffic": None, "launches": dd["launches"], "avg_launch_ms": plm, "share_of_step": dd["ms"] / dev_ms,
-                    "note": "rank 0's kernels; the NCCL exchanges are not in this list (they are the gap between the kernel sum and the step time)"}
-        line = {"metric": METRIC, "value": blockmode.job_throughput_mb_s(n_body, ms_step), "unit": "MB/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}_{n_body}B_single_text_sharded: distributed SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD})",
-                           "text_bytes": n, "threshold": THRESHOLD, "index_bits": 32,
-                           "l2_policy": "working set per GPU far larger than the 126 MB L2; no flush needed",
-                           "parallelism": f"one text sharded over {world} GPUs; NCCL all-to-all of rank buckets, rank updates and rank requests"},
-                "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
-                        "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
-                "dist_stats": stats, "shard_rank0": info, "verify": verified,
-                "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
-                "last_step_phases_ms": {k: round(v, 3) for k, v in phases}}
-        print(json.dumps(line))
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    ms_step = blockmode.reduce_step_time(dev_ms / steps, dist if world > 1 else None)
+    ms_step_e2e = blockmode.reduce_step_time(e2e_ms / steps, dist if world > 1 else None)
     ctx.close()
-    return 0
+    del d_text, h_text, h_factors
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    peak, peak_src = load_peaks()
+    roof = dominant_roofline(prof, dev_ms, peak, peak_src, with_traffic=False)
+    if roof:
+        roof["note"] = "rank 0's kernels; the exchanges are the gap between the kernel sum and the step time"
+    return {"metric": METRIC, "value": blockmode.job_throughput_mb_s(n_body, ms_step), "unit": "MB/s", "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}_{n_body}B_single_text_sharded: distributed SA+ISA+LCP + lzss_lcp(threshold={THRESHOLD})",
+                       "text_bytes": n, "threshold": THRESHOLD, "index_bits": 32,
+                       "l2_policy": "working set per GPU far larger than the 126 MB L2; no flush needed",
+                       "parallelism": (f"one text sharded over {world} GPUs; all-to-all of rank buckets, rank updates and rank requests"
+                                       if not single else "N = 1 point of the strong-scaling curve: the single-GPU context on the same text")},
+            "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
+                    "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
+            "gpu_launches": int(launches), "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
+            "dist_stats": stats, "shard_rank0": info, "verify": verified, "kernels": kernel_table(prof),
+            "last_step_phases_ms": {k: round(v, 3) for k, v in phases}}
 
 
 def main():
@@ -327,11 +353,14 @@ def main():
     ap.add_argument("--workload", default="dna", choices=["dna", "markov", "repetitive"])
     ap.add_argument("--log2-bytes", type=int, default=30, help="text body size per GPU = 2^L bytes (default 1 GiB)")
     ap.add_argument("--bytes", type=int, default=0, help="text body size in bytes (overrides --log2-bytes), e.g. 4000000000")
-    ap.add_argument("--verify", action="store_true", help="dist mode: sampled on-host checks of SA order, LCP values and factors")
+    ap.add_argument("--no-verify", action="store_true", help="skip the full device-side verification after the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dist", action="store_true", help="default mode: skip the sharded-text sub-records (config 4)")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the double-buffered (2 contexts) end-to-end measurement")
+    ap.add_argument("--dist-bytes", type=int, default=2_000_000_000, help="text size of the sharded sub-record (strong scaling over N)")
     ap.add_argument("--mode", default="block", choices=["block", "dist"],
-                    help="N > 1: 'block' = one independent text per GPU (weak scaling, no collective); 'dist' = ONE text of "
-                         "2^L bytes sharded over all GPUs (strong scaling, NCCL all-to-all of rank buckets)")
+                    help="'block' (default, the headline): one independent text per GPU (weak scaling, no collective), with the "
+                         "sharded-text measurement attached as `dist`; 'dist': ONE text of --bytes sharded over all GPUs is the line")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -367,35 +396,51 @@ def main():
         times = times[args.warmup:]
         mean_t = sum(times) / len(times)
         mbps = cores * sample_body / 1e6 / mean_t
+        sample = (f"{cores} consecutive blocks of 2^{int(np.log2(sample_body))} B of the workload text (+ sentinel each), "
+                  f"one single-threaded reference process per block, all {cores} at once; single_core = one block alone")
+        config["reference_sample"] = (f"NOT one {size_name} text: {cores} x 2^{int(np.log2(sample_body))} B blocks of it (bounded sample; the "
+                                      "reference is single-threaded and needs ~15 min per 2^30 B text, tests/golden/size_hashes.json "
+                                      "holds its wall times at full size)")
         line = {"impl": "reference", "metric": METRIC, "value": mbps, "unit": "MB/s", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": 1e3 * mean_t, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "u32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": kind, "single_core": single,
-                                 "sample": f"{cores} consecutive blocks of 2^{int(np.log2(sample_body))} B of the workload text (+ sentinel each), "
-                                           f"one single-threaded reference process per block, all {cores} at once; single_core = one block alone"},
+                "cpu_baseline": {"value": mbps, "unit": "MB/s", "cores": cores, "kind": kind, "single_core": single, "sample": sample},
                 "e2e": {"value": mbps, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
-
-    if args.mode == "dist":
-        return main_dist(args, rank, local_rank, world, n_body, seed_of)
 
     # ------------------------------------------------------------------------------------------------------ our arm
     import torch
 
     import tudocomp_b200 as tdc
+    from tudocomp_b200 import blockmode
 
+    dist = None
+    torch.cuda.set_device(local_rank)
     if world > 1:
         import torch.distributed as dist
 
-        torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
-    torch.cuda.set_device(dev)
     lib = tdc.load()  # raises if the CUDA library is missing: no fallback
-    ctx = tdc.Context(lib, dev)
+    verify = not args.no_verify
 
-    text = gen_text(args.workload, n_body, seed_of + 1000 * rank)
+    if args.mode == "dist":
+        sampler = ClockSampler(dev)
+        sampler.start()
+        line = dist_record(args, lib, rank, local_rank, world, dist, n_body, seed_of, args.steps, args.warmup, verify)
+        clocks = sampler.stop()
+        if rank == 0:
+            line["clocks"] = clocks
+            print(json.dumps(line))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    ctx = tdc.Context(lib, dev)
+    seed = seed_of + 1000 * rank
+    text = gen_text(args.workload, n_body, seed)
     n = int(text.size)
     h_text = torch.from_numpy(text).pin_memory()
     d_text = h_text.to(f"cuda:{dev}", non_blocking=False)
@@ -417,11 +462,13 @@ def main():
     z0, _, _ = step_resident()
     h_factors = torch.empty(int(z0 * 1.05) + 1024, 3, dtype=torch.int32).pin_memory()
 
-    def step_e2e():
-        ctx.set_text_host_ptr(h_text.data_ptr(), n)
-        ctx.build(tdc.SA | tdc.ISA | tdc.LCP)
-        z, mn, mx = ctx.factorize(THRESHOLD)
-        ctx.get_factors_into(h_factors.data_ptr(), h_factors.shape[0])
+    def step_e2e(c=None, hf=None, h_in=None):
+        c = c or ctx
+        c.set_text_host_ptr(h_in if h_in else h_text.data_ptr(), n)
+        c.build(tdc.SA | tdc.ISA | tdc.LCP)
+        z, mn, mx = c.factorize(THRESHOLD)
+        hf = hf if hf is not None else h_factors
+        c.get_factors_into(hf.data_ptr() if hasattr(hf, "data_ptr") else hf.ctypes.data, hf.shape[0])
         return z, mn, mx
 
     for _ in range(args.warmup):
@@ -448,7 +495,27 @@ def main():
     stats = ctx.sa_stats()
     phases = ctx.phases()
 
-    # ---- timed: end to end with host buffers ----
+    # ---- verification of the last timed step's results, outside the timed region ----
+    verified = None
+    if verify:
+        try:
+            verified = ctx.check(THRESHOLD, z)  # every slot and every parse position, on the device
+            verified["how"] = "device checkers (csrc/check.cu): ISA[SA[i]]==i, Burkhardt-Kaerkkaeinen order, LCP by direct comparison, the reference's PSV/NSV rule at every parse position"
+            gname, gold = golden_case(args.workload, n_body, seed)
+            if gold is not None:
+                f = ctx.factors(z)
+                verified["reference_fingerprint"] = {"case": gname, "what": "sha256 of the factor list == the unmodified reference's (tests/golden/size_hashes.json)",
+                                                     "match": bool(z == gold["factors"]["z"] and sha256_of(f) == gold["factors"]["factors"])}
+                verified["ok"] = bool(verified["ok"] and verified["reference_fingerprint"]["match"])
+                del f
+        except Exception as e:  # noqa: BLE001
+            verified = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+        if world > 1:
+            flag = torch.tensor([0 if verified.get("ok") else 1], device=f"cuda:{dev}")
+            dist.all_reduce(flag)
+            verified["all_ranks_ok"] = bool(flag.item() == 0)
+
+    # ---- timed: end to end with host buffers, one context (serial: copy in, compute, copy out) ----
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     barrier()
@@ -459,7 +526,65 @@ def main():
     ctx.event_record(3)
     barrier()
     wall_e2e = time.perf_counter() - t1
-    dev_ms_e2e = max(ctx.event_elapsed_ms(2, 3), 1e3 * wall_e2e)  # host-inclusive, take the larger
+    ms_e2e_serial = max(ctx.event_elapsed_ms(2, 3), 1e3 * wall_e2e) / args.steps  # host-inclusive, take the larger
+
+    # ---- the same with PAGEABLE host buffers (what the tdc driver's View / std::vector are): staged copies (csrc/host_copy.cu)
+    ms_e2e_pageable = None
+    try:
+        pg_text = text  # numpy, pageable
+        pg_factors = np.empty((h_factors.shape[0], 3), np.int32)
+        step_e2e(None, pg_factors, pg_text.ctypes.data)
+        ctx.sync()
+        t1 = time.perf_counter()
+        for _ in range(min(args.steps, 5)):
+            step_e2e(None, pg_factors, pg_text.ctypes.data)
+        ctx.sync()
+        ms_e2e_pageable = 1e3 * (time.perf_counter() - t1) / min(args.steps, 5)
+        del pg_factors
+    except Exception as e:  # noqa: BLE001
+        ms_e2e_pageable = f"{type(e).__name__}: {e}"[:200]
+
+    # ---- timed: end to end, double-buffered: two contexts on the GPU, each driven by its own host thread, so that one text's
+    # H2D / D2H overlaps the other's kernels (a stream of independent texts is exactly what block mode is).  Same C-ABI calls,
+    # same pinned host buffers, every step copies its text in and its factor list out.
+    ms_e2e_pipe, pipe_error = None, None
+    if not args.no_pipeline:
+        ctx2 = None
+        try:
+            ctx2 = tdc.Context(lib, dev)
+            h_factors2 = torch.empty_like(h_factors).pin_memory()
+            step_e2e(ctx2, h_factors2)
+            counts = [(args.steps + 1) // 2, args.steps // 2]
+            errs = []
+
+            def worker(c, hf, k):
+                try:
+                    for _ in range(k):
+                        step_e2e(c, hf)
+                except Exception as e:  # noqa: BLE001
+                    errs.append(e)
+
+            barrier()
+            ctx2.sync()
+            t1 = time.perf_counter()
+            th = [threading.Thread(target=worker, args=(ctx, h_factors, counts[0])), threading.Thread(target=worker, args=(ctx2, h_factors2, counts[1]))]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+            ctx.sync()
+            ctx2.sync()
+            ms_e2e_pipe = 1e3 * (time.perf_counter() - t1) / args.steps
+            if errs:
+                raise errs[0]
+        except Exception as e:  # noqa: BLE001
+            ms_e2e_pipe, pipe_error = None, f"{type(e).__name__}: {e}"[:300]
+        finally:
+            if ctx2 is not None:
+                ctx2.close()
+            torch.cuda.empty_cache()
+    ms_e2e_local = ms_e2e_pipe if (ms_e2e_pipe and ms_e2e_pipe < ms_e2e_serial) else ms_e2e_serial
+
     # ---- timed: host text in -> finished lzss_lcp(bit) archive out (device-side lzss::encode_text).
     # Not the headline: the D2H side is the archive instead of the factor list.  BitCoder's literal words (8 bits) need no
     # host-side table; with HuffmanCoder the C++ plugin builds the table from the same device histogram.
@@ -476,22 +601,27 @@ def main():
         return nbits
 
     # informational, rank-local (no collective inside: a failure here must neither hang the other ranks nor cost the headline)
-    arc_bits, arc_ms, prof_arc, arc_error = 0, None, {}, None
+    arc_bits, arc_ms, prof_arc, arc_error, arc_match = 0, None, {}, None, None
     try:
         arc_bits = step_archive()
         h_arc = torch.empty(arc_bits // 8 + 64, dtype=torch.uint8).pin_memory()
-        step_archive(h_arc.data_ptr(), h_arc.numel())
+        nb = step_archive(h_arc.data_ptr(), h_arc.numel())
+        gname, gold = golden_case(args.workload, n_body, seed)
+        if gold is not None and "bit" in gold and verify:
+            ln = gold["bit"]["archive_len"]
+            arc_match = bool(ln <= h_arc.numel() and sha256_of(h_arc.numpy()[:ln]) == gold["bit"]["archive"])
         lib.profile_reset()
         lib.profile_enable(True)
         torch.cuda.synchronize()
         ctx.sync()
         ctx.event_record(4)
         t2 = time.perf_counter()
-        for _ in range(args.steps):
+        asteps = min(args.steps, 5)
+        for _ in range(asteps):
             step_archive(h_arc.data_ptr(), h_arc.numel())
         ctx.event_record(5)
         ctx.sync()
-        arc_ms = max(ctx.event_elapsed_ms(4, 5), 1e3 * (time.perf_counter() - t2)) / args.steps
+        arc_ms = max(ctx.event_elapsed_ms(4, 5), 1e3 * (time.perf_counter() - t2)) / asteps
         lib.profile_enable(False)
         prof_arc = {k: v for k, v in lib.profile().items() if k.startswith("enc_")}
     except Exception as e:  # noqa: BLE001
@@ -499,46 +629,18 @@ def main():
         arc_error = f"{type(e).__name__}: {e}"
     clocks = sampler.stop()
 
-    from tudocomp_b200 import blockmode
-
     # whole-job step time = max over ranks (block mode: no other communication)
-    ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist if world > 1 else None)
-    ms_step_e2e = blockmode.reduce_step_time(dev_ms_e2e / args.steps, dist if world > 1 else None)
+    ms_step = blockmode.reduce_step_time(dev_ms / args.steps, dist)
+    ms_step_e2e = blockmode.reduce_step_time(ms_e2e_local, dist)
+    ms_step_e2e_serial = blockmode.reduce_step_time(ms_e2e_serial, dist)
     total_bytes = n_body * world
     value = blockmode.job_throughput_mb_s(total_bytes, ms_step)
     e2e_value = blockmode.job_throughput_mb_s(total_bytes, ms_step_e2e)
 
+    line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)"
-        # dominant kernel: the radix-sort digit pass
-        dom_name = max(prof, key=lambda k: prof[k]["ms"]) if prof else None
-        roof = None
-        if dom_name:
-            d = prof[dom_name]
-            per_launch_bytes = d["bytes"] / max(d["launches"], 1)
-            per_launch_ms = d["ms"] / max(d["launches"], 1)
-            achieved = per_launch_bytes / 1e9 / (per_launch_ms / 1e3) if d["bytes"] else None
-            # DRAM bytes per launch: the committed `ncu --set full` capture of this kernel (profiles/traffic.json) gives
-            # dram bytes per algorithmic byte; scaled to the average launch of this run
-            traffic, traffic_src = None, None
-            try:
-                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom_name)
-                if tj and per_launch_bytes:
-                    traffic = tj["dram_per_algorithmic_byte"] * per_launch_bytes
-                    traffic_src = "profiles/traffic.json: " + tj["capture"]
-            except Exception:
-                pass
-            roof = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": peak_src,
-                    "launches": d["launches"], "avg_launch_ms": per_launch_ms, "algorithmic_bytes_per_launch": per_launch_bytes,
-                    "share_of_step": d["ms"] / dev_ms}
+        peak, peak_src = load_peaks()
+        roof = dominant_roofline(prof, dev_ms, peak, peak_src)
         pipeline_bytes = (25.0 * n + 12.0 * z)  # compulsory traffic of SA+ISA+LCP+factorisation
         pipeline = {"algorithmic_bytes": pipeline_bytes, "achieved_GBps": pipeline_bytes / 1e9 / (ms_step / 1e3),
                     "frac_of_peak": pipeline_bytes / 1e9 / (ms_step / 1e3) / peak}
@@ -546,23 +648,30 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": e2e_value, "unit": "MB/s", "h2d_bytes_per_step": n, "d2h_bytes_per_step": int(12 * ze),
-                        "ms_per_step": ms_step_e2e},
+                        "ms_per_step": ms_step_e2e,
+                        "mode": ("double-buffered: 2 device contexts per GPU driven by 2 host threads through the C ABI, pinned host text in and "
+                                 "factor list out every step" if ms_e2e_local == ms_e2e_pipe else "serial: one context, copy in -> compute -> copy out"),
+                        "serial_ms_per_step": ms_step_e2e_serial, "serial_value": blockmode.job_throughput_mb_s(total_bytes, ms_step_e2e_serial),
+                        "pipelined_ms_per_step_rank0": ms_e2e_pipe, "pipeline_error": pipe_error,
+                        "pageable_serial_ms_per_step_rank0": ms_e2e_pageable},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "pipeline_roofline": pipeline,
-                "factors": int(z), "factor_len": [int(mn), int(mx)], "sa_stats": stats,
-                "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "verified": bool(verified and verified.get("ok") and verified.get("all_ranks_ok", True)) if verify else None,
+                "verify": verified,
+                "factors": int(z), "factor_len": [int(mn), int(mx)], "sa_stats": stats, "kernels": kernel_table(prof),
                 "last_step_phases_ms": {k: round(v, 3) for k, v in phases}, "wall_s_timed": wall}
         if arc_error or not arc_ms:
             line["archive"] = {"error": arc_error or "not measured"}
         else:
-            enc_ms = sum(v["ms"] for v in prof_arc.values()) / args.steps
-            enc_bytes = sum(v["bytes"] for v in prof_arc.values()) / args.steps
+            enc_ms = sum(v["ms"] for v in prof_arc.values()) / asteps
+            enc_bytes = sum(v["bytes"] for v in prof_arc.values()) / asteps
             line["archive"] = {"what": "rank 0: host text -> lzss_lcp(coder=bit,threshold=3) archive in pinned host memory, through the C ABI "
                                        "(build + factorize + literal histogram + device-side lzss::encode_text + D2H of the archive)",
                                "value": n_body / 1e6 / (arc_ms / 1e3), "unit": "MB/s", "ms_per_step": arc_ms,
                                "h2d_bytes_per_step": n, "d2h_bytes_per_step": int((arc_bits + 7) // 8 + 1), "archive_bits": int(arc_bits),
+                               "byte_identical_to_reference": arc_match,
                                "encode_kernels_ms_per_step": round(enc_ms, 3),
                                "encode_algorithmic_GBps": (enc_bytes / 1e9 / (enc_ms / 1e3)) if enc_ms else None,
-                               "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)} for k, v in sorted(prof_arc.items(), key=lambda kv: -kv[1]["ms"])}}
+                               "kernels": kernel_table(prof_arc)}
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             sample_body = min(n_body, 1 << CPU_SAMPLE_LOG2)
             sample = text[: sample_body + 1].copy()
@@ -571,12 +680,66 @@ def main():
             line["cpu_baseline"] = {"value": sample_body / 1e6 / times[0], "unit": "MB/s", "cores": 1, "kind": kind,
                                     "host_cores_available": os.cpu_count(),
                                     "sample": f"first 2^{int(np.log2(sample_body))} B of rank 0's text + sentinel, one run; the reference is single-threaded"}
+            try:
+                plug = plugin_e2e(text, n_body, args.steps)
+            except Exception as e:  # noqa: BLE001
+                plug = {"error": f"{type(e).__name__}: {e}"[:200]}
+            if plug:
+                line["plugin_e2e"] = plug
+    # ---- config 4 next to the headline: ONE text sharded over all N GPUs (strong scaling over N) ----
+    ctx.close()
+    del d_text, h_text, h_factors
+    torch.cuda.empty_cache()
+    if not args.no_dist:
+        recs = []
+        sizes = [args.dist_bytes] + ([4_000_000_000] if world >= 4 else [])
+        for nb in sizes:
+            try:
+                rec = dist_record(args, lib, rank, local_rank, world, dist, nb, 4, min(args.steps, 5), min(args.warmup, 2), verify)
+            except Exception as e:  # noqa: BLE001
+                rec = {"error": f"{type(e).__name__}: {e}"[:300], "text_bytes": nb}
+                if world > 1:
+                    raise  # a rank that fails alone would hang the others in the next collective
+            if rank == 0:
+                recs.append(rec)
+        if rank == 0:
+            line["dist"] = recs
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    ctx.close()
     return 0
+
+
+def plugin_e2e(text, n_body, steps):
+    """The same step through the C++ plugin the `tdc` driver uses: LZSSLCPCompressor<coder, GpuTextDS>::compress on an
+    in-memory Input / Output, K times in one process (build/tdc_plugin_bench, built against the reference headers in the
+    build container; absent binary -> no record)."""
+    exe = os.path.join(ROOT, "build", "tdc_plugin_bench")
+    if not os.path.exists(exe):
+        return None
+    import shutil
+    import tempfile
+
+    out = {}
+    try:
+        where = next(d for d in ("/dev/shm", tempfile.gettempdir(), ROOT) if os.path.isdir(d) and shutil.disk_usage(d).free > 2 * n_body + (1 << 28))
+    except StopIteration:
+        return {"error": "no scratch directory with room for the input file"}
+    with tempfile.NamedTemporaryFile(dir=where, suffix=".txt") as f:
+        f.write(memoryview(text[:-1]))  # the driver adds the sentinel itself
+        f.flush()
+        for coder in ("bit", "huff"):
+            try:
+                r = subprocess.run([exe, f.name, coder, str(THRESHOLD), str(max(2, min(steps, 5))), "1"], capture_output=True, text=True, timeout=600)
+                rec = json.loads(r.stdout.strip().splitlines()[-1])
+                rec["value"] = n_body / 1e6 / (rec["ms_per_step"] / 1e3)
+                rec["unit"] = "MB/s"
+                out[coder] = rec
+            except Exception as e:  # noqa: BLE001
+                out[coder] = {"error": f"{type(e).__name__}: {e}"[:200]}
+    return out
 
 
 if __name__ == "__main__":

@@ -34,6 +34,17 @@ def main():
         info = check_against_oracle(ctx, oracle, t, (3, 5))
         if rank == 0:
             print(f"dist ok: {name} n={t.size} world={world} shard0={info} stats={ctx.stats()}", flush=True)
+    # sizes the oracle does not finish in seconds: every slot and every parse position checked on the device
+    big = int(os.environ.get("TDC_DIST_TEST_BIG_BYTES", str(1 << 26)))
+    for name, t in (("dna_big", synth.dna(big, 14)), ("markov_big", synth.markov_text(big // 2, 15)),
+                    ("repetitive_big", synth.repetitive(big // 4, 16, block=1 << 16, p=0.01))):
+        ctx.set_text(t)
+        ctx.build()
+        zl, zt, mn, mx = ctx.factorize(3)
+        res = ctx.verify_full(3, zl, local, dist)
+        assert res["ok"], (name, rank, res)
+        if rank == 0:
+            print(f"dist verified: {name} n={t.size} world={world} factors={zt} rank0={res}", flush=True)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -40,3 +40,16 @@ def test_one_text_over_all_gpus_nccl():
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
     assert r.stdout.count("dist ok:") == 5, r.stdout[-2000:]
+    assert r.stdout.count("dist verified:") == 3, r.stdout[-2000:]
+
+
+def test_single_rank_full_device_verification():
+    """The sharded code path on one rank at 2^26 B, every slot / position checked by the device checkers."""
+    lib = tdc.load()
+    with DistContext.create_nccl(lib, 0, None) as ctx:
+        for name, t in (("dna", synth.dna(1 << 26, 14)), ("markov", synth.markov_text(1 << 25, 15))):
+            ctx.set_text(t)
+            ctx.build()
+            zl, zt, _, _ = ctx.factorize(3)
+            res = ctx.verify_full(3, zl, 0, None)
+            assert res["ok"] and res["checked_slots"] == t.size, (name, res)

@@ -1,0 +1,27 @@
+#!/usr/bin/env bash
+# Round-2 GPU job (one parameterised script instead of round 1's gpu_run1..22.sh): tools/gpu_r2.sh <tag> <stage>...
+#   tests     pytest -m gpu (TDC_SIZE_CASES restricts tests/test_gpu_sizes.py)
+#   bench     default bench.py line (N=1) -> gpurun_out/<tag>_bench.json
+#   launches  ncu launch list of a 2-step bench
+# Everything the job wants to keep goes to gpurun_out/.
+set -u
+cd "$(dirname "$0")/.."
+tag="$1"; shift
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv,noheader > gpurun_out/${tag}_gpu.txt 2>&1
+for stage in "$@"; do
+  case "$stage" in
+    tests)
+      timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/${tag}_tests.txt ;;
+    quicktests)
+      timeout 900 python -m pytest tests/test_check.py tests/test_gpu_parity.py tests/test_gpu_dist.py tests/test_gpu_sizes.py -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/${tag}_tests.txt ;;
+    bench)
+      timeout 900 python bench.py --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+      echo "bench rc=$?"; head -c 3000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err ;;
+    launches)
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
+        python bench.py --steps 2 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
+      echo "launches rc=$?" ;;
+    *) echo "unknown stage $stage" ;;
+  esac
+done

@@ -14,6 +14,7 @@ DIST_EXPORTS = [
     "tdcgpu_dist_shard_info", "tdcgpu_dist_get", "tdcgpu_dist_max_lcp", "tdcgpu_dist_lzss_lcp_factorize",
     "tdcgpu_dist_get_factors", "tdcgpu_dist_sync", "tdcgpu_dist_event_record", "tdcgpu_dist_event_elapsed_ms",
     "tdcgpu_dist_stats", "tdcgpu_dist_phase_count", "tdcgpu_dist_phase_name", "tdcgpu_dist_phase_ms",
+    "tdcgpu_dist_text_device_ptr", "tdcgpu_dist_factors_device_ptr",
 ]
 
 
@@ -40,6 +41,10 @@ def bind_dist(lib: TdcGpuLib) -> None:
     L.tdcgpu_dist_phase_name.restype = C.c_char_p
     L.tdcgpu_dist_phase_ms.argtypes = [C.c_void_p, C.c_int]
     L.tdcgpu_dist_phase_ms.restype = C.c_float
+    L.tdcgpu_dist_text_device_ptr.argtypes = [C.c_void_p]
+    L.tdcgpu_dist_text_device_ptr.restype = C.c_void_p
+    L.tdcgpu_dist_factors_device_ptr.argtypes = [C.c_void_p]
+    L.tdcgpu_dist_factors_device_ptr.restype = C.c_void_p
     L._tdc_dist_bound = True
 
 
@@ -105,6 +110,79 @@ class DistContext:
         out = np.empty(info["pos_cnt"] if which == ISA else info["slot_cnt"], dtype=np.uint32)
         self.lib.check(self.lib.lib.tdcgpu_dist_get(self._h, which, C.c_void_p(out.ctypes.data), 0))
         return out
+
+    def get_into_device(self, which: int, dev_ptr: int) -> None:
+        self.lib.check(self.lib.lib.tdcgpu_dist_get(self._h, which, C.c_void_p(dev_ptr), 1))
+
+    def verify_full(self, threshold: int, zl: int, device: int, dist=None) -> dict:
+        """Collective.  EVERY slot and EVERY parse position is checked on the device (tdcgpu_check_index /
+        tdcgpu_check_factors, csrc/check.cu): the SA / LCP / ISA shards are gathered into full arrays on every rank
+        (torch.distributed all_gather, plumbing), then each rank checks its own slot range and its own position range
+        against them.  Returns the violation counters of this rank plus `ok` (all ranks, all zero)."""
+        import torch
+
+        from ._abi import Context
+
+        dev = torch.device("cuda", device)
+        world = dist.get_world_size() if dist is not None else 1
+        info, n = self.shard_info(), self.n
+
+        # all ranks take the same decision: the three gathered arrays (12 n bytes) must fit next to the shards
+        free = torch.tensor([torch.cuda.mem_get_info(dev)[0]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(free, op=dist.ReduceOp.MIN)
+        if int(free.item()) < 12 * n + (2 << 30):
+            return {"ok": None, "skipped": f"full verification needs {12 * n >> 30} GiB for the gathered arrays, {int(free.item()) >> 30} GiB free"}
+
+        def gather(which, cnt):
+            cnts = torch.zeros(world, dtype=torch.int64, device=dev)
+            cnts[self.rank] = cnt
+            if world > 1:
+                dist.all_reduce(cnts)
+            cnts = [int(x) for x in cnts.tolist()]
+            full = torch.empty(sum(cnts), dtype=torch.int32, device=dev)
+            off = 0
+            for r in range(world):  # every shard goes straight into its place: the owner writes it, then broadcasts the slice
+                part = full[off:off + cnts[r]]
+                if r == self.rank and cnt:
+                    self.get_into_device(which, part.data_ptr())
+                if world > 1 and cnts[r]:
+                    dist.broadcast(part, src=r)
+                off += cnts[r]
+            return full
+
+        sa = gather(SA, info["slot_cnt"])
+        lcp = gather(LCP, info["slot_cnt"])
+        isa = gather(ISA, info["pos_cnt"])
+        torch.cuda.synchronize()  # the checkers run on their own stream
+        assert sa.numel() == n and lcp.numel() == n and isa.numel() == n, "shards do not tile the arrays"
+        L = self.lib.lib
+        t_ptr = L.tdcgpu_dist_text_device_ptr(self._h)
+        f_ptr = L.tdcgpu_dist_factors_device_ptr(self._h) or 0
+        # a factor that starts in an earlier rank's range may cover the first positions of mine
+        ends = torch.zeros(world, dtype=torch.int64, device=dev)
+        if zl:
+            fl = torch.empty(3 * zl, dtype=torch.int32, device=dev)
+            self.lib.check(L.tdcgpu_dist_get_factors(self._h, C.c_void_p(fl.data_ptr()), zl, 1))
+            last = [int(x) & 0xFFFFFFFF for x in fl[-3:].tolist()]
+            ends[self.rank] = last[0] + last[2]
+            del fl
+        if world > 1:
+            dist.all_reduce(ends)
+        covered_to = max([0] + [int(x) for x in ends.tolist()[:self.rank]])
+        pos_lo = max(info["pos_lo"], min(covered_to, info["pos_lo"] + info["pos_cnt"]))
+        pos_cnt = info["pos_lo"] + info["pos_cnt"] - pos_lo
+        with Context(self.lib, device) as chk:  # only its stream and scalar scratch are used
+            res = chk.check_index_ptrs(t_ptr, n, sa.data_ptr(), isa.data_ptr(), lcp.data_ptr(), info["slot_lo"], info["slot_cnt"])
+            res.update(chk.check_factors_ptrs(t_ptr, n, sa.data_ptr(), isa.data_ptr(), lcp.data_ptr(), f_ptr, zl, threshold, pos_lo, pos_cnt))
+        bad = torch.tensor([sum(res.values())], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(bad)
+        res["ok"] = int(bad.item()) == 0
+        res["checked_slots"], res["checked_positions"] = info["slot_cnt"], pos_cnt
+        del sa, lcp, isa
+        torch.cuda.empty_cache()
+        return res
 
     def max_lcp(self) -> int:
         v = C.c_uint32()

@@ -5,7 +5,7 @@
 #   build/tdc_gpu_only   GPU text index as the default ("only")       — same -a strings as the reference
 #   build/tdc_block_ref / build/tdc_block_gpu   block mode driver (tdc_block.cpp) over the reference / GPU-only registry
 # The reference sources are compiled where they lie under $REF (nothing is copied); the two missing third-party headers
-# come from oracle/ref_build/shim.  Needs $REF, so it only runs in the build container; the binaries travel in build/.
+# come from tudocomp_b200/plugin/shim.  Needs $REF, so it only runs in the build container; the binaries travel in build/.
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/../.." && pwd)"
 REF="${REF:-/root/reference}"
@@ -13,7 +13,7 @@ OUT="$ROOT/build/tdc"
 JOBS="${JOBS:-8}"
 [ -d "$REF/include/tudocomp" ] || { echo "build_tdc.sh: $REF absent, keeping prebuilt binaries"; exit 0; }
 [ -f "$ROOT/tudocomp_b200/libtdcgpu.so" ] || make -s -C "$ROOT/tudocomp_b200/csrc"
-CXXFLAGS="-std=gnu++14 -O2 -DNDEBUG -w -I$ROOT/oracle/ref_build/shim -I$ROOT/tudocomp_b200/plugin/include -I$ROOT/include -I$REF/include"
+CXXFLAGS="-std=gnu++14 -O2 -DNDEBUG -w -I$ROOT/tudocomp_b200/plugin/shim -I$ROOT/tudocomp_b200/plugin/include -I$ROOT/include -I$REF/include"
 for mode in none mixed only; do
   case $mode in none) bin=tdc_ref;; mixed) bin=tdc_gpu;; only) bin=tdc_gpu_only;; esac
   gen="$OUT/gen_$mode"; rm -rf "$gen"; mkdir -p "$gen/tudocomp"
@@ -48,3 +48,9 @@ for mode in none mixed only; do
     echo "built build/$bbin"
   fi
 done
+# end-to-end harness over the plugin classes (tdc_plugin_bench.cpp): single translation unit, no registry needed
+gen="$OUT/gen_only"
+g++ $CXXFLAGS -I"$gen" "$ROOT/tudocomp_b200/plugin/tdc_plugin_bench.cpp" "$REF/src/tudocomp_stat/StatPhase.cpp" -o "$ROOT/build/tdc_plugin_bench" \
+  -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+echo "built build/tdc_plugin_bench"
+

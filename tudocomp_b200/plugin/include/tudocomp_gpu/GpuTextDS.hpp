@@ -54,14 +54,14 @@ inline int device_from_env() {
     const char* e = std::getenv("TDCGPU_DEVICE");
     return e ? std::atoi(e) : 0;
 }
-// Opt-in (TDCGPU_CTX_CACHE=1, off by default): keep one device context alive between compress() calls of a process instead
-// of creating and destroying one per text — the arrays and the scratch arena (~57 n bytes) are then allocated once for
-// the largest text seen.  Meant for `tdc_block -c` (many blocks per worker) and for chains of GPU stages; tdc itself is
-// single-threaded, so one cached context is enough.  The cached context is deliberately not destroyed at
-// process exit (static destructors may run after the CUDA runtime has shut down).
+// One device context is kept alive between compress() calls of a process instead of creating and destroying one per text
+// (TDCGPU_CTX_CACHE=0 switches this off): the arrays, the scratch arena (~57 n bytes) and the pinned staging buffers are
+// then allocated once for the largest text seen — per-call cudaMalloc/cudaFree of that much memory costs more than the
+// kernels for mid-size texts.  tdc itself is single-threaded, so one cached context is enough.  The cached
+// context is deliberately not destroyed at process exit (static destructors may run after the CUDA runtime has shut down).
 inline bool ctx_cache_enabled() {
     const char* e = std::getenv("TDCGPU_CTX_CACHE");
-    return e && *e && *e != '0';
+    return !(e && *e == '0');
 }
 inline tdcgpu_ctx*& cached_ctx() {
     static tdcgpu_ctx* c = nullptr;

@@ -1,0 +1,92 @@
+// End-to-end harness over the C++ plugin: the SAME classes the `tdc` driver instantiates from the generated registry
+// (LZSSLCPCompressor<coder_t, GpuTextDS>, tudocomp_gpu/GpuTextDS.hpp) driven K times in one process on an in-memory
+// Input / Output, as a long-running service or `tdc_block` worker would.  bench.py reports its numbers as `plugin_e2e`.
+//
+//   tdc_plugin_bench FILE bit|huff THRESHOLD STEPS 1|0 [ARCHIVE_OUT]
+//
+// The file is read once (untimed); the driver's own input preparation — {0}-escaping + sentinel through
+// Input(in, InputRestrictions({0}, true)), src/tudocomp_driver/tudocomp_driver.cpp:268-270 — is done once (untimed) so
+// that the timed region is exactly Compressor::compress(Input&, Output&): pageable text in, archive bytes out.
+// Last argument 0 runs the reference's CPU TextDS<> instead (same binary): the byte-identity checker and CPU baseline.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include <tudocomp/CreateAlgorithm.hpp>
+#include <tudocomp/coders/BitCoder.hpp>
+#include <tudocomp/coders/HuffmanCoder.hpp>
+#include <tudocomp/compressors/LZSSLCPCompressor.hpp>
+#include <tudocomp/io.hpp>
+#include <tudocomp_gpu/GpuTextDS.hpp>
+#include <tudocomp_stat/StatPhase.hpp>
+
+using namespace tdc;
+
+template <class C>
+static std::vector<uint8_t> run(View text, const std::string& opts, double* ms) {
+    std::vector<uint8_t> out;
+    {
+        Input in(text);
+        Output o = Output::from_memory(out);
+        auto c = create_algo<C>(opts);
+        StatPhase root("root");
+        auto t0 = std::chrono::steady_clock::now();
+        c.compress(in, o);
+        auto t1 = std::chrono::steady_clock::now();
+        *ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    }
+    return out;
+}
+
+static uint64_t fnv1a(const std::vector<uint8_t>& v) {
+    uint64_t h = 1469598103934665603ull;
+    for (uint8_t b : v) { h ^= b; h *= 1099511628211ull; }
+    return h;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 6) { std::fprintf(stderr, "usage: %s FILE bit|huff THRESHOLD STEPS 1|0 [ARCHIVE_OUT]\n", argv[0]); return 2; }
+    const std::string path = argv[1], coder = argv[2], opts = std::string("threshold=") + argv[3];
+    const int steps = std::atoi(argv[4]);
+    const bool gpu = std::atoi(argv[5]) != 0;
+    try {
+        std::ifstream f(path, std::ios::binary | std::ios::ate);
+        if (!f) throw std::runtime_error("cannot open " + path);
+        std::vector<uint8_t> raw(size_t(f.tellg()));
+        f.seekg(0);
+        f.read(reinterpret_cast<char*>(raw.data()), std::streamsize(raw.size()));
+        Input plain{View(raw.data(), raw.size())};
+        Input restricted(plain, io::InputRestrictions({0}, true));
+        auto holder = restricted.as_view();  // owns the escaped copy (io/InputView.hpp); must outlive `text`
+        View text = holder;                  // escaped + sentinel: what uses_textds compressors receive
+        std::vector<uint8_t> arc;
+        std::vector<double> times;
+        for (int s = 0; s < steps + 1; s++) {  // the first run is the warm-up (context creation, first-touch allocations)
+            double ms = 0;
+            if (gpu && coder == "huff") arc = run<LZSSLCPCompressor<HuffmanCoder, GpuTextDS>>(text, opts, &ms);
+            else if (gpu) arc = run<LZSSLCPCompressor<BitCoder, GpuTextDS>>(text, opts, &ms);
+            else if (coder == "huff") arc = run<LZSSLCPCompressor<HuffmanCoder>>(text, opts, &ms);
+            else arc = run<LZSSLCPCompressor<BitCoder>>(text, opts, &ms);
+            times.push_back(ms);
+            if (!gpu) break;  // the CPU reference is timed once
+        }
+        double sum = 0;
+        for (size_t i = times.size() > 1 ? 1 : 0; i < times.size(); i++) sum += times[i];
+        const double mean = sum / double(times.size() > 1 ? times.size() - 1 : 1);
+        if (argc > 6) {
+            std::ofstream o(argv[6], std::ios::binary);
+            o.write(reinterpret_cast<const char*>(arc.data()), std::streamsize(arc.size()));
+        }
+        std::printf("{\"what\": \"LZSSLCPCompressor<%s, %s>::compress(Input&, Output&), in-memory pageable buffers, %d timed runs after 1 warm-up\", "
+                    "\"text_bytes\": %zu, \"archive_bytes\": %zu, \"archive_fnv1a\": \"%016llx\", \"first_run_ms\": %.3f, \"ms_per_step\": %.3f}\n",
+                    coder == "huff" ? "HuffmanCoder" : "BitCoder", gpu ? "GpuTextDS" : "TextDS<>", int(times.size() > 1 ? times.size() - 1 : 1),
+                    size_t(text.size()), arc.size(), (unsigned long long)fnv1a(arc), times[0], mean);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+    return 0;
+}
