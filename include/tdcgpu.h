@@ -198,7 +198,8 @@ int tdcgpu_check_index(tdcgpu_ctx* ctx, const uint8_t* d_text, uint64_t n, const
  * [pos_lo, pos_lo + pos_cnt) they cover.  out[0] = malformed records (len < threshold, src >= pos, past the sentinel);
  * out[1] = order / overlap violations; out[2] = factor starts where the reference's PSV/NSV scan decides another
  * (src, len); out[3] = positions outside every factor where that scan finds a factor; out[4] = positions whose scan
- * exceeded 2^22 steps (not decided). */
+ * exceeded 2^16 steps at a text position >= 2^20 (not decided; earlier positions are decided by comparing with all earlier
+ * suffixes directly). */
 int tdcgpu_check_factors(tdcgpu_ctx* ctx, const uint8_t* d_text, uint64_t n, const uint32_t* d_sa, const uint32_t* d_isa,
                          const uint32_t* d_lcp, const tdcgpu_factor* d_factors, uint64_t z, uint32_t threshold,
                          uint64_t pos_lo, uint64_t pos_cnt, uint64_t out[5]);

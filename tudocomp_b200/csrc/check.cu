@@ -19,7 +19,12 @@
 
 namespace tdc {
 
-static const u32 CHECK_SCAN_CAP = 1u << 22;  // steps of one naive PSV / NSV scan before it is counted as "not decided"
+#ifdef TDC_CUSIM
+static const u32 CHECK_SCAN_CAP = 64;         // tiny, so that the CPU tests exercise the early-position route
+#else
+static const u32 CHECK_SCAN_CAP = 1u << 16;   // steps of one naive PSV / NSV scan before the position takes the other route
+#endif
+static const u64 CHECK_EARLY_POS = u64(1) << 20;  // ... which is affordable for text positions below this bound
 
 static __global__ void __launch_bounds__(256)
 check_index_kernel(const uint8_t* __restrict__ text, u64 n, const u32* __restrict__ sa, const u32* __restrict__ isa,
@@ -91,6 +96,36 @@ static __device__ __forceinline__ u32 naive_decision(const u32* __restrict__ sa,
     return u32(mx);
 }
 
+// Longest common prefix of two suffixes by direct comparison (8 bytes per step; the unique 0 at n-1 ends it).
+static __device__ __forceinline__ u64 direct_lce(const uint8_t* __restrict__ text, u64 a, u64 b) {
+    u64 l = 0;
+    while (true) {
+        const u64 x = load_text8(text, a + l) ^ load_text8(text, b + l);
+        if (x) return l + (u64(__ffsll((long long)x) - 1) >> 3);
+        l += 8;
+    }
+}
+
+// The same decision for an EARLY text position i (few suffixes start before it, so the naive scans run for ~n/i steps):
+// PSV / NSV of rank ISA[i] among the suffixes 0..i-1 by looking at all of them, the two lengths by direct comparison
+// (equal to the LCP range minima the reference takes, given the checked LCP array).  O(i) instead of O(n/i).
+static __device__ u32 early_decision(const uint8_t* __restrict__ text, const u32* __restrict__ isa, u64 i, u32* src) {
+    const u32 cur = isa[i];
+    long long best_up = -1, best_dn = -1;  // text positions of the nearest smaller / larger rank among j < i
+    u32 r_up = 0, r_dn = 0xffffffffu;
+    for (u64 j = 0; j < i; j++) {
+        const u32 r = isa[j];
+        if (r < cur) { if (best_up < 0 || r > r_up) { r_up = r; best_up = (long long)j; } }
+        else { if (best_dn < 0 || r < r_dn) { r_dn = r; best_dn = (long long)j; } }
+    }
+    const u64 l_up = best_up >= 0 ? direct_lce(text, u64(best_up), i) : 0;
+    const u64 l_dn = best_dn >= 0 ? direct_lce(text, u64(best_dn), i) : 0;
+    const u64 mx = max(l_up, l_dn);
+    if (mx == 0) { *src = 0; return 0; }
+    *src = u32(mx == l_up ? best_up : best_dn);  // PSV wins ties (LZSSLCPCompressor.hpp:101)
+    return u32(mx);
+}
+
 // one thread per factor: copy check, order / overlap with the predecessor, and the reference's decision at its start
 static __global__ void __launch_bounds__(128)
 check_factor_starts_kernel(const uint8_t* __restrict__ text, u64 n, const u32* __restrict__ sa, const u32* __restrict__ isa,
@@ -105,15 +140,18 @@ check_factor_starts_kernel(const uint8_t* __restrict__ text, u64 n, const u32* _
     }
     u32 src = 0;
     bool undecided = false;
-    const u32 len = naive_decision(sa, isa, lcp, n, me.pos, 0u, &src, &undecided);
-    if (undecided) { atomicAdd(&bad[4], 1ull); return; }
+    u32 len = naive_decision(sa, isa, lcp, n, me.pos, 0u, &src, &undecided);
+    if (undecided) {
+        if (me.pos >= CHECK_EARLY_POS) { atomicAdd(&bad[4], 1ull); return; }
+        len = early_decision(text, isa, me.pos, &src);
+    }
     if (len != me.len || src != me.src) atomicAdd(&bad[2], 1ull);
 }
 
 // one thread per text position of [pos_lo, pos_lo + pos_cnt): positions outside every factor (and before n-1) must not
 // admit a factor.  The covering factor is found by binary search over the position-sorted list.
 static __global__ void __launch_bounds__(256)
-check_literals_kernel(u64 n, const u32* __restrict__ sa, const u32* __restrict__ isa, const u32* __restrict__ lcp,
+check_literals_kernel(const uint8_t* __restrict__ text, u64 n, const u32* __restrict__ sa, const u32* __restrict__ isa, const u32* __restrict__ lcp,
                       const Factor* __restrict__ f, u64 z, u32 threshold, u64 pos_lo, u64 pos_cnt, ull* __restrict__ bad) {
     const u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (t >= pos_cnt) return;
@@ -130,8 +168,11 @@ check_literals_kernel(u64 n, const u32* __restrict__ sa, const u32* __restrict__
     }
     u32 src = 0;
     bool undecided = false;
-    const u32 len = naive_decision(sa, isa, lcp, n, i, threshold, &src, &undecided);
-    if (undecided) { atomicAdd(&bad[4], 1ull); return; }
+    u32 len = naive_decision(sa, isa, lcp, n, i, threshold, &src, &undecided);
+    if (undecided) {
+        if (i >= CHECK_EARLY_POS) { atomicAdd(&bad[4], 1ull); return; }
+        len = early_decision(text, isa, i, &src);
+    }
     if (len >= threshold) atomicAdd(&bad[3], 1ull);
 }
 
@@ -172,7 +213,7 @@ int tdcgpu_check_factors(tdcgpu_ctx* ctx, const uint8_t* d_text, uint64_t n, con
     TDC_CUDA(cudaMemsetAsync(d_bad, 0, 8 * sizeof(ull), c.stream));
     const Factor* f = reinterpret_cast<const Factor*>(d_factors);
     if (z) TDC_LAUNCH(check_factor_starts_kernel, u32(div_up(z, 128)), 128, 0, c.stream, d_text, n, d_sa, d_isa, d_lcp, f, z, threshold, d_bad);
-    if (pos_cnt) TDC_LAUNCH(check_literals_kernel, u32(div_up(pos_cnt, 256)), 256, 0, c.stream, n, d_sa, d_isa, d_lcp, f, z, threshold, pos_lo, pos_cnt, d_bad);
+    if (pos_cnt) TDC_LAUNCH(check_literals_kernel, u32(div_up(pos_cnt, 256)), 256, 0, c.stream, d_text, n, d_sa, d_isa, d_lcp, f, z, threshold, pos_lo, pos_cnt, d_bad);
     TDC_KCHECK();
     ull h[8];
     TDC_CUDA(cudaMemcpyAsync(h, d_bad, sizeof(h), cudaMemcpyDeviceToHost, c.stream));

@@ -1,6 +1,9 @@
 // C ABI of libtdcgpu (see include/tdcgpu.h for the contract and the reference interfaces each entry replaces).
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <new>
 
 #include "../../include/tdcgpu.h"
@@ -27,7 +30,7 @@ struct PendingLaunch {
     int entry;
     cudaEvent_t a, b;
 };
-static u64 g_launches = 0;
+static std::atomic<u64> g_launches{0};
 static bool g_prof_on = false;
 static std::vector<ProfEntry> g_prof;
 static std::vector<PendingLaunch> g_pending;
@@ -98,6 +101,20 @@ PhaseTimer::~PhaseTimer() {
     cudaEventDestroy(a);
     cudaEventDestroy(b);
 }
+
+// One context computes at a time per device.  Several contexts on one GPU (a host thread each) are how a stream of
+// independent texts is double-buffered: while one context runs its kernels, another one copies its next text in or its
+// last result out.  Letting their kernels run concurrently only makes every kernel slower (each of them fills the GPU, and
+// the sort and scatter kernels rely on in-order CTA dispatch for L2 locality), so the compute calls take this lock and the
+// copy calls do not.  TDCGPU_NO_COMPUTE_LOCK=1 removes it (A/B measurements).
+static std::mutex g_compute_mu[64];
+struct ComputeLock {
+    std::unique_lock<std::mutex> lk;
+    explicit ComputeLock(int device) {
+        static const bool off = [] { const char* e = std::getenv("TDCGPU_NO_COMPUTE_LOCK"); return e && *e && *e != '0'; }();
+        if (!off) lk = std::unique_lock<std::mutex>(g_compute_mu[device & 63]);
+    }
+};
 
 static const u64 TEXT_PAD = 1024;  // zero bytes readable past the text (8-byte LCE loads, warp-wide look-ahead)
 
@@ -312,6 +329,7 @@ int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_dev
 
 int tdcgpu_textds_build(tdcgpu_ctx* ctx, uint32_t flags) {
     API_GUARD(ctx);
+    ComputeLock lock(c.device);
     c.phases.clear();
     return do_build(c, flags);
 }
@@ -336,6 +354,7 @@ int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, ui
     if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
     if (elem != 4 || width < 1 || width > 32) { set_error("get_packed: 32-bit arrays only, 1 <= width <= 32"); return TDCGPU_ERR_ARG; }
     const u64 nwords = div_up(c.n * u64(width), 64);
+    ComputeLock lock(c.device);
     if (cap_words < nwords) { set_error("get_packed: buffer too small: %llu < %llu words", (unsigned long long)cap_words, (unsigned long long)nwords); return TDCGPU_ERR_ARG; }
     c.arena.reset();  // scratch: whatever the previous phase kept there (e.g. the encoder's masks) is stale from here on
     u64* packed = c.arena.take<u64>(nwords);
@@ -365,6 +384,7 @@ int tdcgpu_textds_max_lcp(tdcgpu_ctx* ctx, uint32_t* max_lcp) {
 
 int tdcgpu_lzss_lcp_factorize(tdcgpu_ctx* ctx, uint32_t threshold, uint64_t* count, uint32_t* min_len, uint32_t* max_len) {
     API_GUARD(ctx);
+    ComputeLock lock(c.device);
     c.phases.clear();
     if (threshold < 1) { set_error("lzss_lcp: threshold must be >= 1"); return TDCGPU_ERR_ARG; }
     TDC_TRY(do_build(c, DS_SA | DS_ISA | DS_LCP));
@@ -392,6 +412,7 @@ int tdcgpu_lzss_lcp_get_factors(tdcgpu_ctx* ctx, tdcgpu_factor* dst, uint64_t ca
 
 int tdcgpu_lzss_literal_histogram(tdcgpu_ctx* ctx, uint64_t hist[256], uint64_t* fdist_max) {
     API_GUARD(ctx);
+    ComputeLock lock(c.device);
     c.phases.clear();
     {
         PhaseTimer t(c, "Encode: literal histogram");
@@ -406,6 +427,7 @@ int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t
                        uint8_t lead_byte, uint64_t* nbits) {
     API_GUARD(ctx);
     if (!codes || !lens) { set_error("null code table"); return TDCGPU_ERR_ARG; }
+    ComputeLock lock(c.device);
     c.phases.clear();
     {
         PhaseTimer t(c, "Encode: bit stream");
@@ -627,7 +649,7 @@ int tdcgpu_event_elapsed_ms(tdcgpu_ctx* ctx, int slot_a, int slot_b, float* ms) 
     return 0;
 }
 
-uint64_t tdcgpu_launch_count(void) { return g_launches; }
+uint64_t tdcgpu_launch_count(void) { return g_launches.load(); }
 
 void tdcgpu_profile_enable(int on) { g_prof_on = on != 0; }
 
