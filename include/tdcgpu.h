@@ -122,6 +122,17 @@ int tdcgpu_lzss_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t
  * fewer than 3 bits are free).  *nbytes = bytes written (ceil(nbits / 8), + at most 1 when finalized). */
 int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device);
 
+/* The same stream in pieces: bytes [offset, offset + cap) to a HOST buffer, so that a large archive is drained through one
+ * small (ideally pinned, tdcgpu_pinned_alloc) buffer straight into the caller's output stream instead of through an
+ * archive-sized intermediate vector.  *total = length of the whole (finalized) stream, *written = bytes stored by this call
+ * (0 once offset >= total). */
+int tdcgpu_lzss_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst, uint64_t cap, int finalize, uint64_t* total,
+                                 uint64_t* written);
+
+/* Page-locked host memory for caller-side staging buffers (cudaMallocHost / cudaFreeHost); NULL on failure. */
+void* tdcgpu_pinned_alloc(uint64_t bytes);
+void tdcgpu_pinned_free(void* p);
+
 /* ---- byte-stream stages behind the BWT in `bwt:mtf:rle:encode(huff)` (BASELINE config 3) -------------------------
  * Stateless with respect to the text index: they only use the context's stream and a scratch buffer of their own.
  * on_device != 0: in/out are device pointers on the context's device; otherwise host pointers.
@@ -146,6 +157,8 @@ int tdcgpu_literal_encode_begin(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, 
 int tdcgpu_literal_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint8_t lens[256], uint32_t lead_bits, uint8_t lead_byte,
                           uint64_t* nbits);
 int tdcgpu_literal_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device);
+int tdcgpu_literal_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst, uint64_t cap, int finalize, uint64_t* total,
+                                    uint64_t* written);
 
 /* One-shot host-buffer convenience used by the C++ provider shims: text in, arrays out (NULL = not wanted).
  * Same semantics as constructing TextDS<>(env, view, flags) and reading the providers. */

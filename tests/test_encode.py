@@ -107,6 +107,9 @@ def _device_vs_oracle(lib, oracle, name, t, thr, coder_of, check_archive=None, d
             assert c.encode(codes, lens, lb, lbyte) == nbits, (name, thr, coder)
             got = c.encoded(nbits)
             assert np.array_equal(got, body), (name, thr, coder)
+            for chunk in (7, 4096):  # the same stream drained in pieces, tail bytes split across pieces included
+                if got.size <= 40000 or chunk > 7:
+                    assert np.array_equal(c.encoded_chunks(chunk), body), (name, thr, coder, chunk)
             raw = c.encoded(nbits, finalize=False)
             assert raw.size == (nbits + 7) // 8 and np.array_equal(raw[:nbits // 8], body[:nbits // 8])
             if check_archive:

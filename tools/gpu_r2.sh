@@ -22,6 +22,10 @@ for stage in "$@"; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
         python bench.py --steps 2 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
       echo "launches rc=$?" ;;
+    sortbench)  # A/B of radix-pass variants built by: nvcc ... -D<flag> tools/sortbench.cu -o build/sortbench_<name>
+      for b in build/sortbench_*; do echo "== $b"; timeout 120 $b 28 48; done 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
+    plugintests)
+      timeout 900 python -m pytest tests/test_plugin.py tests/test_encode.py tests/test_check.py tests/test_stream_stages.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_plugintests.txt ;;
     *) echo "unknown stage $stage" ;;
   esac
 done

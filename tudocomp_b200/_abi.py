@@ -21,6 +21,7 @@ EXPORTS = [
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
     "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
     "tdcgpu_mtf_encode", "tdcgpu_rle_encode", "tdcgpu_literal_encode_begin", "tdcgpu_literal_encode", "tdcgpu_literal_encode_get",
+    "tdcgpu_lzss_encode_get_chunk", "tdcgpu_literal_encode_get_chunk", "tdcgpu_pinned_alloc", "tdcgpu_pinned_free",
     "tdcgpu_check_index", "tdcgpu_check_factors", "tdcgpu_text_device_ptr", "tdcgpu_factors_device_ptr",
 ]
 
@@ -63,6 +64,12 @@ class TdcGpuLib:
         L.tdcgpu_lzss_encode_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.c_int]
         L.tdcgpu_textds_build_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64] + [C.c_void_p] * 5 + [C.POINTER(C.c_uint32)]
         L.tdcgpu_bwt_host.argtypes = [C.c_int, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.tdcgpu_lzss_encode_get_chunk.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.tdcgpu_literal_encode_get_chunk.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.tdcgpu_pinned_alloc.argtypes = [C.c_uint64]
+        L.tdcgpu_pinned_alloc.restype = C.c_void_p
+        L.tdcgpu_pinned_free.argtypes = [C.c_void_p]
+        L.tdcgpu_pinned_free.restype = None
         L.tdcgpu_check_index.argtypes = [C.c_void_p] + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         L.tdcgpu_check_factors.argtypes = [C.c_void_p] + [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                          C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p]
@@ -214,6 +221,19 @@ class Context:
         self.lib.check(self.lib.lib.tdcgpu_lzss_encode_get(self._h, _host_ptr(out), out.size, 1 if finalize else 0,
                                                            C.byref(nb), 0))
         return out[:int(nb.value)]
+
+    def encoded_chunks(self, chunk: int = 1 << 20, finalize: bool = True) -> np.ndarray:
+        """The stream drained piece by piece (tdcgpu_lzss_encode_get_chunk), concatenated."""
+        buf = np.empty(chunk, np.uint8)
+        parts, off = [], 0
+        while True:
+            total, wr = C.c_uint64(), C.c_uint64()
+            self.lib.check(self.lib.lib.tdcgpu_lzss_encode_get_chunk(self._h, off, _host_ptr(buf), chunk, 1 if finalize else 0, C.byref(total), C.byref(wr)))
+            if wr.value == 0:
+                break
+            parts.append(buf[:wr.value].copy())
+            off += wr.value
+        return np.concatenate(parts) if parts else np.zeros(0, np.uint8)
 
     def encoded_into(self, host_ptr: int, cap: int, finalize: bool = True) -> int:
         nb = C.c_uint64()

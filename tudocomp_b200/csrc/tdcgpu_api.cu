@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <new>
@@ -463,6 +464,50 @@ static int copy_bitstream_out(Ctx& c, const uint8_t* d_stream, u64 nbits, uint8_
     return 0;
 }
 
+// Bytes [offset, offset + cap) of the (optionally finalized) stream to a HOST buffer: lets a caller drain a large archive
+// through one small pinned buffer straight into its output stream.  *total = length of the whole stream, *written = bytes
+// stored at dst by this call.
+static int copy_bitstream_chunk(Ctx& c, const uint8_t* d_stream, u64 nbits, u64 offset, uint8_t* dst, u64 cap, int finalize, u64* total_out,
+                                u64* written) {
+    const u64 whole = nbits / 8;
+    const u32 used = u32(nbits % 8);
+    const u64 body = whole + (used ? 1 : 0);
+    const u64 total = finalize ? whole + (used <= 5 ? 1 : 2) : body;
+    if (total_out) *total_out = total;
+    if (written) *written = 0;
+    if (offset >= total || cap == 0) return 0;
+    if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
+    const u64 end = std::min(total, offset + cap);
+    if (offset < body) TDC_TRY(host_copy(c, dst, d_stream + offset, std::min(end, body) - offset, false));
+    if (finalize && end > whole) {  // BitOStream::~BitOStream's tail (io/BitOStream.hpp:53-64), see copy_bitstream_out
+        uint8_t tail[2] = {0, 0};
+        if (used) {
+            TDC_CUDA(cudaMemcpyAsync(&tail[0], d_stream + whole, 1, cudaMemcpyDeviceToHost, c.stream));
+            TDC_CUDA(cudaStreamSynchronize(c.stream));
+        }
+        if (used <= 5) tail[0] |= uint8_t(used); else tail[1] = uint8_t(used);
+        for (u64 p = std::max(offset, whole); p < end; p++) dst[p - offset] = tail[p - whole];
+    }
+    if (written) *written = end - offset;
+    return 0;
+}
+
+int tdcgpu_lzss_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst, uint64_t cap, int finalize, uint64_t* total,
+                                 uint64_t* written) {
+    API_GUARD(ctx);
+    if (!c.enc.encoded || c.enc.gen != c.arena.gen) { set_error("no encoded stream (call tdcgpu_lzss_encode first)"); return TDCGPU_ERR_STATE; }
+    return copy_bitstream_chunk(c, c.enc.out, c.enc.nbits, offset, dst, cap, finalize, total, written);
+}
+
+void* tdcgpu_pinned_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_error("pinned allocation of %llu bytes failed", (unsigned long long)bytes); return nullptr; }
+    return p;
+}
+void tdcgpu_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
     API_GUARD(ctx);
     if (!c.enc.encoded || c.enc.gen != c.arena.gen) { set_error("no encoded stream (call tdcgpu_lzss_encode first)"); return TDCGPU_ERR_STATE; }
@@ -559,6 +604,13 @@ int tdcgpu_literal_encode(tdcgpu_ctx* ctx, const uint64_t codes[256], const uint
     c.lit.encoded = true;
     if (nbits) *nbits = c.lit.nbits;
     return 0;
+}
+
+int tdcgpu_literal_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst, uint64_t cap, int finalize, uint64_t* total,
+                                    uint64_t* written) {
+    API_GUARD(ctx);
+    if (!c.lit.encoded) { set_error("no encoded stream (call tdcgpu_literal_encode first)"); return TDCGPU_ERR_STATE; }
+    return copy_bitstream_chunk(c, c.lit.d_out, c.lit.nbits, offset, dst, cap, finalize, total, written);
 }
 
 int tdcgpu_literal_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {

@@ -157,6 +157,19 @@ inline uint64_t strip_bitstream_tail(std::vector<uint8_t>& bytes) {
     return bits;
 }
 
+/// Page-locked staging buffer of the C ABI (falls back to pageable memory, which the ABI stages itself).
+struct PinnedBuffer {
+    uint8_t* data;
+    size_t size;
+    bool pinned;
+    explicit PinnedBuffer(size_t n) : data(static_cast<uint8_t*>(tdcgpu_pinned_alloc(n))), size(n), pinned(data != nullptr) {
+        if (!data) data = new uint8_t[n];
+    }
+    ~PinnedBuffer() { if (pinned) tdcgpu_pinned_free(data); else delete[] data; }
+    PinnedBuffer(const PinnedBuffer&) = delete;
+    PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+};
+
 inline bool host_encode_forced() {
     const char* e = std::getenv("TDCGPU_HOST_ENCODE");  // A/B switch: run the reference's encode_text on the host
     return e && *e && *e != '0';
@@ -359,11 +372,18 @@ public:
             uint64_t nbits = 0, nbytes = 0;
             gpu_detail::check(tdcgpu_lzss_encode(text.device(), table.codes, table.lens, lead_bits, lead_byte, &nbits), "encode");
             gpu_detail::log_phases(text.device());
-            std::vector<uint8_t> body(nbits / 8 + 2);
-            gpu_detail::check(tdcgpu_lzss_encode_get(text.device(), body.data(), body.size(), 1, &nbytes, 0), "encode");
+            // 3. drain the stream through one pinned buffer straight into the output (no archive-sized vector in between)
             auto os = output.as_stream();
             os.write(reinterpret_cast<const char*>(head.data()), std::streamsize(head_bits / 8));
-            os.write(reinterpret_cast<const char*>(body.data()), std::streamsize(nbytes));
+            gpu_detail::PinnedBuffer buf(size_t(16) << 20);
+            for (uint64_t off = 0;;) {
+                uint64_t total = 0, wr = 0;
+                gpu_detail::check(tdcgpu_lzss_encode_get_chunk(text.device(), off, buf.data, buf.size, 1, &total, &wr), "encode");
+                if (wr == 0) break;
+                os.write(reinterpret_cast<const char*>(buf.data), std::streamsize(wr));
+                off += wr;
+                nbytes = total;
+            }
             StatPhase::log("archive_bytes", size_t(head_bits / 8 + nbytes));
         });
     }

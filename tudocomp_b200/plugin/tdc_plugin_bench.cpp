@@ -25,19 +25,28 @@
 
 using namespace tdc;
 
+static std::string g_phases;  // StatPhase JSON of the last run (per-phase wall times of compress())
+static std::string g_out_path;
+
+// The archive goes to a FILE like in the driver (Output::from_path, src/tudocomp_driver/tudocomp_driver.cpp:232-247): the
+// reference's in-memory Output appends byte by byte (1.4 s for a 350 MB archive), which no tdc run ever pays.
 template <class C>
 static std::vector<uint8_t> run(View text, const std::string& opts, double* ms) {
-    std::vector<uint8_t> out;
     {
         Input in(text);
-        Output o = Output::from_memory(out);
+        Output o = Output::from_path(io::Path{g_out_path}, true);
         auto c = create_algo<C>(opts);
         StatPhase root("root");
         auto t0 = std::chrono::steady_clock::now();
         c.compress(in, o);
         auto t1 = std::chrono::steady_clock::now();
         *ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        g_phases = root.to_json().str();
     }
+    std::ifstream f(g_out_path, std::ios::binary | std::ios::ate);
+    std::vector<uint8_t> out(size_t(f.tellg()));
+    f.seekg(0);
+    f.read(reinterpret_cast<char*>(out.data()), std::streamsize(out.size()));
     return out;
 }
 
@@ -52,6 +61,7 @@ int main(int argc, char** argv) {
     const std::string path = argv[1], coder = argv[2], opts = std::string("threshold=") + argv[3];
     const int steps = std::atoi(argv[4]);
     const bool gpu = std::atoi(argv[5]) != 0;
+    g_out_path = argc > 6 ? std::string(argv[6]) : path + ".plugin_out";
     try {
         std::ifstream f(path, std::ios::binary | std::ios::ate);
         if (!f) throw std::runtime_error("cannot open " + path);
@@ -76,11 +86,38 @@ int main(int argc, char** argv) {
         double sum = 0;
         for (size_t i = times.size() > 1 ? 1 : 0; i < times.size(); i++) sum += times[i];
         const double mean = sum / double(times.size() > 1 ? times.size() - 1 : 1);
-        if (argc > 6) {
-            std::ofstream o(argv[6], std::ios::binary);
-            o.write(reinterpret_cast<const char*>(arc.data()), std::streamsize(arc.size()));
+        if (argc <= 6) std::remove(g_out_path.c_str());
+        std::string top;  // "title": ms of the first-level phases of the last run
+        {
+            // the JSON is {"title":..,"timeStart":..,"timeEnd":..,"sub":[{...},...]}: pull (title, timeEnd - timeStart) of depth 1
+            int depth = 0;
+            std::string title;
+            double ts = 0, te = 0;
+            for (size_t i = 0; i < g_phases.size(); i++) {
+                const char ch = g_phases[i];
+                if (ch == '{') depth++;
+                else if (ch == '}') {
+                    if (depth == 2 && !title.empty()) {
+                        char b[160];
+                        std::snprintf(b, sizeof b, "%s\"%s\": %.1f", top.empty() ? "" : ", ", title.c_str(), te - ts);
+                        top += b;
+                        title.clear();
+                    }
+                    depth--;
+                } else if (depth == 2 && ch == '"') {
+                    const size_t e = g_phases.find('"', i + 1);
+                    const std::string key = g_phases.substr(i + 1, e - i - 1);
+                    size_t v = g_phases.find(':', e) + 1;
+                    while (v < g_phases.size() && g_phases[v] == ' ') v++;
+                    if (key == "title") { const size_t e2 = g_phases.find('"', v + 1); title = g_phases.substr(v + 1, e2 - v - 1); i = e2; continue; }
+                    if (key == "timeStart") ts = std::atof(g_phases.c_str() + v);
+                    if (key == "timeEnd") te = std::atof(g_phases.c_str() + v);
+                    i = e;
+                }
+            }
         }
-        std::printf("{\"what\": \"LZSSLCPCompressor<%s, %s>::compress(Input&, Output&), in-memory pageable buffers, %d timed runs after 1 warm-up\", "
+        std::printf("{\"phases_ms_last_run\": {%s}, ", top.c_str());
+        std::printf("\"what\": \"LZSSLCPCompressor<%s, %s>::compress(Input&, Output&), pageable in-memory Input, file Output, %d timed runs after 1 warm-up\", "
                     "\"text_bytes\": %zu, \"archive_bytes\": %zu, \"archive_fnv1a\": \"%016llx\", \"first_run_ms\": %.3f, \"ms_per_step\": %.3f}\n",
                     coder == "huff" ? "HuffmanCoder" : "BitCoder", gpu ? "GpuTextDS" : "TextDS<>", int(times.size() > 1 ? times.size() - 1 : 1),
                     size_t(text.size()), arc.size(), (unsigned long long)fnv1a(arc), times[0], mean);
