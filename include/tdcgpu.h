@@ -180,6 +180,11 @@ float tdcgpu_phase_ms(tdcgpu_ctx* ctx, int i);
  * in the reference), [7] sum over rounds of active suffixes x known common prefix (the route's LCP-sum estimate). */
 int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[8]);
 
+/* Record layout of the initial sort of the last SA build: [0] 1 = packed 64-bit records (key bits | suffix index, 16 B per
+ * suffix and radix pass), 0 = (64-bit key, 32-bit suffix) pairs (24 B); [1] key bits sorted; [2] index bits inside a
+ * packed record; [3] whole symbols the key decides. */
+int tdcgpu_sa_layout(tdcgpu_ctx* ctx, uint64_t out[4]);
+
 /* Block until all work queued on the context's stream is done. */
 int tdcgpu_sync(tdcgpu_ctx* ctx);
 

@@ -23,7 +23,17 @@ for stage in "$@"; do
         python bench.py --steps 2 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
       echo "launches rc=$?" ;;
     sortbench)  # A/B of radix-pass variants built by: nvcc ... -D<flag> tools/sortbench.cu -o build/sortbench_<name>
-      for b in build/sortbench_*; do echo "== $b"; timeout 120 $b 28 48; done 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
+      { for b in build/sortbench_*; do echo "== $b"; timeout 120 $b 28 33 keys; done; timeout 120 build/sortbench_k16x4 28 48; } 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
+    benchmodes)  # the initial-sort layouts side by side (resident timing only)
+      for mode in wide packed; do
+        TDCGPU_SA_MODE=$mode timeout 600 python bench.py --steps 5 --warmup 2 --no-dist --no-pipeline --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_$mode.json 2> gpurun_out/${tag}_bench_$mode.err
+        echo "$mode rc=$?"; python - <<PY
+import json
+d=json.load(open("gpurun_out/${tag}_bench_$mode.json"))
+print("$mode", "ms/step", round(d["ms_per_step"],2), "verified", d["verified"], d["sa_stats"])
+print({k:(v["launches"],v["ms"]) for k,v in list(d["kernels"].items())[:14]})
+PY
+      done ;;
     plugintests)
       timeout 900 python -m pytest tests/test_plugin.py tests/test_encode.py tests/test_check.py tests/test_stream_stages.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_plugintests.txt ;;
     *) echo "unknown stage $stage" ;;

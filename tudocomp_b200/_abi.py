@@ -22,7 +22,7 @@ EXPORTS = [
     "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
     "tdcgpu_mtf_encode", "tdcgpu_rle_encode", "tdcgpu_literal_encode_begin", "tdcgpu_literal_encode", "tdcgpu_literal_encode_get",
     "tdcgpu_lzss_encode_get_chunk", "tdcgpu_literal_encode_get_chunk", "tdcgpu_pinned_alloc", "tdcgpu_pinned_free",
-    "tdcgpu_check_index", "tdcgpu_check_factors", "tdcgpu_text_device_ptr", "tdcgpu_factors_device_ptr",
+    "tdcgpu_sa_layout", "tdcgpu_check_index", "tdcgpu_check_factors", "tdcgpu_text_device_ptr", "tdcgpu_factors_device_ptr",
 ]
 
 FACTOR_DTYPE = np.dtype([("pos", "<u4"), ("src", "<u4"), ("len", "<u4")])
@@ -83,6 +83,7 @@ class TdcGpuLib:
         L.tdcgpu_phase_ms.argtypes = [C.c_void_p, C.c_int]
         L.tdcgpu_phase_ms.restype = C.c_float
         L.tdcgpu_sa_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+        L.tdcgpu_sa_layout.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
         L.tdcgpu_sync.argtypes = [C.c_void_p]
         L.tdcgpu_event_record.argtypes = [C.c_void_p, C.c_int]
         L.tdcgpu_event_elapsed_ms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]
@@ -308,7 +309,11 @@ class Context:
         buf = (C.c_uint64 * 8)()
         self.lib.check(self.lib.lib.tdcgpu_sa_stats(self._h, buf))
         keys = ["rounds", "active_sum", "radix_passes", "radix_elems", "alphabet", "symbols_per_key", "lcp_route", "prefix_work"]
-        return dict(zip(keys, [int(x) for x in buf]))
+        out = dict(zip(keys, [int(x) for x in buf]))
+        lay = (C.c_uint64 * 4)()
+        self.lib.check(self.lib.lib.tdcgpu_sa_layout(self._h, lay))
+        out.update(packed_records=int(lay[0]), key_bits=int(lay[1]), record_index_bits=int(lay[2]))
+        return out
 
     def sync(self) -> None:
         self.lib.check(self.lib.lib.tdcgpu_sync(self._h))

@@ -275,11 +275,11 @@ static int dist_rerank(DistCtx& d, const u64* keys, const u32* vals, const u32* 
     if (m == 0) return 0;
     const u32 ntiles = u32(div_up(m, RR_TILE));
     auto rerank_reduce = rerank_reduce_kernel<u64>;
-    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt);
+    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt, 0u);
     TDC_LAUNCH(rerank_scan_kernel, 1, 1024, 0, c.stream, agg_lasthead, agg_cnt, ntiles, c.d_scalars);
     auto rerank_apply = rerank_apply_kernel<u64, FIRST>;
     TDC_LAUNCH(rerank_apply, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, d.d_sa, rank_idx,
-               rank_val, pos_out, idx_out, gid_out, lcp_out, pp, u32(d.slot_lo));
+               rank_val, pos_out, idx_out, gid_out, lcp_out, pp, u32(d.slot_lo), u32(d.n));
     TDC_KCHECK();
     TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, c.stream));
     TDC_CUDA(cudaStreamSynchronize(c.stream));

@@ -250,7 +250,9 @@ lcp_fix_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u64
         if (unknown) {
             if (lane_id() == 0) prev = sa[j - 1];  // j >= 1: slot 0 is never unknown
             bool done;
-            l = lce_thread(text, own, prev, l0, l0 + LCPD_THREAD_LIMIT, &done);
+            // (keys without a length field: a suffix shorter than l0 shares its padded key, not l0 real symbols)
+            const u32 start = min(l0, min(u32(n - 1) - own, u32(n - 1) - prev));
+            l = lce_thread(text, own, prev, start, start + LCPD_THREAD_LIMIT, &done);
             if (!done) queue[atomicAdd(queue_len, 1u)] = u32(j);
             lcp[j] = l;
         }
@@ -261,6 +263,23 @@ lcp_fix_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u64
     if (threadIdx.x == 0) {
         for (int q = 0; q < 256 / 32; q++) mx = max(mx, s_max[q]);
         if (mx) atomicMax(max_lcp, mx);
+    }
+}
+
+// Packed initial keys without a length field (suffix_array.cu): the `span` suffixes that reach the sentinel inside their
+// key were padded with code 0, so the key-derived LCP of a slot next to one of them may count padding.  Recompute the
+// two slots around each of them by direct comparison (they are shorter than a key: a few bytes each).
+static __global__ void lcp_tail_fix_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, const u32* __restrict__ isa,
+                                           u64 n, u32 span, u32* __restrict__ lcp) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > span || u64(j) >= n) return;
+    const u64 p = isa[n - 1 - j];
+    for (u64 s = p; s <= p + 1 && s < n; s++) {
+        if (s == 0) continue;
+        const u64 a = sa[s - 1], b = sa[s];
+        u32 l = 0;
+        while (text[a + l] == text[b + l]) l++;  // two different suffixes: the unique 0 at n-1 ends the loop
+        lcp[s] = l;
     }
 }
 

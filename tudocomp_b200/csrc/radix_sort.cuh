@@ -51,6 +51,16 @@ struct SortWorkspace {
 template <class K> struct RsCfg;
 template <> struct RsCfg<u64> { static const int IPT = RS_IPT64_CFG; static const int MIN_CTAS = RS_MIN_CTAS_CFG; };
 template <> struct RsCfg<u32> { static const int IPT = 16; static const int MIN_CTAS = 4; };
+#ifndef RS_MIN_CTAS_KEYS_CFG
+#define RS_MIN_CTAS_KEYS_CFG 4
+#endif
+// KEYSONLY passes (packed records: the value lives in the low bits of the key) move 16 B per element instead of 24 and
+// need neither the value registers nor the value half of the staging buffer
+#ifndef RS_IPT_KEYS_CFG
+#define RS_IPT_KEYS_CFG 16
+#endif
+template <class K, bool KEYSONLY> struct RsOcc { static const int MIN_CTAS = RsCfg<K>::MIN_CTAS; static const int IPT = RsCfg<K>::IPT; };
+template <> struct RsOcc<u64, true> { static const int MIN_CTAS = RS_MIN_CTAS_KEYS_CFG; static const int IPT = RS_IPT_KEYS_CFG; };
 
 static const ull RS_STATUS_AGG = 1, RS_STATUS_PREFIX = 2;
 
@@ -134,16 +144,16 @@ __device__ __forceinline__ u32 match_digit(u32 d, u32 nbits_mask) {
 
 // Tile ids are blockIdx.x: CTAs of a 1-D grid are dispatched in index order, so every predecessor a tile looks back
 // at is resident or finished (the same assumption CUB's decoupled look-back scan makes).
-template <class K, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS, RsCfg<K>::MIN_CTAS)
+template <class K, bool IOTA, bool KEYSONLY = false>
+__global__ void __launch_bounds__(RS_THREADS, (RsOcc<K, KEYSONLY>::MIN_CTAS))
 rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* __restrict__ vin, u32* __restrict__ vout,
                    u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc, u32 epoch) {
-    constexpr int IPT = RsCfg<K>::IPT;
+    constexpr int IPT = RsOcc<K, KEYSONLY>::IPT;
     constexpr int TILE = RS_THREADS * IPT;
     TDC_DYN_SMEM(smem_raw);
     K* skeys = reinterpret_cast<K*>(smem_raw);                                  // TILE keys
-    u32* svals = reinterpret_cast<u32*>(smem_raw + sizeof(K) * TILE);           // TILE values
-    u32* warp_cnt = svals + TILE;                                               // [RS_WARPS][256]
+    u32* svals = reinterpret_cast<u32*>(smem_raw + sizeof(K) * TILE);           // TILE values (absent when KEYSONLY)
+    u32* warp_cnt = svals + (KEYSONLY ? 0 : TILE);                              // [RS_WARPS][256]
     u32* digit_start = warp_cnt + RS_WARPS * RS_RADIX;                          // [256]
     u32* gbase = digit_start + RS_RADIX;                                        // [256]
     u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch
@@ -161,7 +171,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     // shared memory right away with cp.async — no registers held across the ranking and the look-back (prefetching them
     // into registers measured 20 % slower), and the staging step below finds them on chip instead of paying a second
     // exposed global-load latency per tile.  16-byte chunks; the partial last tile clamps the source size (zero fill).
-    if (!IOTA) {
+    if (!IOTA && !KEYSONLY) {
         for (u32 c16 = tid; c16 < u32(TILE / 4); c16 += RS_THREADS) {
             const u32 e0 = c16 * 4;
             if (e0 < count) {
@@ -268,7 +278,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         gbase[tid] = bucket_start[tid] + exclusive - ex;
     }
 #if defined(RS_VALS_ASYNC) && !defined(TDC_CUSIM)
-    if (!IOTA) asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's chunks have landed; the barrier publishes them
+    if (!IOTA && !KEYSONLY) asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's chunks have landed; the barrier publishes them
 #endif
     __syncthreads();
 
@@ -279,11 +289,13 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
         const u64 idx = wbase + u32(k) * 32 + lane;
         skeys[p] = key[k];
+        if (!KEYSONLY) {
 #ifdef RS_VALS_ASYNC
-        if (idx < m) svals[p] = IOTA ? u32(idx) : svals_in[u32(idx - tile_base)];
+            if (idx < m) svals[p] = IOTA ? u32(idx) : svals_in[u32(idx - tile_base)];
 #else
-        if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];  // (prefetching these before the look-back measured 20 % slower)
+            if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];  // (prefetching these before the look-back measured 20 % slower)
 #endif
+        }
     }
     __syncthreads();
 
@@ -293,7 +305,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         const u32 d = u32(kk >> shift) & mask;
         const u64 o = u64(gbase[d] + j);
         kout[o] = kk;
-        vout[o] = svals[j];
+        if (!KEYSONLY) vout[o] = svals[j];
     }
 }
 
@@ -309,11 +321,11 @@ static __global__ void rs_iota_kernel(u32* v, u64 m) {
 }
 
 template <class K>
-static inline size_t rs_smem_bytes() {
-    constexpr int TILE = RS_THREADS * RsCfg<K>::IPT;
-    size_t bytes = sizeof(K) * TILE + 4 * TILE + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
+static inline size_t rs_smem_bytes(bool keysonly = false) {
+    const int TILE = RS_THREADS * (keysonly ? RsOcc<u64, true>::IPT : RsCfg<K>::IPT);
+    size_t bytes = sizeof(K) * TILE + (keysonly ? 0 : 4 * TILE) + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
 #ifdef RS_VALS_ASYNC
-    bytes += 4 * TILE;
+    if (!keysonly) bytes += 4 * TILE;
 #endif
     return bytes;
 }
@@ -321,6 +333,7 @@ template <class K>
 static inline u64 rs_tiles(u64 m) {
     return div_up(m, u64(RS_THREADS) * RsCfg<K>::IPT);
 }
+static inline u64 rs_tiles_keys(u64 m) { return div_up(m, u64(RS_THREADS) * RsOcc<u64, true>::IPT); }
 
 int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count);
 void sort_workspace_free(SortWorkspace& ws);
@@ -401,6 +414,58 @@ static int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[
     if (need_iota) {
         TDC_LAUNCH(rs_iota_kernel, u32(div_up(m, 256)), 256, 0, st, v[cur], m);
         TDC_KCHECK();
+    }
+    *result = cur;
+    return 0;
+}
+
+// Sorts m 64-bit RECORDS by their bits [begin_bit, end_bit); the bits below begin_bit are payload (the suffix index of
+// the packed initial sort, suffix_array.cu) and travel inside the record: 16 B per element and pass instead of 24.
+// Stable.  Input in k[0]; *result = slot holding the output.
+static int radix_sort_keys(SortWorkspace& ws, cudaStream_t st, u64* k[2], u64 m, int begin_bit, int end_bit, int* result) {
+    *result = 0;
+    if (m == 0) return 0;
+    auto kern = rs_onesweep_kernel<u64, false, true>;
+    const size_t smem = rs_smem_bytes<u64>(true);
+    TDC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    const int bits = end_bit - begin_bit;
+    PassPlan plan;
+    plan.npass = bits <= 0 ? 0 : (bits + 7) / 8;
+    if (plan.npass > RS_MAX_PASSES) { set_error("radix_sort_keys: %d bits need more than %d passes", bits, RS_MAX_PASSES); return -1; }
+    if (rs_tiles_keys(m) > ws.max_tiles) { set_error("radix_sort_keys: workspace too small"); return -1; }
+    if (plan.npass == 0) return 0;
+    {
+        int base = bits / plan.npass, extra = bits % plan.npass, sh = begin_bit;
+        for (int p = 0; p < plan.npass; p++) {
+            int wd = base + (p < extra ? 1 : 0);
+            plan.shift[p] = u32(sh);
+            plan.mask[p] = (1u << wd) - 1u;
+            sh += wd;
+        }
+    }
+    TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
+    TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
+    const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
+    auto rs_histogram = rs_histogram_kernel<u64>;
+    TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
+    prof_add_bytes("rs_histogram", double(m) * 8);
+    TDC_LAUNCH(rs_scan_kernel, plan.npass, 256, 0, st, ws.hist, ws.uniform, m);
+    TDC_KCHECK();
+    TDC_CUDA(cudaMemcpyAsync(ws.h_uniform, ws.uniform, sizeof(u32) * RS_MAX_PASSES, cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaStreamSynchronize(st));
+    int cur = 0;
+    const u32 grid = u32(rs_tiles_keys(m));
+    for (int p = 0; p < plan.npass; p++) {
+        if (ws.h_uniform[p]) continue;
+        ws.epoch++;
+        auto rs_onesweep_keys = kern;
+        TDC_LAUNCH(rs_onesweep_keys, grid, RS_THREADS, smem, st, k[cur], k[cur ^ 1], (const u32*)nullptr, (u32*)nullptr, m, plan.shift[p],
+                   plan.mask[p], ws.hist + p * RS_RADIX, ws.desc, ws.epoch);
+        prof_add_bytes("rs_onesweep_keys", double(m) * 16);
+        TDC_KCHECK();
+        cur ^= 1;
+        ws.stat_passes++;
+        ws.stat_elems += m;
     }
     *result = cur;
     return 0;

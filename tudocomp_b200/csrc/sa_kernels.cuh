@@ -43,8 +43,14 @@ static __global__ void __launch_bounds__(256) byte_histogram_kernel(const uint8_
 // ---------------------------------------------------------------------------------------------------------------
 struct PackParams {
     u32 b;        // bits per symbol
-    u32 k;        // symbols per key
+    u32 k;        // symbols per key (the last one may be cut by `drop`)
     u32 lenbits;  // width of the trailing length field (0: sentinel has its own code 0, no field needed)
+    // packed records (single-GPU initial sort, suffix_array.cu): key = the b*k-bit symbol string without its lowest `drop`
+    // bits, record = key << idx_bits | suffix.  idx_bits == 0: plain keys (values travel separately).
+    u32 drop;
+    u32 idx_bits;
+    u32 known;    // whole symbols a key decides: (b*k - drop) / b
+    u32 pow2;     // power-of-two alphabet: symbols are coded 0..s-1 and code 0 is shared with the sentinel / the padding
 };
 
 static const int PK_THREADS = 256;
@@ -80,6 +86,7 @@ pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restr
             const u64 len = p + 1 < n ? min(u64(pp.k), n - 1 - p) : u64(0);
             key = (packed << pp.lenbits) | len;
         }
+        if (pp.idx_bits) key = ((packed >> pp.drop) << pp.idx_bits) | p;  // packed record: the suffix rides in the low bits
         out[q] = key;
         packed = ((packed << pp.b) & mask) | codes[l0 + q + pp.k];  // roll one symbol
     }
@@ -97,10 +104,11 @@ pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restr
 }
 
 // number of equal leading symbols of two different keys = LCP of the two suffixes when it is < k
-__device__ __forceinline__ u32 key_common_symbols(u64 a, u64 c, PackParams pp) {
+__device__ __forceinline__ u32 key_common_symbols(u64 a, u64 c, PackParams pp) {  // a, c: keys (records >> idx_bits)
     const u64 pa = a >> pp.lenbits, pc = c >> pp.lenbits;
-    u32 common = pp.k;
-    if (pa != pc) common = (u32(__clzll((long long)(pa ^ pc))) - (64u - pp.b * pp.k)) / pp.b;
+    const u32 width = pp.b * pp.k - pp.drop;
+    u32 common = pp.known;
+    if (pa != pc) common = min(common, (u32(__clzll((long long)(pa ^ pc))) - (64u - width)) / pp.b);
     if (pp.lenbits) {
         const u32 lm = (1u << pp.lenbits) - 1u;
         common = min(common, min(u32(a) & lm, u32(c) & lm));  // a suffix ends where its sentinel stands
@@ -153,12 +161,12 @@ __device__ __forceinline__ void rr_load_keys(const K* __restrict__ keys, u64 m, 
 // flags for the RR_IPT consecutive elements owned by this thread.
 // head bit q: element t0+q starts a group; ns bit q: its group has more than one member.
 template <class K>
-__device__ __forceinline__ void rr_flags(const K* kv, u64 m, u64 t0, u32* head_bits, u32* ns_bits) {
+__device__ __forceinline__ void rr_flags(const K* kv, u64 m, u64 t0, u32* head_bits, u32* ns_bits, u32 idx_bits = 0) {
     u32 hb = 0;  // bit q (0..RR_IPT) = head(t0+q), with head(m) := 1 and head(0) := 1
 #pragma unroll
     for (int q = 0; q <= RR_IPT; q++) {
         const u64 t = t0 + q;
-        const bool h = (t == 0) || (t >= m) || (kv[q] != kv[q + 1]);
+        const bool h = (t == 0) || (t >= m) || ((kv[q] >> idx_bits) != (kv[q + 1] >> idx_bits));
         hb |= u32(h) << q;
     }
     u32 nb = 0;
@@ -173,14 +181,14 @@ __device__ __forceinline__ void rr_flags(const K* kv, u64 m, u64 t0, u32* head_b
 
 template <class K>
 static __global__ void __launch_bounds__(RR_THREADS)
-rerank_reduce_kernel(const K* __restrict__ keys, u64 m, u32* __restrict__ agg_lasthead, ull* __restrict__ agg_cnt) {
+rerank_reduce_kernel(const K* __restrict__ keys, u64 m, u32* __restrict__ agg_lasthead, ull* __restrict__ agg_cnt, u32 idx_bits) {
     __shared__ u32 s_max[RR_THREADS / 32];
     __shared__ ull s_sum[RR_THREADS / 32];
     const u64 t0 = u64(blockIdx.x) * RR_TILE + u64(threadIdx.x) * RR_IPT;
     u32 hb, nb;
     K kv[RR_IPT + 2];
     rr_load_keys<K>(keys, m, t0, kv);
-    rr_flags<K>(kv, m, t0, &hb, &nb);
+    rr_flags<K>(kv, m, t0, &hb, &nb, idx_bits);
     u32 lasthead = 0;  // (index + 1) of the last head owned by this thread, 0 if none
 #pragma unroll
     for (int q = 0; q < RR_IPT; q++)
@@ -241,14 +249,16 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
                     const u32* __restrict__ pre_lasthead, const ull* __restrict__ pre_cnt, u32* __restrict__ sa,
                     u32* __restrict__ rank_idx, u32* __restrict__ rank_val, u32* __restrict__ pos_out,
                     u32* __restrict__ idx_out, u32* __restrict__ gid_out, u32* __restrict__ lcp_out, PackParams pp,
-                    u32 slot_base) {  // slot_base: global SA slot of this rank's first slot (0 on a single GPU)
+                    u32 slot_base,  // slot_base: global SA slot of this rank's first slot (0 on a single GPU)
+                    u32 n_text) {   // packed records (pp.idx_bits != 0, FIRST only): text length; `vals` is unused
     __shared__ ull scratch_s[33];
     __shared__ u32 scratch_m[33];
     const u64 t0 = u64(blockIdx.x) * RR_TILE + u64(threadIdx.x) * RR_IPT;
     u32 hb, nb;
     K kv[RR_IPT + 2];
+    const u32 ib = FIRST ? pp.idx_bits : 0u;
     rr_load_keys<K>(keys, m, t0, kv);
-    rr_flags<K>(kv, m, t0, &hb, &nb);
+    rr_flags<K>(kv, m, t0, &hb, &nb, ib);
     u32 lasthead = 0;
 #pragma unroll
     for (int q = 0; q < RR_IPT; q++)
@@ -266,7 +276,11 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
     u32 cur_head = max(pre_lasthead[blockIdx.x], ex_m);
     const bool full = t0 + RR_IPT <= m;
     u32 sfxv[RR_IPT], headv[RR_IPT], lcpv[RR_IPT];
-    if (full) {
+    if (FIRST && ib) {
+        const u64 im = (u64(1) << ib) - 1;
+#pragma unroll
+        for (int q = 0; q < RR_IPT; q++) sfxv[q] = t0 + q < m ? u32(u64(kv[q + 1]) & im) : 0u;
+    } else if (full) {
         const uint4* v4 = reinterpret_cast<const uint4*>(vals + t0);
 #pragma unroll
         for (int q = 0; q < RR_IPT / 4; q++) {
@@ -291,7 +305,11 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
         const u32 sfx = sfxv[q];
         headv[q] = headslot;  // rank[sfx] = headslot, applied by the partitioned scatter that follows
         if (FIRST) {
-            if (sizeof(K) == 8 && lcp_out) lcpv[q] = t == 0 ? 0u : (h ? key_common_symbols(u64(kv[q]), u64(kv[q + 1]), pp) : LCP_UNKNOWN);
+            if (sizeof(K) == 8 && lcp_out) {
+                // (packed keys over a power-of-two alphabet have no length field: next to a suffix that runs into the sentinel
+                // inside the key this value can be too large; lcp_tail_fix_kernel recomputes those few slots afterwards)
+                lcpv[q] = t == 0 ? 0u : (h ? key_common_symbols(u64(kv[q]) >> ib, u64(kv[q + 1]) >> ib, pp) : LCP_UNKNOWN);
+            }
         } else {
             rank_idx[t] = sfx;
             rank_val[t] = headslot;
@@ -333,11 +351,19 @@ rerank_apply_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, co
 // ---------------------------------------------------------------------------------------------------------------
 static __global__ void __launch_bounds__(256)
 build_keys_kernel(const u32* __restrict__ idx, const u32* __restrict__ gid, const u32* __restrict__ rank, u64 m, u64 h,
-                  u64 n, u32 rbits, u64* __restrict__ keys) {
+                  u64 n, u32 rbits, u64* __restrict__ keys, u32 overshoot) {
     const u64 o = u64(blockIdx.x) * blockDim.x + threadIdx.x;
     if (o >= m) return;
     const u64 j = u64(idx[o]) + h;
-    const u32 r2 = j < n ? rank[j] : 0u;  // j < n always holds for active suffixes; the guard is defensive
+    u64 r2;
+    if (!overshoot) {
+        r2 = j < n ? rank[j] : 0u;  // j < n always holds for active suffixes here; the guard is defensive
+    } else {
+        // Initial keys without a length field (packed records over a power-of-two alphabet): a suffix that ran into the
+        // sentinel inside its known prefix is grouped with suffixes that continue with code-0 symbols.  It is the smaller
+        // one, and of two such suffixes the shorter: rank them below every real rank, by how far they overshoot the end.
+        r2 = j < n ? n + u64(rank[j]) : n - 1 - min(j - (n - 1), n - 1);
+    }
     keys[o] = (u64(gid[o]) << rbits) | r2;
 }
 
@@ -354,7 +380,11 @@ static u32 bits_of_lenfield(u32 k) { return bits_for_host(k); }
 // first k bytes (k = 1..8, from sample_prefix_collisions; > 0 means "not measured").  It replaces the memoryless
 // estimate 2^(-H0 k), which is far too optimistic for text with context (order-3 Markov English: H0 = 4.1 bit/symbol but
 // ~2.3 bit/symbol of discrimination), and is extrapolated geometrically beyond k = 8.
-static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbits, const double* log2_collide = nullptr) {
+// idx_bits_avail > 0 (single-GPU builder): the initial sort may also run on PACKED records, key << idx_bits | suffix in one
+// 64-bit word, which moves 16 B per suffix and pass instead of 24 but leaves only 64 - idx_bits key bits (a shorter known
+// prefix, hence more suffixes for the doubling rounds).  The model prices both layouts and takes the cheaper one.
+static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbits, const double* log2_collide = nullptr,
+                              u32 idx_bits_avail = 0) {
     u32 real = 0;
     double h0 = 0;
     for (int b = 1; b < 256; b++)
@@ -370,34 +400,54 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
     u32 kmax = 1;
     for (u32 k = 1; k <= u32(PK_HALO); k++)
         if (b * k + (pow2 ? bits_of_lenfield(k) : 0) <= 64) kmax = k;
+    // expected share of suffixes that a prefix of kf symbols (fractional: a cut symbol counts for its share of bits)
+    // leaves in groups, and the doubling rounds a grouped suffix then still has to go through
+    int k2 = 0, k1 = 0;
+    double rate = 0;
+    if (log2_collide) {
+        // last two measured points with enough collisions give the decay rate for the extrapolation
+        for (int q = 8; q >= 2; q--)
+            if (log2_collide[q] <= 0.0 && log2_collide[q - 1] <= 0.0) { k2 = q; break; }
+        if (k2) {
+            k1 = k2 >= 3 && log2_collide[k2 - 2] <= 0.0 ? k2 - 2 : k2 - 1;
+            rate = (log2_collide[k1] - log2_collide[k2]) / double(k2 - k1);  // bits per symbol
+        }
+    }
+    auto residue_of = [&](double kf, double* rounds_left) {
+        double residue = h0 > 1e-9 ? exp2(log2(double(n)) - h0 * kf) : 1.0;
+        *rounds_left = 0.0;
+        if (k2) {
+            double lp;
+            if (kf <= double(k2)) {
+                const int lo = kf < 1.0 ? 1 : int(kf);
+                const int hi = lo < 8 && log2_collide[lo + 1] <= 0.0 ? lo + 1 : lo;
+                const double f = kf < 1.0 ? 0.0 : kf - double(lo);
+                lp = log2_collide[lo] + (log2_collide[hi] - log2_collide[lo]) * f;
+            } else {
+                lp = log2_collide[k2] - rate * (kf - double(k2));
+            }
+            const double expected_twins = exp2(log2(double(n)) + lp);
+            residue = 1.0 - exp(-expected_twins);
+            // a text that keeps most suffixes in groups whatever k is (repeats) pays one doubling round per factor of two
+            // that the initial key is shorter than the longest possible one
+            *rounds_left = kf < double(kmax) ? 0.5 * log2(double(kmax) / kf) : 0.0;
+        }
+        return residue > 1.0 ? 1.0 : residue;
+    };
     u32 best = kmax;
-    if (const char* e = getenv("TDCGPU_SA_SYMBOLS")) {  // tuning/debug override
+    double best_cost = 1e300;
+    const char* mode_env = getenv("TDCGPU_SA_MODE");  // tuning/debug: "wide" | "packed"
+    const bool force_wide = mode_env && mode_env[0] == 'w', force_packed = mode_env && mode_env[0] == 'p';
+    if (const char* e = getenv("TDCGPU_SA_SYMBOLS")) {  // tuning/debug override (wide layout)
         const long v = atol(e);
         if (v >= 1 && v <= long(kmax)) best = u32(v);
+        best_cost = -1.0;
     } else {
-        double best_cost = 1e300;
         for (u32 k = 1; k <= kmax; k++) {
             const u32 bits = b * k + (pow2 ? bits_of_lenfield(k) : 0);
             const double passes = double((bits + 7) / 8);
-            double residue = h0 > 1e-9 ? exp2(log2(double(n)) - h0 * double(k)) : 1.0;
-            double rounds_left = 0.0;
-            if (log2_collide) {
-                // last two measured points with enough collisions give the decay rate for the extrapolation
-                int k2 = 0;
-                for (int q = 8; q >= 2; q--)
-                    if (log2_collide[q] <= 0.0 && log2_collide[q - 1] <= 0.0) { k2 = q; break; }
-                if (k2) {
-                    const int k1 = k2 >= 3 && log2_collide[k2 - 2] <= 0.0 ? k2 - 2 : k2 - 1;
-                    const double rate = (log2_collide[k1] - log2_collide[k2]) / double(k2 - k1);  // bits per symbol
-                    const double lp = int(k) <= k2 ? log2_collide[k >= 1 ? k : 1] : log2_collide[k2] - rate * double(int(k) - k2);
-                    const double expected_twins = exp2(log2(double(n)) + lp);
-                    residue = 1.0 - exp(-expected_twins);
-                    // a text that keeps most suffixes in groups whatever k is (repeats) pays one doubling round per
-                    // factor of two that the initial key is shorter than the longest possible one
-                    rounds_left = 0.5 * log2(double(kmax) / double(k));
-                }
-            }
-            if (residue > 1.0) residue = 1.0;
+            double rounds_left;
+            const double residue = residue_of(double(k), &rounds_left);
             const double cost = passes * 24.0 + residue * SA_ACTIVE_COST * (1.0 + rounds_left);
             if (cost <= best_cost) { best_cost = cost; best = k; }  // ties: more symbols
         }
@@ -405,7 +455,36 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
     pp->b = b;
     pp->k = best;
     pp->lenbits = pow2 ? bits_of_lenfield(best) : 0;
+    pp->drop = 0;
+    pp->idx_bits = 0;
+    pp->known = best;
+    pp->pow2 = pow2 ? 1u : 0u;
     *sigbits = b * best + pp->lenbits;
+    if (!idx_bits_avail || idx_bits_avail >= 64 - b || force_wide || (best_cost < 0 && !force_packed)) return;
+    // packed records: kb key bits, no length field (suffixes that run into the sentinel are handled by the doubling keys)
+    const u32 kb_max = min(64u - idx_bits_avail, b * u32(PK_HALO));
+    u32 best_kb = 0;
+    double best_pcost = 1e300;
+    if (const char* e = getenv("TDCGPU_SA_KEYBITS")) {
+        const long v = atol(e);
+        if (v >= long(b) && v <= long(kb_max)) { best_kb = u32(v); best_pcost = -1.0; }
+    }
+    if (!best_kb) {
+        for (u32 kb = b; kb <= kb_max; kb++) {
+            const double passes = double((kb + 7) / 8);
+            double rounds_left;
+            const double residue = residue_of(double(kb) / double(b), &rounds_left);
+            const double cost = passes * 16.0 - 8.0 + residue * SA_ACTIVE_COST * (1.0 + rounds_left);  // -8: no separate value array to re-rank
+            if (cost <= best_pcost) { best_pcost = cost; best_kb = kb; }
+        }
+    }
+    if (!best_kb || (!force_packed && best_pcost >= best_cost)) return;
+    pp->k = (best_kb + b - 1) / b;
+    pp->lenbits = 0;
+    pp->drop = b * pp->k - best_kb;
+    pp->idx_bits = idx_bits_avail;
+    pp->known = best_kb / b;
+    *sigbits = best_kb;
 }
 
 

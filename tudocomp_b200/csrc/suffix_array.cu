@@ -19,6 +19,8 @@
 //   3. doubling round with offset h: key = (group id << rbits) | rank[suffix + h]; sort the active list; rerank; h *= 2.
 //      Active suffixes always satisfy suffix + h <= n-1 (a suffix whose h-prefix reaches the sentinel is unique).
 //   When the active list is empty, sa[] is the suffix array and rank[] is the inverse suffix array.
+#include <algorithm>
+
 #include "sa_kernels.cuh"
 
 namespace tdc {
@@ -28,8 +30,8 @@ int sort_workspace_init(SortWorkspace& ws, u64 max_elems, int sm_count) {
     sort_workspace_free(ws);
     ws.sm_count = sm_count;
     // tiles of the smallest tile configuration bound the descriptor count
-    const u64 t64 = rs_tiles<u64>(max_elems), t32 = rs_tiles<u32>(max_elems);
-    ws.max_tiles = (t64 > t32 ? t64 : t32) + 1;
+    const u64 t64 = rs_tiles<u64>(max_elems), t32 = rs_tiles<u32>(max_elems), tk = rs_tiles_keys(max_elems);
+    ws.max_tiles = std::max(std::max(t64, t32), tk) + 1;
     TDC_CUDA(cudaMalloc(&ws.hist, sizeof(u32) * RS_MAX_PASSES * RS_RADIX));
     TDC_CUDA(cudaMalloc(&ws.uniform, sizeof(u32) * RS_MAX_PASSES));
     TDC_CUDA(cudaMalloc(&ws.desc, sizeof(ull) * ws.max_tiles * RS_RADIX));
@@ -58,13 +60,13 @@ static int rerank(Ctx& c, const K* keys, const u32* vals, const u32* pos_in, u64
                   u64* m_out, u64* g_out) {
     const u32 ntiles = u32(div_up(m, RR_TILE));
     auto rerank_reduce = rerank_reduce_kernel<K>;
-    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt);
+    TDC_LAUNCH(rerank_reduce, ntiles, RR_THREADS, 0, c.stream, keys, m, agg_lasthead, agg_cnt, FIRST ? pp.idx_bits : 0u);
     prof_add_bytes("rerank_reduce", double(m) * sizeof(K));
     TDC_LAUNCH(rerank_scan_kernel, 1, 1024, 0, c.stream, agg_lasthead, agg_cnt, ntiles, c.d_scalars);
     auto rerank_apply = rerank_apply_kernel<K, FIRST>;
     TDC_LAUNCH(rerank_apply, ntiles, RR_THREADS, 0, c.stream, keys, vals, pos_in, m, agg_lasthead, agg_cnt, c.d_sa, sc_idx[0],
-               sc_val[0], pos_out, idx_out, gid_out, lcp_out, pp, 0u);
-    prof_add_bytes("rerank_apply", double(m) * (sizeof(K) + 4 + (FIRST ? 8 + (lcp_out ? 4 : 0) : 12)));
+               sc_val[0], pos_out, idx_out, gid_out, lcp_out, pp, 0u, u32(c.n));
+    prof_add_bytes("rerank_apply", double(m) * (sizeof(K) + ((FIRST && pp.idx_bits) ? 0 : 4) + (FIRST ? 8 + (lcp_out ? 4 : 0) : 12)));
     TDC_KCHECK();
     // first round: the pairs are (vals[t], head slot) and vals is a permutation of 0..n-1
     TDC_TRY(partitioned_scatter(c.sortws, c.stream, sc_idx, sc_val, m, c.d_isa, c.n, FIRST));
@@ -90,6 +92,9 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     c.sa_active_sum = 0;
     c.sa_prefix_work = 0;
     c.sa_lcp_seeded = false;
+    c.sa_packed = false;
+    c.sa_tail_span = 0;
+    c.sa_key_bits = 0;
     c.sortws.stat_passes = 0;
     c.sortws.stat_elems = 0;
     if (n == 1) {  // text == "\0"
@@ -138,11 +143,13 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
             have_collide = true;
         }
     }
-    choose_key_layout(hist, n, &pp, &sigbits, have_collide ? log2_collide : nullptr);
+    // packed records need the suffix index next to the key bits in one 64-bit word
+    choose_key_layout(hist, n, &pp, &sigbits, have_collide ? log2_collide : nullptr, bits_for_host(n - 1));
+    const bool packed = pp.idx_bits != 0;
     uint8_t code_map[256];
     u32 sigma = 1;
     {
-        u32 next = pp.lenbits ? 0 : 1;
+        u32 next = pp.pow2 ? 0 : 1;
         code_map[0] = 0;
         for (int b = 1; b < 256; b++) {
             code_map[b] = uint8_t(next);
@@ -150,7 +157,10 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
         }
     }
     c.alphabet = sigma;
-    c.symbols_per_key = pp.k;
+    c.symbols_per_key = pp.known;
+    c.sa_packed = packed;
+    c.sa_tail_span = (packed && pp.pow2) ? pp.k : 0;
+    c.sa_key_bits = sigbits;
 
     // ---- scratch ----
     c.arena.reset();
@@ -175,30 +185,35 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     prof_add_bytes("pack_keys_kernel", double(n) * 9);
     TDC_KCHECK();
     int res = 0;
-    TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, keys, vals, n, 0, int(sigbits), true, &res));
+    if (packed) TDC_TRY(radix_sort_keys(c.sortws, st, keys, n, int(pp.idx_bits), int(pp.idx_bits + sigbits), &res));
+    else TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, keys, vals, n, 0, int(sigbits), true, &res));
     u64 m = 0, g = 0;
     int pcur = 0;
     // the sorted (key, suffix) pairs are in slot `res`; compacted survivors go to the other slot's value buffer
     {
         // ISA updates of this round: index side = the sorted suffix list itself (read only), value side and the
         // partition scratch live in the key buffer that does not hold the sorted keys plus sc_a/sc_b
-        u32* sc_idx[2] = {vals[res], sc_a};
+        // (packed records: there is no value array; the sorted suffix list is what rerank_apply writes to sa[])
+        u32* sc_idx[2] = {packed ? c.d_sa : vals[res], sc_a};
         u32* sc_val[2] = {reinterpret_cast<u32*>(keys[res ^ 1]), sc_b};
         u32* lcp_out = (want_lcp && c.d_lcp) ? c.d_lcp : nullptr;
-        TDC_TRY((rerank<u64, true>(c, keys[res], vals[res], nullptr, n, agg_lasthead, agg_cnt, pos[pcur], vals[res ^ 1], gid, sc_idx, sc_val, lcp_out, pp, &m, &g)));
+        TDC_TRY((rerank<u64, true>(c, keys[res], packed ? nullptr : vals[res], nullptr, n, agg_lasthead, agg_cnt, pos[pcur], vals[res ^ 1], gid, sc_idx, sc_val, lcp_out, pp, &m, &g)));
         c.sa_lcp_seeded = lcp_out != nullptr;
     }
     c.sa_rounds = 1;
     c.sa_active_sum = n;
     c.sa_first_residue = m;
 
-    const u32 rbits = bits_for_host(n - 1);
-    u64 h = pp.k;
+    // keys without a length field over a power-of-two alphabet: suffixes that ran into the sentinel are ranked by their
+    // overshoot, below all real ranks (build_keys_kernel), which takes one more bit
+    const u32 overshoot = (packed && pp.pow2) ? 1u : 0u;
+    const u32 rbits = overshoot ? bits_for_host(2 * n - 1) : bits_for_host(n - 1);
+    u64 h = min(u64(pp.known), n - 1);  // (a shorter known prefix is always valid; the overshoot ranks need h <= n - 1)
     while (m > 0) {
         // active list: slots pos[pcur][0..m), suffixes vals[res^1][0..m), group ids gid[0..m)
         u64* k2[2] = {keys[0], keys[1]};
         u32* v2[2] = {vals[res ^ 1], vals[res]};
-        TDC_LAUNCH(build_keys_kernel, u32(div_up(m, 256)), 256, 0, st, v2[0], gid, c.d_isa, m, h, n, rbits, k2[0]);
+        TDC_LAUNCH(build_keys_kernel, u32(div_up(m, 256)), 256, 0, st, v2[0], gid, c.d_isa, m, h, n, rbits, k2[0], overshoot);
         prof_add_bytes("build_keys_kernel", double(m) * 20);
         TDC_KCHECK();
         const int gbits = g > 1 ? int(bits_for_host(g - 1)) : 0;

@@ -117,6 +117,9 @@ struct Ctx {
     u32 sa_rounds = 0;
     u64 sa_active_sum = 0;
     u32 alphabet = 0, symbols_per_key = 0;
+    bool sa_packed = false;  // the initial sort ran on packed 64-bit records (key | suffix)
+    u32 sa_key_bits = 0;     // key bits of the initial sort
+    u32 sa_tail_span = 0;    // packed keys without a length field: symbols per key (suffixes that close to the end were padded)
     double sa_prefix_work = 0;  // sum over doubling rounds of (active suffixes x already-known common prefix): LCP-sum estimate
     bool sa_lcp_seeded = false;  // d_lcp holds key-derived LCPs / LCP_UNKNOWN marks from the initial sort
     u64 sa_first_residue = 0;    // suffixes the initial sort left in groups

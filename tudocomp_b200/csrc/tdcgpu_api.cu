@@ -676,6 +676,15 @@ int tdcgpu_sa_stats(tdcgpu_ctx* ctx, uint64_t out[8]) {
     return 0;
 }
 
+int tdcgpu_sa_layout(tdcgpu_ctx* ctx, uint64_t out[4]) {
+    API_GUARD(ctx);
+    out[0] = c.sa_packed ? 1 : 0;
+    out[1] = c.sa_key_bits;
+    out[2] = c.sa_packed ? bits_for_host(c.n > 1 ? c.n - 1 : 1) : 0;
+    out[3] = c.symbols_per_key;
+    return 0;
+}
+
 int tdcgpu_sync(tdcgpu_ctx* ctx) {
     API_GUARD(ctx);
     TDC_CUDA(cudaStreamSynchronize(c.stream));
