@@ -36,6 +36,36 @@ PY
       done ;;
     plugintests)
       timeout 900 python -m pytest tests/test_plugin.py tests/test_encode.py tests/test_check.py tests/test_stream_stages.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_plugintests.txt ;;
+    sanitize)  # compute-sanitizer memcheck + racecheck over the smoke path, the checkers and the stream stages (small inputs)
+      for tool in memcheck racecheck; do
+        timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitize_${tool}_smoke.log 2>&1
+        tail -3 gpurun_out/${tag}_sanitize_${tool}_smoke.log
+        TDCGPU_SA_MODE=packed timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_cases.py > gpurun_out/${tag}_sanitize_${tool}_cases.log 2>&1
+        tail -3 gpurun_out/${tag}_sanitize_${tool}_cases.log
+      done ;;
+    block)  # BASELINE config 5 through the real plugin: tdc_block over the GPU registry, 256 MiB blocks, one worker per GPU
+      N=${BLOCK_GPUS:-1}; GIB=${BLOCK_GIB:-2}
+      python - <<PY
+import sys; sys.path.insert(0, ".")
+from tudocomp_b200 import synth
+with open("/dev/shm/block_in.txt", "wb") as f:
+    for i in range($GIB):
+        f.write(synth.markov_text(1 << 30, 500 + i)[:-1].tobytes())
+PY
+      ./build/tdc_block_gpu -a "lzss_lcp(coder=huff)" -b 268435456 -g $N /dev/shm/block_in.txt -o /dev/shm/block_out.tdcb 2>&1 | sed "s#^#[-g $N] #" | tee -a gpurun_out/${tag}_block_mode.txt
+      ls -l /dev/shm/block_in.txt /dev/shm/block_out.tdcb | tee -a gpurun_out/${tag}_block_mode.txt
+      # the container is decoded by the REFERENCE registry (tdc_block_ref -d) and compared with the input
+      ( time ./build/tdc_block_ref -d /dev/shm/block_out.tdcb -o /dev/shm/block_back.txt ) 2>&1 | tail -4 | tee -a gpurun_out/${tag}_block_mode.txt
+      cmp /dev/shm/block_in.txt /dev/shm/block_back.txt && echo "round trip through the reference decoder: identical" | tee -a gpurun_out/${tag}_block_mode.txt
+      rm -f /dev/shm/block_in.txt /dev/shm/block_out.tdcb /dev/shm/block_back.txt ;;
+    ncu)  # one `ncu --set full` capture of the dominant kernel inside the real bench (full-size launch: skip the sample sort)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-rs_onesweep} -s ${NCU_SKIP:-3} -c 1 -o gpurun_out/${tag}_ncu -f \
+        python bench.py --steps 1 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_ncu.log 2>&1
+      echo "ncu rc=$?"; tail -3 gpurun_out/${tag}_ncu.log ;;
+    dist)  # the default bench line on all GPUs of the box (block-mode headline + sharded sub-records)
+      N=$(nvidia-smi -L | wc -l)
+      timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_n$N.json 2> gpurun_out/${tag}_bench_n$N.err
+      echo "dist bench rc=$?"; tail -c 1500 gpurun_out/${tag}_bench_n$N.json; tail -3 gpurun_out/${tag}_bench_n$N.err ;;
     *) echo "unknown stage $stage" ;;
   esac
 done
