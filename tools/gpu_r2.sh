@@ -36,6 +36,22 @@ PY
       done ;;
     plugintests)
       timeout 900 python -m pytest tests/test_plugin.py tests/test_encode.py tests/test_check.py tests/test_stream_stages.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_plugintests.txt ;;
+    workloads)  # the other single-GPU configs of BASELINE.json: 100 MB Markov (1), 2^30 B repetitive (3); resident + e2e, verified
+      timeout 600 python bench.py --steps 5 --warmup 2 --workload markov --bytes 100000000 --no-dist --no-cpu-baseline > gpurun_out/${tag}_bench_markov1e8.json 2> gpurun_out/${tag}_bench_markov1e8.err
+      echo "markov rc=$?"
+      timeout 900 python bench.py --steps 3 --warmup 1 --workload repetitive --log2-bytes 30 --no-dist --no-cpu-baseline --no-pipeline > gpurun_out/${tag}_bench_rep30.json 2> gpurun_out/${tag}_bench_rep30.err
+      echo "repetitive rc=$?"
+      python - <<PY
+import json
+for f in ("markov1e8", "rep30"):
+    try:
+        d = json.load(open("gpurun_out/${tag}_bench_%s.json" % f))
+        print(f, "ms/step", round(d["ms_per_step"], 2), "MB/s", round(d["value"]), "e2e", round(d["e2e"]["value"]), "verified", d["verified"], d["sa_stats"], d["last_step_phases_ms"])
+        print({k: (v["launches"], v["ms"]) for k, v in list(d["kernels"].items())[:12]})
+    except Exception as e:
+        print(f, "failed", e)
+PY
+      ;;
     sanitize)  # compute-sanitizer memcheck + racecheck over the smoke path, the checkers and the stream stages (small inputs)
       for tool in memcheck racecheck; do
         timeout 900 compute-sanitizer --tool $tool --print-limit 20 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_sanitize_${tool}_smoke.log 2>&1

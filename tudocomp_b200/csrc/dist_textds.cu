@@ -425,7 +425,7 @@ static int dist_build_sa(DistCtx& d) {
             TDC_TRY(a2a_elems(d, S[0], S[1], 4, back.data()));
         }
         if (m) {
-            TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256)), 256, 0, st, S[2], S[1], m, S[3]);
+            TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256 * SP_EPT)), 256, 0, st, S[2], S[1], m, S[3]);
             TDC_LAUNCH(build_keys_from_kernel, u32(div_up(m, 256)), 256, 0, st, G, S[3], m, rbits, K[0]);
             TDC_KCHECK();
         }
@@ -466,7 +466,7 @@ static int dist_build_lcp(DistCtx& d) {
     TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
     u64 mine[2] = {0, mr};
     if (mr) {
-        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(mr, 256)), 256, 0, st, c.d_text, d.d_sa, mr, d.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
+        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(mr, 256 * LCPFIX_EPT)), 256, 0, st, c.d_text, d.d_sa, mr, d.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
         TDC_KCHECK();
         TDC_CUDA(cudaMemcpyAsync(c.h_scalars + 8, d.d_sa + (mr - 1), sizeof(u32), cudaMemcpyDeviceToHost, st));
         TDC_CUDA(cudaStreamSynchronize(st));
@@ -518,7 +518,7 @@ static int dist_factorize(DistCtx& d, u32 threshold) {
         u32* a = c.arena.take<u32>(szo);
         u32* l = c.arena.take<u32>(szo);
         if (!a || !l) { set_error("dist lzss_lcp: scratch arena too small"); return TDCGPU_ERR_NOMEM; }
-        TDC_LAUNCH(mintree_level_kernel, u32(div_up(u64(szo) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
+        TDC_LAUNCH(mintree_level_kernel, u32(div_up(div_up(u64(szo), MT_OUT_PER_WARP) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
         T.a[T.nlev] = a;
         T.l[T.nlev] = l;
         T.sz[T.nlev] = szo;

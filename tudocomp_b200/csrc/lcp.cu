@@ -25,7 +25,7 @@ int build_lcp_direct(Ctx& c) {
     TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
     if (c.sa_lcp_seeded) {
         if (c.sa_tail_span) TDC_LAUNCH(lcp_tail_fix_kernel, u32(div_up(u64(c.sa_tail_span) + 1, 64)), 64, 0, st, c.d_text, c.d_sa, c.d_isa, n, c.sa_tail_span, c.d_lcp);
-        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
+        TDC_LAUNCH(lcp_fix_kernel, u32(div_up(n, 256 * LCPFIX_EPT)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, c.symbols_per_key, queue, d_qlen, d_max);
         prof_add_bytes("lcp_fix_kernel", double(n) * 4 + double(c.sa_first_residue) * 72);
     } else {
         TDC_LAUNCH(lcp_direct_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_sa, n, c.d_lcp, queue, d_qlen, d_max);

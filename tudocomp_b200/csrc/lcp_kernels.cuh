@@ -236,28 +236,37 @@ lcp_direct_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, 
 
 // Seeded variant: the initial sort already wrote the LCP of every pair its keys separate (suffix_array.cu,
 // key_common_symbols); only pairs marked LCP_UNKNOWN — same k-symbol prefix — are compared, starting at offset k.
+static const int LCPFIX_EPT = 4;  // slots per thread: one 16-byte load of the seeded values (a 4-byte load per thread ran at 1 TB/s)
 static __global__ void __launch_bounds__(256)
 lcp_fix_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ sa, u64 n, u32* __restrict__ lcp, u32 l0,
                u32* __restrict__ queue, u32* __restrict__ queue_len, u32* __restrict__ max_lcp) {
     __shared__ u32 s_max[256 / 32];
-    const u64 j = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool valid = j < n;
-    u32 l = valid ? lcp[j] : 0u;
-    const bool unknown = valid && l == LCP_UNKNOWN;
-    if (__any_sync(kFull, unknown)) {
-        const u32 own = valid ? sa[j] : 0u;
-        u32 prev = __shfl_up_sync(kFull, own, 1);
-        if (unknown) {
-            if (lane_id() == 0) prev = sa[j - 1];  // j >= 1: slot 0 is never unknown
-            bool done;
+    const u64 j0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * LCPFIX_EPT;
+    u32 lv[LCPFIX_EPT];
+    if (j0 + LCPFIX_EPT <= n) {
+        const uint4 q = *reinterpret_cast<const uint4*>(lcp + j0);
+        lv[0] = q.x; lv[1] = q.y; lv[2] = q.z; lv[3] = q.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < LCPFIX_EPT; q++) lv[q] = j0 + q < n ? lcp[j0 + q] : 0u;
+    }
+    u32 mx = 0;
+#pragma unroll
+    for (int q = 0; q < LCPFIX_EPT; q++) {
+        const u64 j = j0 + q;
+        u32 l = lv[q];
+        if (j < n && l == LCP_UNKNOWN) {  // j >= 1: slot 0 is never unknown
+            const u32 own = sa[j], prev = sa[j - 1];
             // (keys without a length field: a suffix shorter than l0 shares its padded key, not l0 real symbols)
             const u32 start = min(l0, min(u32(n - 1) - own, u32(n - 1) - prev));
+            bool done;
             l = lce_thread(text, own, prev, start, start + LCPD_THREAD_LIMIT, &done);
             if (!done) queue[atomicAdd(queue_len, 1u)] = u32(j);
             lcp[j] = l;
         }
+        mx = max(mx, l);
     }
-    u32 mx = warp_max(l);
+    mx = warp_max(mx);
     if (lane_id() == 0) s_max[warp_id()] = mx;
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -48,7 +48,7 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         u32* a = c.arena.take<u32>(szo);
         u32* l = c.arena.take<u32>(szo);
         if (!a || !l) { set_error("lzss_lcp: scratch arena too small"); return -2; }
-        TDC_LAUNCH(mintree_level_kernel, u32(div_up(u64(szo) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
+        TDC_LAUNCH(mintree_level_kernel, u32(div_up(div_up(u64(szo), MT_OUT_PER_WARP) * 32, 256)), 256, 0, st, T.a[T.nlev - 1], T.l[T.nlev - 1], szi, a, l, szo);
         T.a[T.nlev] = a;
         T.l[T.nlev] = l;
         T.sz[T.nlev] = szo;

@@ -16,18 +16,33 @@ struct MinTree {
     __device__ __forceinline__ int levels() const { return nlev; }
 };
 
-// one warp per output element: min over 32 inputs
+// one warp per 4 output elements (128 inputs): every lane takes 4 consecutive inputs with one 16-byte load per array,
+// 8 lanes form one output
+static const int MT_OUT_PER_WARP = 4;
 static __global__ void __launch_bounds__(256)
 mintree_level_kernel(const u32* __restrict__ a_in, const u32* __restrict__ l_in, u32 sz_in, u32* __restrict__ a_out,
                      u32* __restrict__ l_out, u32 sz_out) {
-    const u32 o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (o >= sz_out) return;  // whole warps leave together (sz_out is tested per warp)
-    const u64 i = u64(o) * 32 + lane_id();
-    u32 av = i < sz_in ? a_in[i] : 0xffffffffu;
-    u32 lv = i < sz_in ? l_in[i] : 0xffffffffu;
-    av = warp_min(av);
-    lv = warp_min(lv);
-    if (lane_id() == 0) { a_out[o] = av; l_out[o] = lv; }
+    const u32 wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 o0 = wi * MT_OUT_PER_WARP;
+    if (o0 >= sz_out) return;  // whole warps leave together
+    const u64 i = u64(o0) * 32 + u64(lane_id()) * 4;
+    u32 av = 0xffffffffu, lv = 0xffffffffu;
+    if (i + 4 <= sz_in) {
+        const uint4 a = *reinterpret_cast<const uint4*>(a_in + i);
+        const uint4 l = *reinterpret_cast<const uint4*>(l_in + i);
+        av = min(min(a.x, a.y), min(a.z, a.w));
+        lv = min(min(l.x, l.y), min(l.z, l.w));
+    } else {
+        for (u32 q = 0; q < 4; q++)
+            if (i + q < sz_in) { av = min(av, a_in[i + q]); lv = min(lv, l_in[i + q]); }
+    }
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) {
+        av = min(av, __shfl_xor_sync(kFull, av, d));
+        lv = min(lv, __shfl_xor_sync(kFull, lv, d));
+    }
+    const u32 o = o0 + (lane_id() >> 3);
+    if ((lane_id() & 7u) == 0 && o < sz_out) { a_out[o] = av; l_out[o] = lv; }
 }
 
 enum : int { WALK_ABANDONED = 0, WALK_FOUND = 1, WALK_OFF_TREE = 2 };

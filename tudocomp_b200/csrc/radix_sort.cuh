@@ -28,6 +28,7 @@ static const int RS_THREADS = RS_THREADS_CFG;  // >= 256: one thread per digit i
 static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
 static const int RS_WARPS = RS_THREADS / 32;
 static const int RS_RADIX = 256;
+static const int RS_HIST_EPT = 4;
 static const int RS_MAX_PASSES = 8;
 
 struct PassPlan {
@@ -90,21 +91,34 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const K* __restrict__
     __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
     for (u32 i = threadIdx.x; i < RS_MAX_PASSES * RS_RADIX; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const u64 m_round = (m + 31) & ~u64(31);
-    const u64 stride = u64(gridDim.x) * blockDim.x;
-    for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < m_round; i += stride) {
-        const bool valid = i < m;
-        const K k = valid ? keys[i] : K(0);
+    // RS_HIST_EPT keys per thread and iteration, all loads issued before the first counter update (one key per iteration
+    // left the kernel waiting on a single 8-byte load per thread: 1.5 TB/s)
+    constexpr int EPT = RS_HIST_EPT;
+    const u64 chunk = u64(32) * EPT;                       // keys per warp and iteration, lane-strided inside the chunk
+    const u64 m_round = (m + chunk - 1) / chunk * chunk;
+    const u64 warps = (u64(gridDim.x) * blockDim.x) >> 5;
+    for (u64 base = ((u64(blockIdx.x) * blockDim.x + threadIdx.x) >> 5) * chunk; base < m_round; base += warps * chunk) {
+        K kk[EPT];
 #pragma unroll
-        for (int p = 0; p < RS_MAX_PASSES; p++) {
-            if (p < plan.npass) {
-                const u32 d = u32(k >> plan.shift[p]) & plan.mask[p];
-                // warp-uniform digit (constant high bits, runs): one shared atomic instead of a 32-way conflict
-                const u32 d0 = __shfl_sync(kFull, d, 0);
-                if (__all_sync(kFull, valid && d == d0)) {
-                    if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d0], 32u);
-                } else if (valid) {
-                    atomicAdd(&sh[p * RS_RADIX + d], 1u);
+        for (int e = 0; e < EPT; e++) {
+            const u64 i = base + u64(e) * 32 + lane_id();
+            kk[e] = i < m ? keys[i] : K(0);
+        }
+#pragma unroll
+        for (int e = 0; e < EPT; e++) {
+            const bool valid = base + u64(e) * 32 + lane_id() < m;
+            const K k = kk[e];
+#pragma unroll
+            for (int p = 0; p < RS_MAX_PASSES; p++) {
+                if (p < plan.npass) {
+                    const u32 d = u32(k >> plan.shift[p]) & plan.mask[p];
+                    // warp-uniform digit (constant high bits, runs): one shared atomic instead of a 32-way conflict
+                    const u32 d0 = __shfl_sync(kFull, d, 0);
+                    if (__all_sync(kFull, valid && d == d0)) {
+                        if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d0], 32u);
+                    } else if (valid) {
+                        atomicAdd(&sh[p * RS_RADIX + d], 1u);
+                    }
                 }
             }
         }
@@ -481,10 +495,21 @@ static int radix_sort_keys(SortWorkspace& ws, cudaStream_t st, u64* k[2], u64 m,
 // One element per thread, CTAs in index order: the in-order CTA dispatch keeps all resident CTAs inside the same window
 // (measured with tools/scatterbench.cu: 160 Gelem/s for 16 MiB windows vs 23 Gelem/s unpartitioned; a grid-stride
 // loop loses the locality and most of the gain).
+static const int SP_EPT = 4;  // pairs per thread (two 16-byte loads); a CTA still covers one contiguous run of the pairs
 static __global__ void __launch_bounds__(256)
 scatter_pairs_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 m, u32* __restrict__ dst) {
-    const u64 t = u64(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t < m) dst[idx[t]] = val[t];
+    const u64 t0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * SP_EPT;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(val)) & 15u) == 0;  // kernel-uniform
+    if (aligned && t0 + SP_EPT <= m) {
+        const uint4 i4 = *reinterpret_cast<const uint4*>(idx + t0);
+        const uint4 v4 = *reinterpret_cast<const uint4*>(val + t0);
+        dst[i4.x] = v4.x;
+        dst[i4.y] = v4.y;
+        dst[i4.z] = v4.z;
+        dst[i4.w] = v4.w;
+    } else {
+        for (u64 t = t0; t < min(t0 + u64(SP_EPT), m); t++) dst[idx[t]] = val[t];
+    }
 }
 
 #ifdef TDC_CUSIM
@@ -506,7 +531,7 @@ static inline int partitioned_scatter(SortWorkspace& ws, cudaStream_t st, u32* i
         const int wbits = bits - PS_WINDOW_BITS > 8 ? 8 : bits - PS_WINDOW_BITS;  // at most 256 windows
         TDC_TRY(radix_sort_pairs<u32>(ws, st, idx, val, m, bits - wbits, bits, false, &res, full_perm && m == n_dst));
     }
-    TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256)), 256, 0, st, idx[res], val[res], m, dst);
+    TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256 * SP_EPT)), 256, 0, st, idx[res], val[res], m, dst);
     prof_add_bytes("scatter_pairs_kernel", double(m) * 12);
     TDC_KCHECK();
     return 0;

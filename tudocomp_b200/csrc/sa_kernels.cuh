@@ -373,6 +373,7 @@ build_keys_kernel(const u32* __restrict__ idx, const u32* __restrict__ gid, cons
 // with probability about n * 2^(-H0 k), H0 = order-0 entropy of the byte histogram.  A wrong guess (text with
 // memory) only moves work between the two phases; the result is the same.
 static const double SA_ACTIVE_COST = 400.0;
+static const double SA_PACKED_ACTIVE_COST = 540.0;  // packed-vs-pairs decision, see choose_key_layout
 
 static u32 bits_of_lenfield(u32 k) { return bits_for_host(k); }
 
@@ -474,7 +475,10 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
             const double passes = double((kb + 7) / 8);
             double rounds_left;
             const double residue = residue_of(double(kb) / double(b), &rounds_left);
-            const double cost = passes * 16.0 - 8.0 + residue * SA_ACTIVE_COST * (1.0 + rounds_left);  // -8: no separate value array to re-rank
+            // measured (profiles/r2c_summary.md, dna 2^30): a keys-only pass takes 0.72 of a pair pass although it moves 0.67 of
+            // the bytes (both are issue bound), and a suffix left to the doubling rounds costs ~540 B of pair-pass time
+            // (round-2 sort, rank gather, re-rank, rank scatter, direct LCP of its slot)
+            const double cost = passes * 17.5 - 8.0 + residue * SA_PACKED_ACTIVE_COST * (1.0 + rounds_left);
             if (cost <= best_pcost) { best_pcost = cost; best_kb = kb; }
         }
     }
