@@ -23,7 +23,11 @@ for stage in "$@"; do
         python bench.py --steps 2 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
       echo "launches rc=$?" ;;
     sortbench)  # A/B of radix-pass variants built by: nvcc ... -D<flag> tools/sortbench.cu -o build/sortbench_<name>
-      { for b in build/sortbench_*; do echo "== $b"; timeout 120 $b 28 33 keys; done; timeout 120 build/sortbench_k16x4 28 48; } 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
+      { for b in build/sortbench_*; do echo "== $b"; timeout 120 $b ${SORT_LG:-28} 48; timeout 120 $b ${SORT_LG:-28} 33 keys; done; } 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
+    ncusort)  # `ncu --set full` of ONE full-size pair pass (deterministic: third onesweep launch of the micro-benchmark = second plain pass)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:rs_onesweep_kernel -s 2 -c 1 -o gpurun_out/${tag}_ncu_sortpass -f \
+        ${NCU_SORT_BIN:-build/sortbench_b_new} ${NCU_SORT_LG:-30} 48 > gpurun_out/${tag}_ncu_sortpass.log 2>&1
+      echo "ncusort rc=$?"; tail -2 gpurun_out/${tag}_ncu_sortpass.log ;;
     benchmodes)  # the initial-sort layouts side by side (resident timing only)
       for mode in wide packed; do
         TDCGPU_SA_MODE=$mode timeout 600 python bench.py --steps 5 --warmup 2 --no-dist --no-pipeline --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_$mode.json 2> gpurun_out/${tag}_bench_$mode.err

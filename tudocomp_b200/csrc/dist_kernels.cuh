@@ -31,6 +31,18 @@ struct OwnerFn {  // position-sharded arrays: owner = position / block, the owne
     __device__ __forceinline__ u32 out(u32 pos, u32 b) const { return pos - b * block; }
 };
 
+// lanes of the warp that hold the same bucket (< 16) and the same validity: 5 ballots instead of one per bucket
+__device__ __forceinline__ u32 bucket_peers(u32 b, bool valid) {
+    u32 peers = kFull;
+#pragma unroll
+    for (int bit = 0; bit < 4; bit++) {
+        const u32 bal = __ballot_sync(kFull, (b >> bit) & 1u);
+        peers &= ((b >> bit) & 1u) ? bal : ~bal;
+    }
+    const u32 balv = __ballot_sync(kFull, valid);
+    return peers & (valid ? balv : ~balv);
+}
+
 static const int BP_THREADS = 256;
 static const int BP_IPT = 8;
 static const int BP_TILE = BP_THREADS * BP_IPT;
@@ -43,11 +55,10 @@ bucket_count_kernel(const K* __restrict__ keys, u64 m, F f, int nbuckets, ull* _
     __syncthreads();
     const u64 m_round = (m + 31) & ~u64(31);
     for (u64 i = u64(blockIdx.x) * blockDim.x + threadIdx.x; i < m_round; i += u64(gridDim.x) * blockDim.x) {
-        const u32 b = i < m ? f.bucket(keys[i]) : 0xffffffffu;
-        for (int bb = 0; bb < nbuckets; bb++) {
-            const u32 mask = __ballot_sync(kFull, b == u32(bb));
-            if (lane_id() == 0 && mask) atomicAdd(&cnt[bb], u32(__popc(mask)));
-        }
+        const bool valid = i < m;
+        const u32 b = valid ? f.bucket(keys[i]) : 0u;
+        const u32 peers = bucket_peers(b, valid);  // one shared atomic per distinct bucket of the warp
+        if (valid && lane_id() == u32(__ffs(int(peers)) - 1)) atomicAdd(&cnt[b], u32(__popc(peers)));
     }
     __syncthreads();
     if (threadIdx.x < u32(nbuckets) && cnt[threadIdx.x]) atomicAdd(&gcount[threadIdx.x], ull(cnt[threadIdx.x]));
@@ -93,16 +104,16 @@ bucket_scatter_kernel(const K* __restrict__ keys, const u32* __restrict__ vals, 
 #pragma unroll
     for (int q = 0; q < BP_IPT; q++) {
         const u64 i = t0 + u64(q) * BP_THREADS + threadIdx.x;
-        key[q] = i < m ? keys[i] : K(0);
-        b[q] = i < m ? f.bucket(key[q]) : 0xffffffffu;
-        lr[q] = 0;
-        for (int bb = 0; bb < nbuckets; bb++) {
-            const u32 mask = __ballot_sync(kFull, b[q] == u32(bb));
-            u32 base = 0;
-            if (lane_id() == 0 && mask) base = atomicAdd(&cnt[bb], u32(__popc(mask)));
-            base = __shfl_sync(kFull, base, 0);
-            if (b[q] == u32(bb)) lr[q] = base + __popc(mask & lanemask_lt());
-        }
+        const bool valid = i < m;
+        key[q] = valid ? keys[i] : K(0);
+        b[q] = valid ? f.bucket(key[q]) : 0u;
+        // rank inside the tile's bucket: the first lane of every group of equal buckets reserves the group's slots
+        const u32 peers = bucket_peers(b[q], valid);
+        const u32 leader = u32(__ffs(int(peers)) - 1);
+        u32 base = 0;
+        if (valid && lane_id() == leader) base = atomicAdd(&cnt[b[q]], u32(__popc(peers)));
+        base = __shfl_sync(kFull, base, leader);
+        lr[q] = base + __popc(peers & lanemask_lt());
     }
     __syncthreads();
     if (threadIdx.x < u32(nbuckets)) gbase[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], ull(cnt[threadIdx.x])) : 0;

@@ -417,16 +417,23 @@ chain_exit_kernel(const u32* __restrict__ lenside, u32 n, u32* __restrict__ exit
     __syncthreads();
     while (true) {
         if (threadIdx.x == 0) changed = 0;
-        __syncthreads();
+        // read phase / write phase with a barrier in between: every hop reads the pointers of the previous round (the
+        // in-place version hopped through pointers other threads were rewriting — same fixed point, but a data race)
+        u32 nxt[CH_IPT];
         bool any = false;
-        for (u32 j = threadIdx.x; j < CH_TILE; j += CH_THREADS) {
-            const u32 t = J[j];
-            if (t < tile_end) {  // still inside: hop through the target's current pointer (always a node on j's path)
-                J[j] = J[t - base];
-                any = true;
-            }
+#pragma unroll
+        for (int q = 0; q < CH_IPT; q++) {
+            const u32 t = J[threadIdx.x + u32(q) * CH_THREADS];
+            const bool inside = t < tile_end;  // still inside: hop through the target's pointer (a node on j's path)
+            nxt[q] = inside ? J[t - base] : t;
+            any |= inside;
         }
-        if (any) changed = 1;
+        __syncthreads();
+        if (any) {
+            changed = 1;
+#pragma unroll
+            for (int q = 0; q < CH_IPT; q++) J[threadIdx.x + u32(q) * CH_THREADS] = nxt[q];
+        }
         __syncthreads();
         const bool again = changed != 0;
         __syncthreads();

@@ -144,14 +144,28 @@ static __global__ void __launch_bounds__(256) rs_scan_kernel(u32* __restrict__ g
 // ---------------------------------------------------------------------------------------------------------------
 // peers of this lane = lanes holding the same digit.  Eight ballots instead of match.any: MATCH is a slow-path
 // instruction on sm_100 (ncu: 43 % of the kernel's stall samples sat on its result), VOTE is full rate.
-__device__ __forceinline__ u32 match_digit(u32 d, u32 nbits_mask) {
+// All eight bits are always voted on: bits above a narrow digit are 0 in every lane and leave `peers` unchanged.  The
+// bit is tested ONCE into a predicate that feeds both the vote and the select — written as `(d >> b) & 1` in two places
+// the compiler emitted 8 instructions per bit (shift, and, compare for the vote; test, select, combine for the mask,
+// plus a uniform branch on the digit width): 64 of the kernel's ~143 instructions per key.  Now 4 per bit.
+__device__ __forceinline__ u32 match_digit(u32 d) {
     u32 peers = kFull;
 #pragma unroll
     for (int b = 0; b < 8; b++) {
-        if ((nbits_mask >> b) & 1u) {  // warp-uniform: digits of the last pass may be narrower than 8 bits
-            const u32 bal = __ballot_sync(kFull, (d >> b) & 1u);
-            peers &= ((d >> b) & 1u) ? bal : ~bal;
-        }
+#ifdef TDC_CUSIM
+        const bool bit = (d & (1u << b)) != 0u;
+        const u32 bal = __ballot_sync(kFull, bit);
+        peers &= bit ? bal : ~bal;
+#else
+        // test -> predicate, vote, select, combine: the C++ form of this compiled to 6-8 instructions per bit
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 t, bal, m;\n\t"
+            "and.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 bal, p, 0xffffffff;\n\t"
+            "selp.b32 m, 0, 0xffffffff, p;\n\t"
+            "xor.b32 bal, bal, m;\n\tand.b32 %0, %0, bal;\n\t}"
+            : "+r"(peers) : "r"(d), "r"(1u << b));
+#endif
     }
     return peers;
 }
@@ -206,11 +220,20 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     // ---- load (warp-striped: coalesced, and index order == (k, lane) order inside a warp) ----
     K key[IPT];
     u32 rank[IPT];
-    const u64 wbase = tile_base + u64(w) * (32 * IPT);
+    // tile-relative 32-bit indices; a full tile (all but the last) skips the per-element bounds checks, which were 6 of
+    // the 7 instructions per key of this load (64-bit compare + select)
+    const bool full = count == u32(TILE);
+    const K* __restrict__ kin_t = kin + tile_base;
+    const u32 wloc = w * (32 * IPT) + lane;  // this thread's first element inside the tile
+    if (full) {
 #pragma unroll
-    for (int k = 0; k < IPT; k++) {
-        const u64 idx = wbase + u32(k) * 32 + lane;
-        key[k] = idx < m ? kin[idx] : ~K(0);
+        for (int k = 0; k < IPT; k++) key[k] = kin_t[wloc + u32(k) * 32];
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const u32 loc = wloc + u32(k) * 32;
+            key[k] = loc < count ? kin_t[loc] : ~K(0);
+        }
     }
     u32* my_cnt = warp_cnt + w * RS_RADIX;
 #pragma unroll
@@ -220,7 +243,7 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const u32 d = u32(key[k] >> shift) & mask;
-        const u32 peers = match_digit(d, mask);
+        const u32 peers = match_digit(d);
         const u32 before = __popc(peers & lanemask_lt());
 #ifdef RS_RANK_ATOMIC
         // the group's first lane reserves the group's slots in the warp's counter and hands the old count to its peers
@@ -297,29 +320,45 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
     __syncthreads();
 
     // ---- stage in shared memory in digit order ----
+    const u32* __restrict__ vin_t = (IOTA || KEYSONLY) ? nullptr : vin + tile_base;
+    u32 val[KEYSONLY ? 1 : IPT];
+    if (!KEYSONLY) {  // all value loads of the thread are issued before the first dependent shared-memory store
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const u32 loc = wloc + u32(k) * 32;
+#ifdef RS_VALS_ASYNC
+            val[k] = IOTA ? u32(tile_base) + loc : svals_in[loc];
+#else
+            val[k] = IOTA ? u32(tile_base) + loc : ((full || loc < count) ? vin_t[loc] : 0u);  // (prefetching these before the look-back measured 20 % slower)
+#endif
+        }
+    }
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const u32 d = u32(key[k] >> shift) & mask;
         const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
-        const u64 idx = wbase + u32(k) * 32 + lane;
-        skeys[p] = key[k];
-        if (!KEYSONLY) {
-#ifdef RS_VALS_ASYNC
-            if (idx < m) svals[p] = IOTA ? u32(idx) : svals_in[u32(idx - tile_base)];
-#else
-            if (idx < m) svals[p] = IOTA ? u32(idx) : vin[idx];  // (prefetching these before the look-back measured 20 % slower)
-#endif
-        }
+        skeys[p] = key[k];  // (padding keys of the partial last tile land behind `count` in the top bin and are never written out)
+        if (!KEYSONLY) svals[p] = val[k];
     }
     __syncthreads();
 
     // ---- coalesced runs out ----
-    for (u32 j = tid; j < count; j += RS_THREADS) {
-        const K kk = skeys[j];
-        const u32 d = u32(kk >> shift) & mask;
-        const u64 o = u64(gbase[d] + j);
-        kout[o] = kk;
-        if (!KEYSONLY) vout[o] = svals[j];
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const u32 j = tid + u32(k) * RS_THREADS;
+            const K kk = skeys[j];
+            const u32 o = gbase[u32(kk >> shift) & mask] + j;
+            kout[o] = kk;
+            if (!KEYSONLY) vout[o] = svals[j];
+        }
+    } else {
+        for (u32 j = tid; j < count; j += RS_THREADS) {
+            const K kk = skeys[j];
+            const u32 o = gbase[u32(kk >> shift) & mask] + j;
+            kout[o] = kk;
+            if (!KEYSONLY) vout[o] = svals[j];
+        }
     }
 }
 
