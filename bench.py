@@ -27,9 +27,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# the image sets NCCL_DEBUG=VERSION, which makes NCCL print a banner on STDOUT next to the one JSON line
+# the image sets NCCL_DEBUG=VERSION, which makes NCCL print a banner on STDOUT next to the one JSON line (WARN prints it
+# too: the banner's level is below WARN); whatever NCCL still has to say goes to stderr
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.pop("NCCL_DEBUG", None)
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 METRIC = "input MB/s for SA+LCP+lzss_lcp factorization"
 THRESHOLD = 3

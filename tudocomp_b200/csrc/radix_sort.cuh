@@ -178,48 +178,24 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
                    u64 m, u32 shift, u32 mask, const u32* __restrict__ bucket_start, ull* __restrict__ desc, u32 epoch) {
     constexpr int IPT = RsOcc<K, KEYSONLY>::IPT;
     constexpr int TILE = RS_THREADS * IPT;
+    static_assert(TILE <= 65536, "tile-local ranks are kept in 16 bits");
     TDC_DYN_SMEM(smem_raw);
     K* skeys = reinterpret_cast<K*>(smem_raw);                                  // TILE keys
     u32* svals = reinterpret_cast<u32*>(smem_raw + sizeof(K) * TILE);           // TILE values (absent when KEYSONLY)
     u32* warp_cnt = svals + (KEYSONLY ? 0 : TILE);                              // [RS_WARPS][256]
-    u32* digit_start = warp_cnt + RS_WARPS * RS_RADIX;                          // [256]
-    u32* gbase = digit_start + RS_RADIX;                                        // [256]
+    u32* gbase = warp_cnt + RS_WARPS * RS_RADIX;                                // [256] (+ 256 spare words)
     u32* misc = gbase + RS_RADIX;                                               // [40]: scan scratch
-#ifdef RS_VALS_ASYNC
-    u32* svals_in = misc + 40;                                                  // TILE incoming values (tile order)
-#endif
 
     const u32 tid = threadIdx.x, lane = lane_id(), w = warp_id();
     const u32 tile = blockIdx.x;
     const u64 tile_base = u64(tile) * TILE;
     const u32 count = u32(min(u64(TILE), m - tile_base));
 
-#ifdef RS_VALS_ASYNC
-    // EXPERIMENT (off by default, A/B with tools/sortbench.cu -DRS_VALS_ASYNC): the tile's values start travelling to
-    // shared memory right away with cp.async — no registers held across the ranking and the look-back (prefetching them
-    // into registers measured 20 % slower), and the staging step below finds them on chip instead of paying a second
-    // exposed global-load latency per tile.  16-byte chunks; the partial last tile clamps the source size (zero fill).
-    if (!IOTA && !KEYSONLY) {
-        for (u32 c16 = tid; c16 < u32(TILE / 4); c16 += RS_THREADS) {
-            const u32 e0 = c16 * 4;
-            if (e0 < count) {
-#ifdef TDC_CUSIM
-                for (u32 e = e0; e < min(e0 + 4, count); e++) svals_in[e] = vin[tile_base + e];
-#else
-                const u32 bytes = min(16u, (count - e0) * 4u);
-                const u32 dst = u32(__cvta_generic_to_shared(svals_in + e0));
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(vin + tile_base + e0), "r"(bytes) : "memory");
-#endif
-            }
-        }
-#ifndef TDC_CUSIM
-        asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
-    }
-#endif
     // ---- load (warp-striped: coalesced, and index order == (k, lane) order inside a warp) ----
     K key[IPT];
-    u32 rank[IPT];
+    u32 rank2[(IPT + 1) / 2];  // tile-local ranks (< TILE <= 65536), two per register: 8 registers less across the look-back
+#pragma unroll
+    for (int k = 0; k < (IPT + 1) / 2; k++) rank2[k] = 0;
     // tile-relative 32-bit indices; a full tile (all but the last) skips the per-element bounds checks, which were 6 of
     // the 7 instructions per key of this load (64-bit compare + select)
     const bool full = count == u32(TILE);
@@ -256,33 +232,50 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         if (before == 0) my_cnt[d] = c + __popc(peers);
         __syncwarp();
 #endif
-        rank[k] = c + before;
+        rank2[k >> 1] |= (c + before) << (16 * (k & 1));
     }
+    const u32* __restrict__ vin_t = (IOTA || KEYSONLY) ? nullptr : vin + tile_base;
+    u32 val[KEYSONLY ? 1 : IPT];
+    // all value loads of the thread are issued before the first dependent shared-memory store
+#define RS_LOAD_VALS()                                                                                         \
+    if (!KEYSONLY) {                                                                                           \
+        _Pragma("unroll") for (int k = 0; k < IPT; k++) {                                                      \
+            const u32 loc = wloc + u32(k) * 32;                                                                \
+            val[k] = IOTA ? u32(tile_base) + loc : ((full || loc < count) ? vin_t[loc] : 0u);                  \
+        }                                                                                                      \
+    }
+#ifdef RS_VALS_EARLY
+    RS_LOAD_VALS();  // EXPERIMENT: the value loads travel while the per-digit section runs
+#endif
     __syncthreads();
 
-    // ---- per-digit totals, warp offsets, tile-local digit starts ----
-    u32 total = 0;
+    // ---- per-digit totals, tile-local digit starts, warp offsets ----
+    u32 total = 0, pub = 0;
     if (tid < RS_RADIX) {
-        u32 run = 0;
 #pragma unroll
-        for (int ww = 0; ww < RS_WARPS; ww++) {
-            const u32 t = warp_cnt[ww * RS_RADIX + tid];
-            warp_cnt[ww * RS_RADIX + tid] = run;
-            run += t;
-        }
-        total = run;
+        for (int ww = 0; ww < RS_WARPS; ww++) total += warp_cnt[ww * RS_RADIX + tid];
         // publish the tile's count of this digit as early as possible (successors are waiting on it)
-        u32 pub = total;
+        pub = total;
         if (tid == mask) pub -= (u32(TILE) - count);  // padding keys (~0) sit in the top bin and are never written
         if (tile != 0) desc_store(desc + u64(tile) * RS_RADIX + tid, (ull(epoch) << 34) | (RS_STATUS_AGG << 32) | pub);
     }
     u32 blk_total;
     const u32 ex = block_exclusive_sum<u32>(total, misc, &blk_total);  // threads >= 256 contribute 0
     if (tid < RS_RADIX) {
-        digit_start[tid] = ex;
-        u32 pub = total;
-        if (tid == mask) pub -= (u32(TILE) - count);
-        // ---- decoupled look-back for digit `tid` ----
+        // warp_cnt[w][d] := tile-local position of warp w's first key with digit d (digit start + keys of earlier warps):
+        // the staging loop then needs ONE random shared-memory read per key instead of two (ncu: 16 of the kernel's 28
+        // shared-memory wavefronts per 32 keys were in that loop, l1tex was the busiest unit at 66 %)
+        u32 run = ex;
+#pragma unroll
+        for (int ww = 0; ww < RS_WARPS; ww++) {
+            const u32 t = warp_cnt[ww * RS_RADIX + tid];
+            warp_cnt[ww * RS_RADIX + tid] = run;
+            run += t;
+        }
+    }
+    // ---- decoupled look-back for digit `tid` ----
+    auto lookback = [&]() {
+        if (tid >= RS_RADIX) return;
         const ull tag = ull(epoch) << 34;
         ull* my_desc = desc + u64(tile) * RS_RADIX + tid;
         u32 exclusive = 0;
@@ -313,33 +306,30 @@ rs_onesweep_kernel(const K* __restrict__ kin, K* __restrict__ kout, const u32* _
         }
         desc_store(my_desc, tag | (RS_STATUS_PREFIX << 32) | ull(exclusive + pub));
         gbase[tid] = bucket_start[tid] + exclusive - ex;
-    }
-#if defined(RS_VALS_ASYNC) && !defined(TDC_CUSIM)
-    if (!IOTA && !KEYSONLY) asm volatile("cp.async.wait_all;" ::: "memory");  // this thread's chunks have landed; the barrier publishes them
+    };
+#ifdef RS_EARLY_LOOKBACK
+    lookback();  // (the round-1 order: A/B only)
 #endif
     __syncthreads();
 
     // ---- stage in shared memory in digit order ----
-    const u32* __restrict__ vin_t = (IOTA || KEYSONLY) ? nullptr : vin + tile_base;
-    u32 val[KEYSONLY ? 1 : IPT];
-    if (!KEYSONLY) {  // all value loads of the thread are issued before the first dependent shared-memory store
-#pragma unroll
-        for (int k = 0; k < IPT; k++) {
-            const u32 loc = wloc + u32(k) * 32;
-#ifdef RS_VALS_ASYNC
-            val[k] = IOTA ? u32(tile_base) + loc : svals_in[loc];
-#else
-            val[k] = IOTA ? u32(tile_base) + loc : ((full || loc < count) ? vin_t[loc] : 0u);  // (prefetching these before the look-back measured 20 % slower)
+#ifndef RS_VALS_EARLY
+    RS_LOAD_VALS();
 #endif
-        }
-    }
 #pragma unroll
     for (int k = 0; k < IPT; k++) {
         const u32 d = u32(key[k] >> shift) & mask;
-        const u32 p = digit_start[d] + warp_cnt[w * RS_RADIX + d] + rank[k];
+        const u32 p = warp_cnt[w * RS_RADIX + d] + ((rank2[k >> 1] >> (16 * (k & 1))) & 0xffffu);
         skeys[p] = key[k];  // (padding keys of the partial last tile land behind `count` in the top bin and are never written out)
         if (!KEYSONLY) svals[p] = val[k];
     }
+#ifndef RS_EARLY_LOOKBACK
+    // The look-back runs AFTER the staging: the predecessors have had the time of this tile's value loads and
+    // shared-memory scatter to publish, so far fewer polls (look-back first: 28 % of the kernel's stall samples and 23 % of
+    // its executed instructions were descriptor polling, profiles/r2e_ncu_sortpass_summary.md; 2.09 -> 1.96 ms per pass at
+    // 2^28 pairs).  The global offsets are only needed by the write-out below.
+    lookback();
+#endif
     __syncthreads();
 
     // ---- coalesced runs out ----
@@ -377,9 +367,6 @@ template <class K>
 static inline size_t rs_smem_bytes(bool keysonly = false) {
     const int TILE = RS_THREADS * (keysonly ? RsOcc<u64, true>::IPT : RsCfg<K>::IPT);
     size_t bytes = sizeof(K) * TILE + (keysonly ? 0 : 4 * TILE) + 4 * (RS_WARPS * RS_RADIX + 2 * RS_RADIX + 40);
-#ifdef RS_VALS_ASYNC
-    if (!keysonly) bytes += 4 * TILE;
-#endif
     return bytes;
 }
 template <class K>
