@@ -132,10 +132,27 @@ int tdcgpu_lzss_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst,
 /* Page-locked host memory for caller-side staging buffers (cudaMallocHost / cudaFreeHost); NULL on failure. */
 void* tdcgpu_pinned_alloc(uint64_t bytes);
 void tdcgpu_pinned_free(void* p);
+/* Device of the calling thread for the context-free calls above (a block-mode worker pins its block buffers on the
+ * device it was dealt, tudocomp_b200/plugin/tdc_block.cpp, instead of opening a context on device 0). */
+int tdcgpu_set_device(int device);
+
+/* Plain device memory on the context's device (cudaMalloc / cudaFree), for callers that keep a byte stream in HBM
+ * between two stages (the GPU-aware chain of the plugin, tudocomp_gpu/GpuStreamStages.hpp, which replaces the host
+ * buffer of tudocomp_driver/ChainCompressor.hpp:54-62).  NULL on failure. */
+void* tdcgpu_device_alloc(tdcgpu_ctx* ctx, uint64_t bytes);
+void tdcgpu_device_free(tdcgpu_ctx* ctx, void* p); /* ctx may be NULL */
+/* Blocking copy on the context's stream; kind: 0 host -> device, 1 device -> host (pageable host memory is staged through
+ * pinned buffers like every other transfer of the ABI), 2 device -> device. */
+int tdcgpu_device_copy(tdcgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind);
 
 /* ---- byte-stream stages behind the BWT in `bwt:mtf:rle:encode(huff)` (BASELINE config 3) -------------------------
  * Stateless with respect to the text index: they only use the context's stream and a scratch buffer of their own.
- * on_device != 0: in/out are device pointers on the context's device; otherwise host pointers.
+ * on_device says where the caller's `in` / `out` buffers are (device pointers are on the context's device): */
+#define TDCGPU_BUF_HOST 0       /* both host */
+#define TDCGPU_BUF_DEVICE 1     /* both device */
+#define TDCGPU_BUF_OUT_DEVICE 2 /* in host, out device (first stage of a device-resident chain) */
+#define TDCGPU_BUF_IN_DEVICE 3  /* in device, out host (last stage) */
+/*
  *
  * mtf_encode (compressors/MTFCompressor.hpp:46-56): out[i] = index of in[i] in the move-to-front table (initially
  * 0..255) before it is moved to the front; n bytes out. */

@@ -72,6 +72,21 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
             r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", b, "--force"], capture_output=True, text=True, env=env)
             assert r.returncode == 0, (name, algo, r.stderr)
             assert open(a, "rb").read() == open(b, "rb").read(), (name, algo)
+    # the GPU-aware chain (GpuChainCompressor.hpp): host-only stages in the middle / at either end of a chain take the
+    # fallback routes (download for a host stage, host buffer between two host stages, upload of a host stage's output),
+    # and the reference's all-host route (TDCGPU_HOST_CHAIN=1) gives the same bytes as the device-resident one
+    src = tmp_path / "markov.bin"
+    for algo in ("bwt:noop:mtf:encode(huff)", "noop:mtf:noop:rle:noop", "mtf:encode(ascii):rle", "bwt:mtf:rle:encode(huff)"):
+        a, b, c = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc"), str(tmp_path / "simh.tdc")
+        assert _run(REF, algo, str(src), a).returncode == 0
+        r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", b, "--force"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, (algo, r.stderr)
+        r = subprocess.run([GPU_ONLY, "-a", algo, str(src), "-o", c, "--force"], capture_output=True, text=True, env=dict(env, TDCGPU_HOST_CHAIN="1"))
+        assert r.returncode == 0, (algo, r.stderr)
+        assert open(a, "rb").read() == open(b, "rb").read() == open(c, "rb").read(), algo
+        back = str(tmp_path / "back.bin")
+        r = subprocess.run([GPU_ONLY, "-d", b, "-o", back, "--force"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and open(back, "rb").read() == src.read_bytes(), (algo, r.stderr)
     # lcpcomp: the reference's own strategies consume the GPU text index through require_* / release_*
     # (arrays come back bit-packed by the device, compress=delayed); mixed registry, so compare under --raw
     for name in ("markov", "empty"):

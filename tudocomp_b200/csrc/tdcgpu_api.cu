@@ -507,6 +507,36 @@ void* tdcgpu_pinned_alloc(uint64_t bytes) {
 void tdcgpu_pinned_free(void* p) {
     if (p) cudaFreeHost(p);
 }
+void* tdcgpu_device_alloc(tdcgpu_ctx* ctx, uint64_t bytes) {
+    if (!ctx) { set_error("null context"); return nullptr; }
+    void* p = nullptr;
+    if (cudaSetDevice(ctx->c.device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("device allocation of %llu bytes failed", (unsigned long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+void tdcgpu_device_free(tdcgpu_ctx* ctx, void* p) {
+    if (!p) return;
+    if (ctx) cudaSetDevice(ctx->c.device);
+    cudaFree(p);
+}
+int tdcgpu_device_copy(tdcgpu_ctx* ctx, void* dst, const void* src, uint64_t bytes, int kind) {
+    API_GUARD(ctx);
+    if (bytes == 0) return 0;
+    if (!dst || !src || kind < 0 || kind > 2) { set_error("device_copy: bad argument"); return TDCGPU_ERR_ARG; }
+    if (kind == 2) {
+        TDC_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c.stream));
+        TDC_CUDA(cudaStreamSynchronize(c.stream));
+        return 0;
+    }
+    return host_copy(c, dst, src, bytes, kind == 0);
+}
+int tdcgpu_set_device(int device) {
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); set_error("cannot select device %d", device); return TDCGPU_ERR_CUDA; }
+    return 0;
+}
 
 int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int finalize, uint64_t* nbytes, int to_device) {
     API_GUARD(ctx);
@@ -514,15 +544,27 @@ int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int fina
     return copy_bitstream_out(c, c.enc.out, c.enc.nbits, dst, cap, finalize, nbytes, to_device);
 }
 
-// in/out staging of the stream stages: [in (n) | out (out_cap) | scratch]
+// where the caller's in / out buffers of a stream stage live (include/tdcgpu.h: TDCGPU_BUF_*)
+static inline bool in_on_device(int on_device) { return on_device == TDCGPU_BUF_DEVICE || on_device == TDCGPU_BUF_IN_DEVICE; }
+static inline bool out_on_device(int on_device) { return on_device == TDCGPU_BUF_DEVICE || on_device == TDCGPU_BUF_OUT_DEVICE; }
+
+// in/out staging of the stream stages: [in (n) | out (out_cap) | scratch]; a side that already is on the device is used in place
 static int stream_stage_in(Ctx& c, const uint8_t* in, u64 n, u64 out_cap, size_t scratch, int on_device, const uint8_t** d_in, uint8_t** d_out) {
-    TDC_TRY(stream_arena_reserve(c, size_t(on_device ? 0 : n + out_cap + 512) + scratch + 4096));
-    if (on_device) { *d_in = in; return 0; }
-    uint8_t* di = c.stream_arena.take<uint8_t>(n + 16);
-    *d_out = c.stream_arena.take<uint8_t>(out_cap + 16);
-    if (!di || !*d_out) { set_error("stream scratch too small"); return TDCGPU_ERR_NOMEM; }
-    if (n) TDC_TRY(host_copy(c, di, in, n, true));
-    *d_in = di;
+    if (on_device < 0 || on_device > 3) { set_error("bad on_device value %d", on_device); return TDCGPU_ERR_ARG; }
+    const bool ind = in_on_device(on_device), outd = out_on_device(on_device);
+    TDC_TRY(stream_arena_reserve(c, size_t(ind ? 0 : n + 256) + size_t(outd ? 0 : out_cap + 256) + scratch + 4096));
+    if (ind) {
+        *d_in = in;
+    } else {
+        uint8_t* di = c.stream_arena.take<uint8_t>(n + 16);
+        if (!di) { set_error("stream scratch too small"); return TDCGPU_ERR_NOMEM; }
+        if (n) TDC_TRY(host_copy(c, di, in, n, true));
+        *d_in = di;
+    }
+    if (!outd) {
+        *d_out = c.stream_arena.take<uint8_t>(out_cap + 16);
+        if (!*d_out) { set_error("stream scratch too small"); return TDCGPU_ERR_NOMEM; }
+    }
     return 0;
 }
 
@@ -538,7 +580,7 @@ int tdcgpu_mtf_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint8_t* o
         PhaseTimer t(c, "MTF");
         TDC_TRY(mtf_encode_device(c, d_in, n, d_out));
     }
-    if (!on_device) TDC_TRY(host_copy(c, out, d_out, n, false));
+    if (!out_on_device(on_device)) TDC_TRY(host_copy(c, out, d_out, n, false));
     TDC_CUDA(cudaStreamSynchronize(c.stream));
     return 0;
 }
@@ -551,7 +593,8 @@ int tdcgpu_rle_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t o
     if (!in || !out) { set_error("null buffer"); return TDCGPU_ERR_ARG; }
     c.phases.clear();
     const u64 worst = rle_max_output(n, offset);
-    if (on_device && cap < worst) { set_error("rle: a device output buffer must hold the worst case (%llu bytes)", (unsigned long long)worst); return TDCGPU_ERR_ARG; }
+    const bool outd = out_on_device(on_device);
+    if (outd && cap < worst) { set_error("rle: a device output buffer must hold the worst case (%llu bytes)", (unsigned long long)worst); return TDCGPU_ERR_ARG; }
     const uint8_t* d_in = nullptr;
     uint8_t* d_out = out;
     TDC_TRY(stream_stage_in(c, in, n, worst, rle_scratch_bytes(n), on_device, &d_in, &d_out));
@@ -561,7 +604,7 @@ int tdcgpu_rle_encode(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, uint64_t o
         TDC_TRY(rle_encode_device(c, d_in, n, offset, d_out, &produced));
     }
     if (out_n) *out_n = produced;
-    if (!on_device) {
+    if (!outd) {
         if (produced > cap) { set_error("rle: output buffer too small: %llu > %llu", (unsigned long long)produced, (unsigned long long)cap); return TDCGPU_ERR_ARG; }
         TDC_TRY(host_copy(c, out, d_out, produced, false));
     }
@@ -577,7 +620,7 @@ int tdcgpu_literal_encode_begin(tdcgpu_ctx* ctx, const uint8_t* in, uint64_t n, 
     c.lit.staged = c.lit.encoded = false;
     const uint8_t* d_in = nullptr;
     uint8_t* d_unused = nullptr;
-    TDC_TRY(stream_stage_in(c, in, n, 0, literal_scratch_bytes(n), on_device, &d_in, &d_unused));
+    TDC_TRY(stream_stage_in(c, in, n, 0, literal_scratch_bytes(n), on_device ? TDCGPU_BUF_DEVICE : TDCGPU_BUF_HOST, &d_in, &d_unused));
     {
         PhaseTimer t(c, "Literal histogram");
         TDC_TRY(stream_histogram_device(c, d_in, n, hist));

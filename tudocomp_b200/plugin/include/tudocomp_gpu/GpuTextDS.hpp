@@ -157,6 +157,64 @@ inline uint64_t strip_bitstream_tail(std::vector<uint8_t>& bytes) {
     return bits;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Device-resident chains.  tudocomp_driver/ChainCompressor.hpp:54-62 hands a host vector from stage to stage, so every GPU
+// stage of `bwt:mtf:rle:encode(huff)` would cross PCIe twice.  A GPU compressor additionally implements DeviceStage; the
+// GPU-aware chain (tudocomp_gpu/GpuChainCompressor.hpp) then keeps the bytes between two such stages in HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+struct DeviceBytes {  // a byte stream in device memory, owned by this object
+    uint8_t* p = nullptr;
+    uint64_t n = 0, cap = 0;
+    DeviceBytes() = default;
+    DeviceBytes(const DeviceBytes&) = delete;
+    DeviceBytes& operator=(const DeviceBytes&) = delete;
+    ~DeviceBytes() { reset(); }
+    void reset() {
+        if (p) tdcgpu_device_free(nullptr, p);
+        p = nullptr;
+        n = cap = 0;
+    }
+    void alloc(tdcgpu_ctx* ctx, uint64_t bytes) {
+        reset();
+        p = static_cast<uint8_t*>(tdcgpu_device_alloc(ctx, bytes));
+        if (!p) throw std::runtime_error(std::string("tdcgpu: device_alloc: ") + tdcgpu_last_error());
+        cap = bytes;
+    }
+};
+
+struct StageInput {  // exactly one of the two is set
+    Input* host = nullptr;
+    const DeviceBytes* dev = nullptr;
+};
+
+struct StreamCtx {  // one context (stream + scratch) for the duration of a call
+    tdcgpu_ctx* ctx = nullptr;
+    StreamCtx() : ctx(acquire_ctx()) {}
+    ~StreamCtx() { release_ctx(ctx); }
+    StreamCtx(const StreamCtx&) = delete;
+    StreamCtx& operator=(const StreamCtx&) = delete;
+};
+inline void download(const DeviceBytes& d, std::vector<uint8_t>& out) {
+    out.resize(d.n);
+    if (!d.n) return;
+    StreamCtx g;
+    check(tdcgpu_device_copy(g.ctx, out.data(), d.p, d.n, 1), "device_copy");
+}
+inline void upload(DeviceBytes& d, const std::vector<uint8_t>& in) {
+    StreamCtx g;
+    d.alloc(g.ctx, in.size());
+    d.n = in.size();
+    if (!in.empty()) check(tdcgpu_device_copy(g.ctx, d.p, in.data(), in.size(), 0), "device_copy");
+}
+
+class DeviceStage {
+public:
+    virtual ~DeviceStage() = default;
+    /// The stage's compress() with its input in `in` and its output in `dev_out` (device-resident, for the next GPU stage)
+    /// if that is non-null, else in `host_out`.  Same bytes as compress(Input&, Output&).
+    virtual void compress_stage(const StageInput& in, DeviceBytes* dev_out, Output* host_out) = 0;
+};
+
 /// Page-locked staging buffer of the C ABI (falls back to pageable memory, which the ABI stages itself).
 struct PinnedBuffer {
     uint8_t* data;
@@ -399,7 +457,7 @@ public:
 // bwt with the device gather (compressors/BWTCompressor.hpp:29-47).  decompress is the reference's.
 // ---------------------------------------------------------------------------------------------------------------------
 template <>
-class BWTCompressor<GpuTextDS> : public Compressor {
+class BWTCompressor<GpuTextDS> : public Compressor, public gpu_detail::DeviceStage {
     using text_t = GpuTextDS;
 
 public:
@@ -413,10 +471,28 @@ public:
     using Compressor::Compressor;
 
     inline virtual void compress(Input& input, Output& output) override {
-        auto ostream = output.as_stream();
-        auto in = input.as_view();
+        gpu_detail::StageInput in;
+        in.host = &input;
+        compress_stage(in, nullptr, &output);
+    }
+
+    /// The BWT stays in device memory when the next stage of a chain runs on the GPU as well (dev_out != nullptr).
+    inline void compress_stage(const gpu_detail::StageInput& sin, gpu_detail::DeviceBytes* dev_out, Output* host_out) override {
+        if (!sin.host) throw std::runtime_error("bwt: the text index is built from a host text");
+        auto in = sin.host->as_view();
         DCHECK(in.ends_with(uint8_t(0)));
         text_t t(env().env_for_option("textds"), in);
+        if (dev_out) {
+            StatPhase::wrap("Construct Text DS", [&] {
+                gpu_detail::check(tdcgpu_textds_build(t.device(), TDCGPU_SA | TDCGPU_BWT), "bwt");
+                gpu_detail::log_phases(t.device());
+                dev_out->alloc(t.device(), t.size());
+                gpu_detail::check(tdcgpu_textds_get(t.device(), TDCGPU_BWT, dev_out->p, 1), "bwt");
+                dev_out->n = t.size();
+            });
+            return;
+        }
+        auto ostream = host_out->as_stream();
         std::string bwt(t.size(), 0);
         StatPhase::wrap("Construct Text DS", [&] {
             gpu_detail::check(tdcgpu_textds_build(t.device(), TDCGPU_SA | TDCGPU_BWT), "bwt");

@@ -79,7 +79,9 @@ tdc.compressors = lcpcomp + stream_stages + [
     AlgorithmConfig(name="LZSSLCPCompressor", header="compressors/LZSSLCPCompressor.hpp", sub=[coders, textds]),
     AlgorithmConfig(name="NoopCompressor", header="compressors/NoopCompressor.hpp"),
     AlgorithmConfig(name="BWTCompressor", header="compressors/BWTCompressor.hpp", sub=[textds]),
-    AlgorithmConfig(name="ChainCompressor", header="../tudocomp_driver/ChainCompressor.hpp"),
+    # `a:b` = chain(a, b): the GPU-only registry keeps the bytes between two GPU stages in device memory
+    (AlgorithmConfig(name="GpuChainCompressor", header="../tudocomp_gpu/GpuChainCompressor.hpp") if mode == "only" else
+     AlgorithmConfig(name="ChainCompressor", header="../tudocomp_driver/ChainCompressor.hpp")),
 ]
 
 tdc.generators = [

@@ -12,6 +12,8 @@
 //
 // Container: "TDCBLOCK1\n", u64 block_bytes, u64 nblocks, u32 algo_len, algo string, then per block u64 archive_len and
 // the raw archive.  All integers little-endian.
+#include <fcntl.h>
+#include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
@@ -22,13 +24,21 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <future>
+#include <memory>
+#include <streambuf>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <tudocomp/Compressor.hpp>
 #include <tudocomp/io.hpp>
 #include <tudocomp_driver/Registry.hpp>
 #include <tudocomp_stat/StatPhase.hpp>
+
+#ifdef TDC_GPU_DEFAULT_TEXTDS
+#include "tdcgpu.h"  // pinned block buffers: the text goes to the device by DMA straight from where the file was read
+#endif
 
 using namespace tdc;
 
@@ -56,19 +66,97 @@ uint64_t get_u64(const uint8_t*& p, const uint8_t* end) {
     return v;
 }
 
+// ---- host side of a worker -----------------------------------------------------------------------------------------
+// A block costs the GPU tens of milliseconds, so the worker's host work decides the throughput (first version: the whole
+// file in a vector, the reference's byte-wise escaping pass and byte-wise in-memory Output per block, archive re-read by
+// the parent: 1.7 s per 256 MiB block, profiles/r2d_block_mode_2GiB_1gpu.txt).  Now: block b+1 is read (pread) into a
+// second buffer while block b is compressed, a block without 0x00 / 0xFF bytes is handed over as a sentinel-terminated
+// View (what the restricted Input would have produced, without its copy and byte loops), the archive is collected through
+// a streambuf that appends whole chunks, and a writer thread stores it while the next block is compressed.
+struct BlockBuffer {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool pinned = false;
+    explicit BlockBuffer(size_t n) : cap(n) {
+#ifdef TDC_GPU_DEFAULT_TEXTDS
+        p = static_cast<uint8_t*>(tdcgpu_pinned_alloc(n));
+        pinned = p != nullptr;
+#endif
+        if (!p) p = static_cast<uint8_t*>(std::malloc(n));
+        if (!p) throw std::bad_alloc();
+    }
+    ~BlockBuffer() {
+#ifdef TDC_GPU_DEFAULT_TEXTDS
+        if (pinned) { tdcgpu_pinned_free(p); return; }
+#endif
+        std::free(p);
+    }
+    BlockBuffer(const BlockBuffer&) = delete;
+    BlockBuffer& operator=(const BlockBuffer&) = delete;
+};
+
+struct LoadedBlock {
+    size_t len = 0;
+    bool clean = false;  // no byte that the driver's input restrictions would escape
+};
+
+LoadedBlock load_block(int fd, uint64_t from, size_t len, BlockBuffer& buf) {
+    size_t got = 0;
+    while (got < len) {
+        const ssize_t r = pread(fd, buf.p + got, len - got, off_t(from + got));
+        if (r <= 0) throw std::runtime_error("cannot read the input");
+        got += size_t(r);
+    }
+    LoadedBlock lb;
+    lb.len = len;
+    lb.clean = std::memchr(buf.p, 0x00, len) == nullptr && std::memchr(buf.p, 0xFF, len) == nullptr;
+    buf.p[len] = 0;  // the sentinel of the clean path (the buffer holds block + 1 bytes)
+    return lb;
+}
+
+class AppendBuf : public std::streambuf {
+    std::vector<uint8_t>& v_;
+
+public:
+    explicit AppendBuf(std::vector<uint8_t>& v) : v_(v) {}
+
+protected:
+    std::streamsize xsputn(const char* s, std::streamsize n) override {
+        v_.insert(v_.end(), reinterpret_cast<const uint8_t*>(s), reinterpret_cast<const uint8_t*>(s) + n);
+        return n;
+    }
+    int_type overflow(int_type c) override {
+        if (c != traits_type::eof()) v_.push_back(uint8_t(c));
+        return c;
+    }
+};
+
 // one block through the registry, exactly as the driver runs a whole file
-std::vector<uint8_t> compress_block(const std::string& algo, const uint8_t* data, size_t len) {
+std::vector<uint8_t> compress_block(const std::string& algo, const uint8_t* data, size_t len, bool sentinel_follows) {
     auto& registry = tdc_algorithms::COMPRESSOR_REGISTRY;
     auto av = registry.parse_algorithm_id(algo);
     auto restrictions = av.textds_flags();
     auto compressor = registry.select_algorithm(av);
     std::vector<uint8_t> arc;
+    arc.reserve(len / 2 + 4096);
     {
         StatPhase root("root");
-        Input inp(View(data, len));
-        if (restrictions.has_restrictions()) inp = Input(inp, restrictions);
-        Output out = Output::from_memory(arc);
-        compressor->compress(inp, out);
+        AppendBuf sb(arc);
+        std::ostream os(&sb);
+        Output out = Output::from_stream(os);
+        // restrictions {escape 0, append sentinel} on a block without 0x00 / 0xFF bytes = the same bytes + one 0
+        // (io/EscapeMap.hpp:39-64, io/RestrictedBuffer.hpp:108-140): hand that View over directly
+        const bool direct = sentinel_follows && restrictions.has_restrictions() && restrictions.null_terminate() &&
+                            restrictions.escape_bytes() == std::vector<uint8_t>{0};
+        if (direct) {
+            Input inp(View(data, len + 1));
+            compressor->compress(inp, out);
+        } else {
+            Input inp(View(data, len));
+            if (restrictions.has_restrictions()) inp = Input(inp, restrictions);
+            compressor->compress(inp, out);
+        }
+        os.flush();
     }
     return arc;
 }
@@ -142,47 +230,91 @@ int main(int argc, char** argv) {
             }
             return 0;
         }
-        const std::vector<uint8_t> data = read_file(input);
-        const uint64_t nblocks = (data.size() + block - 1) / block;
+        const int fd = open(input.c_str(), O_RDONLY);
+        if (fd < 0) throw std::runtime_error("cannot open " + input);
+        struct stat sb;
+        if (fstat(fd, &sb) != 0) throw std::runtime_error("cannot stat " + input);
+        const uint64_t in_size = uint64_t(sb.st_size);
+        const uint64_t nblocks = (in_size + block - 1) / block;
         workers = int(std::min<uint64_t>(uint64_t(workers), nblocks ? nblocks : 1));
         auto run_worker = [&](int k) {
             if (workers > 1) setenv("TDCGPU_DEVICE", std::to_string(k).c_str(), 1);  // device k for worker k (GPU registry)
+#ifdef TDC_GPU_DEFAULT_TEXTDS
+            if (const char* e = std::getenv("TDCGPU_DEVICE")) tdcgpu_set_device(std::atoi(e));  // pinned buffers belong to this worker's device
+#endif
+            const size_t cap = size_t(std::min<uint64_t>(block, in_size)) + 1;
+            std::unique_ptr<BlockBuffer> bufs[2] = {std::make_unique<BlockBuffer>(cap), std::make_unique<BlockBuffer>(cap)};
+            auto span = [&](uint64_t b) { return std::make_pair(b * block, size_t(std::min<uint64_t>(block, in_size - b * block))); };
+            std::future<LoadedBlock> next;
+            std::future<void> writing;
+            int cur = 0;
+            if (uint64_t(k) < nblocks) next = std::async(std::launch::async, load_block, fd, span(k).first, span(k).second, std::ref(*bufs[0]));
             for (uint64_t b = uint64_t(k); b < nblocks; b += uint64_t(workers)) {
-                const uint64_t from = b * block, len = std::min<uint64_t>(block, data.size() - from);
-                const std::vector<uint8_t> arc = compress_block(algo, data.data() + from, len);
-                std::ofstream t(block_tmp(ofile, b), std::ios::binary | std::ios::trunc);
-                t.write(reinterpret_cast<const char*>(arc.data()), std::streamsize(arc.size()));
-                if (!t) throw std::runtime_error("cannot write " + block_tmp(ofile, b));
+                const auto tb0 = std::chrono::steady_clock::now();
+                const LoadedBlock lb = next.get();
+                const auto tb1 = std::chrono::steady_clock::now();
+                const uint64_t nb = b + uint64_t(workers);
+                if (nb < nblocks) next = std::async(std::launch::async, load_block, fd, span(nb).first, span(nb).second, std::ref(*bufs[cur ^ 1]));
+                auto arc = std::make_shared<std::vector<uint8_t>>(compress_block(algo, bufs[cur]->p, lb.len, lb.clean));
+                const auto tb2 = std::chrono::steady_clock::now();
+                if (writing.valid()) writing.get();
+                if (std::getenv("TDC_BLOCK_VERBOSE")) {
+                    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point z) { return std::chrono::duration<double, std::milli>(z - a).count(); };
+                    std::cerr << "[worker " << k << "] block " << b << ": waited for the read " << ms(tb0, tb1) << " ms, compress " << ms(tb1, tb2)
+                              << " ms, waited for the previous write " << ms(tb2, std::chrono::steady_clock::now()) << " ms, " << (lb.clean ? "direct view" : "restricted input")
+                              << ", " << arc->size() << " bytes out\n";
+                }
+                const std::string tmp = block_tmp(ofile, b);
+                writing = std::async(std::launch::async, [arc, tmp] {
+                    const std::string part = tmp + ".part";
+                    {
+                        std::ofstream t(part, std::ios::binary | std::ios::trunc);
+                        t.write(reinterpret_cast<const char*>(arc->data()), std::streamsize(arc->size()));
+                        t.close();
+                        if (!t) throw std::runtime_error("cannot write " + part);
+                    }
+                    if (std::rename(part.c_str(), tmp.c_str()) != 0) throw std::runtime_error("cannot rename " + part);  // complete: visible to the assembler
+                });
+                cur ^= 1;
+            }
+            if (writing.valid()) writing.get();
+        };
+        // Workers are always forked (before any CUDA call: every worker creates its own context on its own device), so
+        // that this process can assemble the container in block order WHILE they run: a finished block archive appears
+        // under its final name by rename() and is appended as soon as all earlier blocks are in.
+        std::vector<pid_t> pids;
+        for (int k = 0; k < workers; k++) {
+            const pid_t pid = fork();
+            if (pid < 0) throw std::runtime_error("fork failed");
+            if (pid == 0) {
+                int rc = 0;
+                try {
+                    run_worker(k);
+                } catch (const std::exception& e) {
+                    std::cerr << "Error (worker " << k << "): " << e.what() << std::endl;
+                    rc = 1;
+                }
+                _exit(rc);
+            }
+            pids.push_back(pid);
+        }
+        auto cleanup = [&] {
+            for (uint64_t b = 0; b < nblocks; b++) {
+                std::remove(block_tmp(ofile, b).c_str());
+                std::remove((block_tmp(ofile, b) + ".part").c_str());
             }
         };
-        if (workers == 1) {
-            run_worker(0);
-        } else {
-            std::vector<pid_t> pids;
-            for (int k = 0; k < workers; k++) {
-                const pid_t pid = fork();  // before any CUDA call: every worker creates its own context on its own device
-                if (pid < 0) throw std::runtime_error("fork failed");
-                if (pid == 0) {
-                    int rc = 0;
-                    try {
-                        run_worker(k);
-                    } catch (const std::exception& e) {
-                        std::cerr << "Error (worker " << k << "): " << e.what() << std::endl;
-                        rc = 1;
-                    }
-                    _exit(rc);
-                }
-                pids.push_back(pid);
-            }
-            bool ok = true;
-            for (pid_t pid : pids) {
+        size_t live = pids.size();
+        bool failed = false;
+        auto reap = [&](bool block_until_all) {  // collect exited workers; a failed one fails the run
+            while (live > 0) {
                 int st = 0;
-                waitpid(pid, &st, 0);
-                ok = ok && WIFEXITED(st) && WEXITSTATUS(st) == 0;
+                const pid_t r = waitpid(-1, &st, block_until_all ? 0 : WNOHANG);
+                if (r <= 0) break;
+                live--;
+                if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) failed = true;
             }
-            if (!ok) throw std::runtime_error("a worker failed");
-        }
-        // assemble the container in block order
+        };
         std::ofstream out(ofile, std::ios::binary | std::ios::trunc);
         out.write(MAGIC, sizeof(MAGIC) - 1);
         put_u64(out, block);
@@ -190,17 +322,41 @@ int main(int argc, char** argv) {
         put_u32(out, uint32_t(algo.size()));
         out.write(algo.data(), std::streamsize(algo.size()));
         uint64_t total = 0;
-        for (uint64_t b = 0; b < nblocks; b++) {
-            const std::vector<uint8_t> arc = read_file(block_tmp(ofile, b));
-            put_u64(out, arc.size());
-            out.write(reinterpret_cast<const char*>(arc.data()), std::streamsize(arc.size()));
-            total += arc.size();
+        std::vector<char> chunk(size_t(16) << 20);
+        for (uint64_t b = 0; b < nblocks && !failed; b++) {
+            struct stat bs;
+            while (stat(block_tmp(ofile, b).c_str(), &bs) != 0) {  // not there yet
+                reap(false);
+                if (failed) break;
+                if (live == 0 && stat(block_tmp(ofile, b).c_str(), &bs) != 0) { failed = true; break; }
+                usleep(500);
+            }
+            if (failed) break;
+            std::ifstream t(block_tmp(ofile, b), std::ios::binary);
+            if (!t) { failed = true; break; }
+            const uint64_t alen = uint64_t(bs.st_size);
+            put_u64(out, alen);
+            for (uint64_t left = alen; left > 0;) {
+                const std::streamsize want = std::streamsize(std::min<uint64_t>(left, chunk.size()));
+                if (!t.read(chunk.data(), want)) { failed = true; break; }
+                out.write(chunk.data(), want);
+                left -= uint64_t(want);
+            }
+            total += alen;
+            t.close();
             std::remove(block_tmp(ofile, b).c_str());
+        }
+        reap(true);
+        if (failed) {
+            cleanup();
+            out.close();
+            std::remove(ofile.c_str());
+            throw std::runtime_error("a worker failed");
         }
         if (!out) throw std::runtime_error("cannot write " + ofile);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-        std::cerr << "tdc_block: " << data.size() << " bytes in " << nblocks << " block(s) of " << block << " on " << workers
-                  << " worker(s) -> " << total << " bytes, " << secs << " s (" << (secs > 0 ? data.size() / 1e6 / secs : 0.0) << " MB/s)\n";
+        std::cerr << "tdc_block: " << in_size << " bytes in " << nblocks << " block(s) of " << block << " on " << workers
+                  << " worker(s) -> " << total << " bytes, " << secs << " s (" << (secs > 0 ? in_size / 1e6 / secs : 0.0) << " MB/s)\n";
         return 0;
     } catch (const std::exception& e) {
         std::cerr << "Error: " << e.what() << std::endl;
