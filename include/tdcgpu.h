@@ -129,6 +129,12 @@ int tdcgpu_lzss_encode_get(tdcgpu_ctx* ctx, uint8_t* dst, uint64_t cap, int fina
 int tdcgpu_lzss_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst, uint64_t cap, int finalize, uint64_t* total,
                                  uint64_t* written);
 
+/* Width of the text-length field at the head of the lzss archive: `coder.encode(n, len_r)`, compressors/lzss/LZSSCoding.hpp:47,
+ * with len_r = TypeRange<len_t> (Range.hpp:95-99, :115) — 32 bits in the reference's default build, 64 in its wide-index
+ * build (-DLEN_BITS=40: len_t becomes a 64-bit type, def.hpp:100-114).  A plugin compiled against a wide-index reference
+ * passes 8 * sizeof(len_t); default 32.  Sticky for the context; affects tdcgpu_lzss_encode only. */
+int tdcgpu_set_len_bits(tdcgpu_ctx* ctx, uint32_t len_field_bits);
+
 /* Page-locked host memory for caller-side staging buffers (cudaMallocHost / cudaFreeHost); NULL on failure. */
 void* tdcgpu_pinned_alloc(uint64_t bytes);
 void tdcgpu_pinned_free(void* p);

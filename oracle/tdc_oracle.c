@@ -221,6 +221,13 @@ void tdcoracle_literal_histogram(const uint8_t* text, uint32_t n, const uint32_t
     while (p < n) hist[text[p++]]++;
 }
 
+/* Width of the text-length field: LengthRange = TypeRange<len_t> (include/tudocomp/Range.hpp:95-99, :115), i.e. 32 bits
+ * in the default build and 64 in a wide-index build (-DLEN_BITS=40 makes len_t = fast_t<uint_t<40>> = uint64_t,
+ * include/tudocomp/def.hpp:100-114).  Checked against oracle/_ref/libtdcref40.so (the reference compiled with
+ * -DLEN_BITS=40). */
+static uint32_t g_len_field_bits = 32;
+void tdcoracle_set_len_field_bits(uint32_t bits) { g_len_field_bits = bits == 64 ? 64 : 32; }
+
 /* The stream continues a coder header of `lead_bits` (0..7) bits held in the high bits of `lead_byte`.
  * finalize: append BitOStream::~BitOStream's tail (io/BitOStream.hpp:53-64).  Returns bytes written, < 0 if cap is
  * too small; *nbits_out = stream bits incl. lead_bits (before the tail). */
@@ -233,7 +240,7 @@ int64_t tdcoracle_lzss_encode(const uint8_t* text, uint32_t n, const uint32_t* t
     const uint32_t bl = bits_for_u64((uint64_t)flen_max - (uint64_t)flen_min); /* size_t arithmetic as in Range::delta */
     bitsink s = {out, cap, 0, 0};
     for (uint32_t i = 0; i < lead_bits; i++) sink_bit(&s, (lead_byte >> (7 - i)) & 1);
-    sink_int(&s, n, 32);         /* coder.encode(n, len_r)          :47 */
+    sink_int(&s, n, g_len_field_bits); /* coder.encode(n, len_r)    :47 */
     sink_int(&s, flen_min, bn);  /* coder.encode(flen_min, text_r)  :48 (INDEX_MAX truncated when there is no factor) */
     sink_int(&s, flen_max, bn);  /* :49 */
     sink_int(&s, fdist_max, bn); /* :50 */

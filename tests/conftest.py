@@ -97,6 +97,9 @@ class Oracle:
         assert m >= 0
         return out[:m].copy(), int(nbits.value)
 
+    def set_len_field_bits(self, bits):
+        self.lib.tdcoracle_set_len_field_bits(ctypes.c_uint32(bits))
+
     def mtf_encode(self, data):
         data = np.ascontiguousarray(data, np.uint8)
         out = np.zeros(data.size, np.uint8)
@@ -133,10 +136,11 @@ class Oracle:
 class Reference:
     """tests-only binding of oracle/_ref/libtdcref.so (the unmodified reference compiled by oracle/Makefile)."""
 
-    def __init__(self):
-        path = os.path.join(ROOT, "oracle", "_ref", "libtdcref.so")
+    def __init__(self, wide=False):
+        # wide: the same wrapper over the reference's wide-index build (-DLEN_BITS=40, oracle/Makefile)
+        path = os.path.join(ROOT, "oracle", "_ref", "libtdcref40.so" if wide else "libtdcref.so")
         if not os.path.exists(path):
-            pytest.skip("oracle/_ref/libtdcref.so not built (needs /root/reference; run `make -C oracle ref`)")
+            pytest.skip(os.path.basename(path) + " not built (needs /root/reference; run `make -C oracle ref`)")
         self.lib = ctypes.CDLL(path)
         for f in ("tdcref_lzss_lcp_factors", "tdcref_lzss_lcp_compress", "tdcref_lzss_lcp_decompress", "tdcref_escape",
                   "tdcref_bwt_compress", "tdcref_stream_stage"):

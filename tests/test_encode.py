@@ -82,6 +82,54 @@ def test_oracle_encode_matches_reference_on_fresh_inputs(oracle, reference):
                 assert np.array_equal(splice(head, hb, body), arc), (name, thr, coder)
 
 
+def _wide_cases():
+    return [("dna", synth.dna(30000, 61)), ("markov", synth.markov_text(30000, 62)), ("rep", synth.repetitive(30000, 63, block=400, p=0.02)),
+            ("no_factor", synth.with_sentinel(np.arange(1, 200, dtype=np.uint8))), ("sentinel_only", np.zeros(1, np.uint8)),
+            ("banana", synth.with_sentinel(np.frombuffer(b"banana", np.uint8)))]
+
+
+def _wide_format_check(encode_body):
+    """The LEN_BITS=40 archive format (text length in 64 bits): `encode_body(t, thr, f, codes, lens,
+    lead_bits, lead_byte)` must reproduce the archive of the reference compiled with -DLEN_BITS=40 (oracle/_ref/libtdcref40.so)."""
+    from conftest import Reference
+    wide, narrow = Reference(wide=True), Reference()
+    for name, t in _wide_cases():
+        for thr in (2, 5):
+            f, _ = wide.factors(t, thr)
+            assert np.array_equal(f, narrow.factors(t, thr)[0]), name  # same factors, only the header differs
+            from conftest import Oracle
+            hist = Oracle().literal_histogram(t, f)
+            for coder in (BIT, HUFF):
+                head, hb, codes, lens = wide.literal_coder(coder, hist)
+                lb, lbyte = lead(head, hb)
+                arc, _ = wide.compress(t, thr, coder)
+                assert arc.size == narrow.compress(t, thr, coder)[0].size + 4, name  # the 32 extra bits of the length field
+                got = splice(head, hb, encode_body(t, thr, f, codes, lens, lb, lbyte))
+                assert np.array_equal(got, arc), (name, thr, coder)
+
+
+def test_oracle_encode_wide_index_format(oracle):
+    def body(t, thr, f, codes, lens, lb, lbyte):
+        oracle.set_len_field_bits(64)
+        try:
+            return oracle.encode(t, f, codes, lens, lb, lbyte)[0]
+        finally:
+            oracle.set_len_field_bits(32)
+    _wide_format_check(body)
+
+
+def _device_wide_body(lib, device=0):
+    def body(t, thr, f, codes, lens, lb, lbyte):
+        with _abi.Context(lib, device) as c:
+            c.set_text(t)
+            c.factorize(thr)
+            c.literal_histogram()
+            c.set_len_bits(64)
+            nbits = c.encode(codes, lens, lb, lbyte)
+            return c.encoded(nbits)
+    return body
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # kernels in the CPU interpreter
 # ---------------------------------------------------------------------------------------------------------------------
@@ -133,6 +181,11 @@ def test_sim_encode_reference_strings(simlib, oracle, reference):
 
 
 @pytest.mark.sim
+def test_sim_encode_wide_index_format(simlib):
+    _wide_format_check(_device_wide_body(simlib))
+
+
+@pytest.mark.sim
 def test_sim_encode_long_codes_and_lead_bits(simlib, oracle):
     """Code words longer than 32 bits (deep Huffman trees), every lead-bit offset, state errors."""
     rng = np.random.default_rng(3)
@@ -173,6 +226,11 @@ def test_gpu_encode_golden_archives(gpulib, gold):
                 lb, lbyte = lead(head, hb)
                 nbits = c.encode(codes, lens, lb, lbyte)
                 assert same_archive(splice(head, hb, c.encoded(nbits)), gold[f"{name}/arc_{cname}"]), (name, cname)
+
+
+@pytest.mark.gpu
+def test_gpu_encode_wide_index_format(gpulib):
+    _wide_format_check(_device_wide_body(gpulib))
 
 
 @pytest.mark.gpu

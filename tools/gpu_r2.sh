@@ -75,9 +75,34 @@ PY
       ./build/tdc_block_gpu -a "lzss_lcp(coder=huff)" -b 268435456 -g $N /dev/shm/block_in.txt -o /dev/shm/block_out.tdcb 2>&1 | sed "s#^#[-g $N] #" | tee -a gpurun_out/${tag}_block_mode.txt
       ls -l /dev/shm/block_in.txt /dev/shm/block_out.tdcb | tee -a gpurun_out/${tag}_block_mode.txt
       # the container is decoded by the REFERENCE registry (tdc_block_ref -d) and compared with the input
-      ( time ./build/tdc_block_ref -d /dev/shm/block_out.tdcb -o /dev/shm/block_back.txt ) 2>&1 | tail -4 | tee -a gpurun_out/${tag}_block_mode.txt
-      cmp /dev/shm/block_in.txt /dev/shm/block_back.txt && echo "round trip through the reference decoder: identical" | tee -a gpurun_out/${tag}_block_mode.txt
+      if [ -z "${BLOCK_SKIP_RT:-}" ]; then
+        ( time ./build/tdc_block_ref -d /dev/shm/block_out.tdcb -o /dev/shm/block_back.txt ) 2>&1 | tail -4 | tee -a gpurun_out/${tag}_block_mode.txt
+        cmp /dev/shm/block_in.txt /dev/shm/block_back.txt && echo "round trip through the reference decoder: identical" | tee -a gpurun_out/${tag}_block_mode.txt
+      fi
       rm -f /dev/shm/block_in.txt /dev/shm/block_out.tdcb /dev/shm/block_back.txt ;;
+    chain)  # BASELINE config 3 through the stock driver + GPU-only registry: bwt:mtf:rle:encode(huff), device-resident chain vs host chain
+      python - <<PY
+import sys; sys.path.insert(0, ".")
+from tudocomp_b200 import synth
+for lg in (25, 28, 30):
+    open("/dev/shm/rep%d.txt" % lg, "wb").write(synth.repetitive(1 << lg, 3)[:-1].tobytes())
+PY
+      {
+        A="bwt:mtf:rle:encode(huff)"
+        ./build/tdc_ref -a "$A" /dev/shm/rep25.txt -o /dev/shm/rep25.ref --force
+        ./build/tdc_gpu_only -a "$A" /dev/shm/rep25.txt -o /dev/shm/rep25.gpu --force
+        TDCGPU_HOST_CHAIN=1 ./build/tdc_gpu_only -a "$A" /dev/shm/rep25.txt -o /dev/shm/rep25.gpuh --force
+        cmp /dev/shm/rep25.ref /dev/shm/rep25.gpu && cmp /dev/shm/rep25.ref /dev/shm/rep25.gpuh && echo "2^25 B chain archives identical (reference driver, device-resident chain, host chain): $(stat -c %s /dev/shm/rep25.ref) bytes"
+        for lg in 28 30; do
+          for mode in 0 1; do
+            t0=$(date +%s%N)
+            TDCGPU_HOST_CHAIN=$mode ./build/tdc_gpu_only -a "$A" /dev/shm/rep$lg.txt -o /dev/shm/rep$lg.gpu$mode --force --stats > gpurun_out/${tag}_chain_stats_${lg}_$mode.json
+            echo "$(( ($(date +%s%N) - t0) / 1000000 )) ms wall  <- tdc_gpu_only $A, 2^$lg B repetitive, TDCGPU_HOST_CHAIN=$mode"
+          done
+          cmp /dev/shm/rep$lg.gpu0 /dev/shm/rep$lg.gpu1 && echo "2^$lg B: device-resident and host chain archives identical: $(stat -c %s /dev/shm/rep$lg.gpu0) bytes"
+        done
+        rm -f /dev/shm/rep2*.txt /dev/shm/rep3*.txt /dev/shm/rep*.gpu* /dev/shm/rep*.ref
+      } 2>&1 | tee gpurun_out/${tag}_chain.txt ;;
     ncu)  # one `ncu --set full` capture of the dominant kernel inside the real bench (full-size launch: skip the sample sort)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-rs_onesweep} -s ${NCU_SKIP:-3} -c 1 -o gpurun_out/${tag}_ncu -f \
         python bench.py --steps 1 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_ncu.log 2>&1

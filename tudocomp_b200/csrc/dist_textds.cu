@@ -353,7 +353,8 @@ static int dist_build_sa(DistCtx& d) {
 
     // ---- round 0: keys of my positions, splitters, exchange, local sort ----
     if (d.pos_cnt) {
-        TDC_LAUNCH(pack_keys_kernel, u32(div_up(d.pos_cnt, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, K[0], d.pos_lo, d.pos_cnt);
+        auto pack_keys_kernel = tdc::pack_keys_kernel<false>;
+        TDC_LAUNCH(pack_keys_kernel, u32(div_up(d.pos_cnt, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, K[0], d.pos_lo, d.pos_cnt, PassPlan(), (u32*)nullptr);
         TDC_KCHECK();
     }
     SplitterFn sf;

@@ -242,11 +242,15 @@ enc_tile_kernel(const uint8_t* __restrict__ text, const Factor* __restrict__ f, 
 
 // the stream head: `lead_bits` bits already in the coder's current byte, then n and the three header values
 // (LZSSCoding.hpp:46-50).  One thread.
-static __global__ void enc_header_kernel(u32 lead_bits, u32 lead_byte, EncParams P, u32 flen_max, u32 fdist_max, u32* __restrict__ out32) {
+// len_field_bits: 32, or 64 for the wide-index build of the reference (LengthRange over a 64-bit len_t; n < 2^32 here, so
+// the upper word is zero).
+static __global__ void enc_header_kernel(u32 lead_bits, u32 lead_byte, EncParams P, u32 flen_max, u32 fdist_max, u32 len_field_bits,
+                                         u32* __restrict__ out32) {
     if (threadIdx.x || blockIdx.x) return;
-    u32 w[6] = {0, 0, 0, 0, 0, 0};
+    u32 w[7] = {0, 0, 0, 0, 0, 0, 0};
     u32 cur = 0;
     if (lead_bits) { enc_put<false>(w, cur, lead_byte >> (8 - lead_bits), lead_bits); cur += lead_bits; }
+    if (len_field_bits == 64) cur += 32;
     enc_put<false>(w, cur, P.n, 32); cur += 32;
     enc_put<false>(w, cur, P.flen_min, P.bn); cur += P.bn;
     enc_put<false>(w, cur, flen_max, P.bn); cur += P.bn;

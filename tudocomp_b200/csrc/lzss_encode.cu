@@ -82,7 +82,7 @@ int encode_lzss(Ctx& c, const u64* codes, const uint8_t* lens, u32 lead_bits, u3
     TDC_LAUNCH(enc_count, e.ntiles, ENC_THREADS, 0, st, c.d_text, c.d_factors, e.S, e.E, e.scan_s, e.scan_e, P, e.d_code, e.d_len,
                (ull*)nullptr, e.tile_bits, (const u64*)nullptr, (u32*)nullptr);
     prof_add_bytes("enc_count", double(n) * 1.25);
-    const u64 head_bits = u64(lead_bits) + 32 + 3 * u64(P.bn);
+    const u64 head_bits = u64(lead_bits) + c.len_field_bits + 3 * u64(P.bn);
     u64* d_total = reinterpret_cast<u64*>(c.d_scalars + 12);  // 8-byte aligned
     auto enc_scan_u64 = enc_scan_kernel<u64>;
     TDC_LAUNCH(enc_scan_u64, 1, 1024, 0, st, e.tile_bits, e.ntiles, head_bits, e.tile_off, d_total);
@@ -100,7 +100,7 @@ int encode_lzss(Ctx& c, const u64* codes, const uint8_t* lens, u32 lead_bits, u3
     }
     TDC_CUDA(cudaMemsetAsync(e.out, 0, out_bytes, st));
     u32* out32 = reinterpret_cast<u32*>(e.out);
-    TDC_LAUNCH(enc_header_kernel, 1, 32, 0, st, lead_bits, lead_byte, P, c.flen_max, e.fdist_max, out32);
+    TDC_LAUNCH(enc_header_kernel, 1, 32, 0, st, lead_bits, lead_byte, P, c.flen_max, e.fdist_max, c.len_field_bits, out32);
     auto enc_write = enc_tile_kernel<2>;
     TDC_LAUNCH(enc_write, e.ntiles, ENC_THREADS, 0, st, c.d_text, c.d_factors, e.S, e.E, e.scan_s, e.scan_e, P, e.d_code, e.d_len,
                (ull*)nullptr, (u32*)nullptr, e.tile_off, out32);

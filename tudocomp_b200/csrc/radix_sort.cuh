@@ -37,6 +37,42 @@ struct PassPlan {
     u32 mask[RS_MAX_PASSES];
 };
 
+// digits of the key bits [begin_bit, end_bit): as few passes as 8-bit digits allow, widths balanced
+static inline PassPlan make_pass_plan(int begin_bit, int end_bit) {
+    PassPlan plan;
+    const int bits = end_bit - begin_bit;
+    plan.npass = bits <= 0 ? 0 : (bits + 7) / 8;
+    const int np = plan.npass <= RS_MAX_PASSES ? plan.npass : RS_MAX_PASSES;
+    const int base = np ? bits / plan.npass : 0, extra = np ? bits % plan.npass : 0;
+    int sh = begin_bit;
+    for (int p = 0; p < np; p++) {
+        const int wd = base + (p < extra ? 1 : 0);
+        plan.shift[p] = u32(sh);
+        plan.mask[p] = (1u << wd) - 1u;
+        sh += wd;
+    }
+    return plan;
+}
+
+// One key's digits of every planned pass into the CTA's shared-memory histograms sh[pass][256]; must be called by all 32
+// lanes of a warp (`valid` = this lane has a key).  A warp-uniform digit (constant high bits, runs) costs one shared
+// atomic instead of a 32-way conflict.
+template <class K>
+__device__ __forceinline__ void rs_count_digits(u32* sh, const PassPlan& plan, K k, bool valid) {
+#pragma unroll
+    for (int p = 0; p < RS_MAX_PASSES; p++) {
+        if (p < plan.npass) {
+            const u32 d = u32(k >> plan.shift[p]) & plan.mask[p];
+            const u32 d0 = __shfl_sync(kFull, d, 0);
+            if (__all_sync(kFull, valid && d == d0)) {
+                if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d0], 32u);
+            } else if (valid) {
+                atomicAdd(&sh[p * RS_RADIX + d], 1u);
+            }
+        }
+    }
+}
+
 struct SortWorkspace {
     u32* hist = nullptr;          // device [RS_MAX_PASSES][256]: digit counts, then exclusive bucket starts
     u32* uniform = nullptr;       // device [RS_MAX_PASSES]: 1 if one bin holds every key (pass can be skipped)
@@ -106,21 +142,7 @@ __global__ void __launch_bounds__(512) rs_histogram_kernel(const K* __restrict__
         }
 #pragma unroll
         for (int e = 0; e < EPT; e++) {
-            const bool valid = base + u64(e) * 32 + lane_id() < m;
-            const K k = kk[e];
-#pragma unroll
-            for (int p = 0; p < RS_MAX_PASSES; p++) {
-                if (p < plan.npass) {
-                    const u32 d = u32(k >> plan.shift[p]) & plan.mask[p];
-                    // warp-uniform digit (constant high bits, runs): one shared atomic instead of a 32-way conflict
-                    const u32 d0 = __shfl_sync(kFull, d, 0);
-                    if (__all_sync(kFull, valid && d == d0)) {
-                        if (lane_id() == 0) atomicAdd(&sh[p * RS_RADIX + d0], 32u);
-                    } else if (valid) {
-                        atomicAdd(&sh[p * RS_RADIX + d], 1u);
-                    }
-                }
-            }
+            rs_count_digits<K>(sh, plan, kk[e], base + u64(e) * 32 + lane_id() < m);
         }
     }
     __syncthreads();
@@ -384,7 +406,9 @@ void sort_workspace_free(SortWorkspace& ws);
 // digit reaching the top key bit, so the bucket starts are known without a histogram.  Stable.
 template <class K>
 static int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[2], u64 m, int begin_bit, int end_bit,
-                            bool iota, int* result, bool keys_are_perm = false) {
+                            bool iota, int* result, bool keys_are_perm = false, bool hist_ready = false) {
+    // hist_ready: the producer of the keys has already counted the digits of make_pass_plan(begin_bit, end_bit) into
+    // ws.hist (rs_count_digits; pack_keys_kernel does, which saves one full read of the keys)
     *result = 0;
     if (m == 0) return 0;
     {
@@ -396,31 +420,23 @@ static int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[
         TDC_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, int(rs_smem_bytes<K>())));
     }
     const int bits = end_bit - begin_bit;
-    PassPlan plan;
-    plan.npass = bits <= 0 ? 0 : (bits + 7) / 8;
+    const PassPlan plan = make_pass_plan(begin_bit, end_bit);
     if (plan.npass > RS_MAX_PASSES) { set_error("radix_sort_pairs: %d bits need more than %d passes", bits, RS_MAX_PASSES); return -1; }
     if (rs_tiles<K>(m) > ws.max_tiles) { set_error("radix_sort_pairs: workspace too small"); return -1; }
-    {
-        int base = plan.npass ? bits / plan.npass : 0, extra = plan.npass ? bits % plan.npass : 0, sh = begin_bit;
-        for (int p = 0; p < plan.npass; p++) {
-            int wd = base + (p < extra ? 1 : 0);
-            plan.shift[p] = u32(sh);
-            plan.mask[p] = (1u << wd) - 1u;
-            sh += wd;
-        }
-    }
     int cur = 0;
     bool need_iota = iota;
     if (plan.npass == 1 && keys_are_perm) {
         TDC_LAUNCH(rs_perm_starts_kernel, 1, 256, 0, st, ws.hist, m, plan.shift[0]);
         ws.h_uniform[0] = 0;
     } else if (plan.npass > 0) {
-        TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
         TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
-        const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
-        auto rs_histogram = rs_histogram_kernel<K>;
-        TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
-        prof_add_bytes("rs_histogram", double(m) * sizeof(K));
+        if (!hist_ready) {
+            TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
+            const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
+            auto rs_histogram = rs_histogram_kernel<K>;
+            TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
+            prof_add_bytes("rs_histogram", double(m) * sizeof(K));
+        }
         TDC_LAUNCH(rs_scan_kernel, plan.npass, 256, 0, st, ws.hist, ws.uniform, m);
         TDC_KCHECK();
         TDC_CUDA(cudaMemcpyAsync(ws.h_uniform, ws.uniform, sizeof(u32) * RS_MAX_PASSES, cudaMemcpyDeviceToHost, st));

@@ -181,12 +181,22 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     TDC_CUDA(cudaMemcpyAsync(d_code_map, code_map, 256, cudaMemcpyHostToDevice, st));
 
     // ---- initial sort by k-symbol prefix ----
-    TDC_LAUNCH(pack_keys_kernel, u32(div_up(n, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, keys[0], u64(0), n);
+    // (wide layout: the digit histograms of the sort are counted by the pack kernel, see pack_keys_kernel)
+    const bool fused_hist = !packed && !getenv("TDCGPU_SA_SEPARATE_HIST");
+    if (fused_hist) {
+        TDC_CUDA(cudaMemsetAsync(c.sortws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
+        auto pack_keys_kernel = tdc::pack_keys_kernel<true>;
+        TDC_LAUNCH(pack_keys_kernel, u32(div_up(n, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, keys[0], u64(0), n,
+                   make_pass_plan(0, int(sigbits)), c.sortws.hist);
+    } else {
+        auto pack_keys_kernel = tdc::pack_keys_kernel<false>;
+        TDC_LAUNCH(pack_keys_kernel, u32(div_up(n, PK_TILE)), PK_THREADS, 0, st, c.d_text, n, d_code_map, pp, keys[0], u64(0), n, PassPlan(), (u32*)nullptr);
+    }
     prof_add_bytes("pack_keys_kernel", double(n) * 9);
     TDC_KCHECK();
     int res = 0;
     if (packed) TDC_TRY(radix_sort_keys(c.sortws, st, keys, n, int(pp.idx_bits), int(pp.idx_bits + sigbits), &res));
-    else TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, keys, vals, n, 0, int(sigbits), true, &res));
+    else TDC_TRY(radix_sort_pairs<u64>(c.sortws, st, keys, vals, n, 0, int(sigbits), true, &res, false, fused_hist));
     u64 m = 0, g = 0;
     int pcur = 0;
     // the sorted (key, suffix) pairs are in slot `res`; compacted survivors go to the other slot's value buffer

@@ -85,6 +85,7 @@ struct Ctx {
     Factor* d_factors = nullptr;
     u64 factors_cap = 0, num_factors = 0;
     u32 flen_min = 0xffffffffu, flen_max = 0;
+    u32 len_field_bits = 32;  // width of the archive's text-length field (tdcgpu_set_len_bits)
     bool have_factors = false;  // factorize_lzss_lcp has run on the current text
     EncodeState enc;
 

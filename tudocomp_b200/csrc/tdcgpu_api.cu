@@ -499,6 +499,13 @@ int tdcgpu_lzss_encode_get_chunk(tdcgpu_ctx* ctx, uint64_t offset, uint8_t* dst,
     return copy_bitstream_chunk(c, c.enc.out, c.enc.nbits, offset, dst, cap, finalize, total, written);
 }
 
+int tdcgpu_set_len_bits(tdcgpu_ctx* ctx, uint32_t len_field_bits) {
+    API_GUARD(ctx);
+    if (len_field_bits != 32 && len_field_bits != 64) { set_error("len_field_bits must be 32 or 64"); return TDCGPU_ERR_ARG; }
+    c.len_field_bits = len_field_bits;
+    return 0;
+}
+
 void* tdcgpu_pinned_alloc(uint64_t bytes) {
     void* p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_error("pinned allocation of %llu bytes failed", (unsigned long long)bytes); return nullptr; }

@@ -428,6 +428,7 @@ public:
             const uint8_t lead_byte = lead_bits ? head[head_bits / 8] : uint8_t(0);
             // 2. the body of lzss::encode_text on the device, continuing the header's partial byte
             uint64_t nbits = 0, nbytes = 0;
+            gpu_detail::check(tdcgpu_set_len_bits(text.device(), uint32_t(8 * sizeof(len_t))), "encode");  // LengthRange of THIS build (LEN_BITS)
             gpu_detail::check(tdcgpu_lzss_encode(text.device(), table.codes, table.lens, lead_bits, lead_byte, &nbits), "encode");
             gpu_detail::log_phases(text.device());
             // 3. drain the stream through one pinned buffer straight into the output (no archive-sized vector in between)

@@ -132,7 +132,7 @@ protected:
 };
 
 // one block through the registry, exactly as the driver runs a whole file
-std::vector<uint8_t> compress_block(const std::string& algo, const uint8_t* data, size_t len, bool sentinel_follows) {
+std::vector<uint8_t> compress_block(const std::string& algo, const uint8_t* data, size_t len, bool sentinel_follows, std::string* stats_json = nullptr) {
     auto& registry = tdc_algorithms::COMPRESSOR_REGISTRY;
     auto av = registry.parse_algorithm_id(algo);
     auto restrictions = av.textds_flags();
@@ -157,6 +157,7 @@ std::vector<uint8_t> compress_block(const std::string& algo, const uint8_t* data
             compressor->compress(inp, out);
         }
         os.flush();
+        if (stats_json) *stats_json = root.to_json().str();
     }
     return arc;
 }
@@ -255,7 +256,9 @@ int main(int argc, char** argv) {
                 const auto tb1 = std::chrono::steady_clock::now();
                 const uint64_t nb = b + uint64_t(workers);
                 if (nb < nblocks) next = std::async(std::launch::async, load_block, fd, span(nb).first, span(nb).second, std::ref(*bufs[cur ^ 1]));
-                auto arc = std::make_shared<std::vector<uint8_t>>(compress_block(algo, bufs[cur]->p, lb.len, lb.clean));
+                std::string stats;
+                const bool verbose = std::getenv("TDC_BLOCK_VERBOSE") != nullptr;
+                auto arc = std::make_shared<std::vector<uint8_t>>(compress_block(algo, bufs[cur]->p, lb.len, lb.clean, verbose ? &stats : nullptr));
                 const auto tb2 = std::chrono::steady_clock::now();
                 if (writing.valid()) writing.get();
                 if (std::getenv("TDC_BLOCK_VERBOSE")) {
@@ -263,6 +266,7 @@ int main(int argc, char** argv) {
                     std::cerr << "[worker " << k << "] block " << b << ": waited for the read " << ms(tb0, tb1) << " ms, compress " << ms(tb1, tb2)
                               << " ms, waited for the previous write " << ms(tb2, std::chrono::steady_clock::now()) << " ms, " << (lb.clean ? "direct view" : "restricted input")
                               << ", " << arc->size() << " bytes out\n";
+                    if (std::getenv("TDC_BLOCK_VERBOSE")[0] == '2') std::cerr << stats << "\n";
                 }
                 const std::string tmp = block_tmp(ofile, b);
                 writing = std::async(std::launch::async, [arc, tmp] {
