@@ -107,6 +107,18 @@ PY
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-rs_onesweep} -s ${NCU_SKIP:-3} -c 1 -o gpurun_out/${tag}_ncu -f \
         python bench.py --steps 1 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_ncu.log 2>&1
       echo "ncu rc=$?"; tail -3 gpurun_out/${tag}_ncu.log ;;
+    distab)  # sharded path A/B on all GPUs of the box: every rank uploads the whole text vs its own slice (+ peer exchange)
+      N=$(nvidia-smi -L | wc -l)
+      for su in 0 1; do
+        TDCGPU_DIST_SLICE_UPLOAD=$su timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$su bench.py --gpus $N --mode dist --bytes ${DIST_BYTES:-2000000000} --steps 3 --warmup 2 > gpurun_out/${tag}_dist_n${N}_slice$su.json 2> gpurun_out/${tag}_dist_n${N}_slice$su.err
+        python - <<PY
+import json
+for ln in open("gpurun_out/${tag}_dist_n${N}_slice$su.json"):
+    if ln.startswith("{"):
+        d = json.loads(ln)
+        print("slice_upload=$su N=$N", d["config"]["workload"], "ms/step", round(d["ms_per_step"], 2), "MB/s", round(d["value"]), "e2e MB/s", round(d["e2e"]["value"]), "e2e ms", round(d["e2e"]["ms_per_step"], 2), "verified", (d.get("verify") or {}).get("ok"))
+PY
+      done 2>&1 | tee gpurun_out/${tag}_distab.txt ;;
     dist)  # the default bench line on all GPUs of the box (block-mode headline + sharded sub-records)
       N=$(nvidia-smi -L | wc -l)
       timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N --steps ${STEPS:-5} --warmup 3 ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_n$N.json 2> gpurun_out/${tag}_bench_n$N.err

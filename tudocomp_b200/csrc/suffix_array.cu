@@ -181,8 +181,10 @@ int build_suffix_array(Ctx& c, bool want_lcp) {
     TDC_CUDA(cudaMemcpyAsync(d_code_map, code_map, 256, cudaMemcpyHostToDevice, st));
 
     // ---- initial sort by k-symbol prefix ----
-    // (wide layout: the digit histograms of the sort are counted by the pack kernel, see pack_keys_kernel)
-    const bool fused_hist = !packed && !getenv("TDCGPU_SA_SEPARATE_HIST");
+    // EXPERIMENT (TDCGPU_SA_FUSED_HIST=1): the digit histograms of the sort counted by the pack kernel.  Measured at
+    // dna 2^30 (profiles/r2_summary.md): the fused kernel takes 10.4 ms, pack 4.05 + histogram 5.77 ms apart — both are
+    // bound by the shared-memory atomics (6 per key), not by the 8 B/key read that the fusion saves.  Off by default.
+    const bool fused_hist = !packed && getenv("TDCGPU_SA_FUSED_HIST") != nullptr;
     if (fused_hist) {
         TDC_CUDA(cudaMemsetAsync(c.sortws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
         auto pack_keys_kernel = tdc::pack_keys_kernel<true>;

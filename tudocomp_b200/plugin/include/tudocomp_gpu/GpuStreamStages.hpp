@@ -190,7 +190,7 @@ public:
         gpu_detail::log_phases(g.ctx);
         auto os = host_out->as_stream();
         os.write(reinterpret_cast<const char*>(head.data()), std::streamsize(head_bits / 8));
-        gpu_detail::PinnedBuffer buf(size_t(16) << 20);  // drained chunk by chunk, no stream-sized vector in between
+        gpu_detail::PinnedBuffer& buf = gpu_detail::drain_buffer();  // drained chunk by chunk, no stream-sized vector in between
         for (uint64_t off = 0;;) {
             uint64_t total = 0, wr = 0;
             gpu_detail::check(tdcgpu_literal_encode_get_chunk(g.ctx, off, buf.data, buf.size, 1, &total, &wr), "encode");

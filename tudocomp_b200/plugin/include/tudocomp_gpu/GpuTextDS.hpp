@@ -228,6 +228,13 @@ struct PinnedBuffer {
     PinnedBuffer& operator=(const PinnedBuffer&) = delete;
 };
 
+// the 16 MiB drain buffer of the archive streams, allocated once per process (tdc is single-threaded; like the cached
+// context it is deliberately not released at exit): cudaMallocHost + cudaFreeHost per compress() cost a few ms each
+inline PinnedBuffer& drain_buffer() {
+    static PinnedBuffer* b = new PinnedBuffer(size_t(16) << 20);
+    return *b;
+}
+
 inline bool host_encode_forced() {
     const char* e = std::getenv("TDCGPU_HOST_ENCODE");  // A/B switch: run the reference's encode_text on the host
     return e && *e && *e != '0';
@@ -434,7 +441,7 @@ public:
             // 3. drain the stream through one pinned buffer straight into the output (no archive-sized vector in between)
             auto os = output.as_stream();
             os.write(reinterpret_cast<const char*>(head.data()), std::streamsize(head_bits / 8));
-            gpu_detail::PinnedBuffer buf(size_t(16) << 20);
+            gpu_detail::PinnedBuffer& buf = gpu_detail::drain_buffer();
             for (uint64_t off = 0;;) {
                 uint64_t total = 0, wr = 0;
                 gpu_detail::check(tdcgpu_lzss_encode_get_chunk(text.device(), off, buf.data, buf.size, 1, &total, &wr), "encode");
