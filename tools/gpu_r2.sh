@@ -68,9 +68,9 @@ PY
       python - <<PY
 import sys; sys.path.insert(0, ".")
 from tudocomp_b200 import synth
-with open("/dev/shm/block_in.txt", "wb") as f:
+with open("/dev/shm/block_in.txt", "wb") as f:  # Markov text generated on the GPU, 1 GiB at a time (numpy: 2 min per GiB)
     for i in range($GIB):
-        f.write(synth.markov_text(1 << 30, 500 + i)[:-1].tobytes())
+        f.write(synth.markov_text_device(1 << 30, 500 + i).cpu().numpy().tobytes())
 PY
       ./build/tdc_block_gpu -a "lzss_lcp(coder=huff)" -b 268435456 -g $N /dev/shm/block_in.txt -o /dev/shm/block_out.tdcb 2>&1 | sed "s#^#[-g $N] #" | tee -a gpurun_out/${tag}_block_mode.txt
       ls -l /dev/shm/block_in.txt /dev/shm/block_out.tdcb | tee -a gpurun_out/${tag}_block_mode.txt

@@ -61,6 +61,29 @@ def markov_text(n_body: int, seed: int = 1, lanes: int | None = None) -> np.ndar
     return with_sentinel(body)
 
 
+def markov_text_device(n_body: int, seed: int = 1, device: str = "cuda:0", lanes: int = 1 << 20):
+    """The same order-3 chain as markov_text (same transition table), advanced on the GPU with torch's generator: GiB-sized
+    inputs of the block-mode / sharded measurements in seconds instead of minutes (numpy: ~2 min per GiB).  Different
+    random stream than markov_text, hence different bytes — only for measurements whose checker does not need the CPU
+    generator (round trips, device checkers).  Returns a uint8 CUDA tensor of n_body bytes WITHOUT sentinel."""
+    import torch
+
+    cum = torch.from_numpy(_markov_table(seed)).to(device)
+    syms = torch.from_numpy(_SYMS.copy()).to(device)
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lanes = int(min(lanes, max(1, n_body // 1024)))
+    steps = -(-n_body // lanes)
+    ctx = torch.randint(0, 27 ** 3, (lanes,), generator=g, device=device, dtype=torch.int64)
+    out = torch.empty((steps, lanes), dtype=torch.uint8, device=device)
+    for s in range(steps):
+        u = torch.rand(lanes, generator=g, device=device, dtype=torch.float32)
+        nxt = (cum[ctx] < u[:, None]).sum(dim=1).clamp_(max=26)
+        out[s] = syms[nxt]
+        ctx = (ctx * 27 + nxt) % (27 ** 3)
+    return out.t().reshape(-1)[:n_body].contiguous()
+
+
 def dna(n_body: int, seed: int = 2) -> np.ndarray:
     rng = np.random.default_rng(seed)
     body = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n_body, dtype=np.uint8)]
