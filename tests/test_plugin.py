@@ -114,10 +114,11 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
 
 
 def _block_container(path):
-    """(block_bytes, algo, [archive bytes per block]) of a tdc_block container (tudocomp_b200/plugin/tdc_block.cpp)."""
+    """(block_bytes, algo, [archive bytes per block]) of a tdc_block container (tudocomp_b200/plugin/tdc_block.cpp):
+    header, archives in completion order, index (offset, length per block, in block order), index offset, end mark."""
     import struct
     c = open(path, "rb").read()
-    assert c.startswith(b"TDCBLOCK1\n")
+    assert c.startswith(b"TDCBLOCK2\n") and c.endswith(b"TDCBEND\n")
     p = 10
     blk, nb = struct.unpack_from("<QQ", c, p)
     p += 16
@@ -125,13 +126,15 @@ def _block_container(path):
     p += 4
     algo = c[p:p + al].decode()
     p += al
-    arcs = []
-    for _ in range(nb):
-        (ln,) = struct.unpack_from("<Q", c, p)
-        p += 8
-        arcs.append(c[p:p + ln])
-        p += ln
-    assert p == len(c)
+    (index_off,) = struct.unpack_from("<Q", c, len(c) - 16)
+    assert index_off + 16 * nb + 16 == len(c)
+    arcs, covered = [], 0
+    for b in range(nb):
+        off, ln = struct.unpack_from("<QQ", c, index_off + 16 * b)
+        assert p <= off and off + ln <= index_off
+        arcs.append(c[off:off + ln])
+        covered += ln
+    assert covered == index_off - p  # the archives tile the space between header and index
     return blk, algo, arcs
 
 
@@ -165,8 +168,11 @@ def test_block_mode_driver_over_the_simulator_library(tmp_path):
     r = subprocess.run([BLOCK_GPU, "-a", algo, "-b", str(blk), "-c", str(src), "-o", gpu_c + ".c"], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stderr
     assert open(ref_c, "rb").read() == open(gpu_c + ".c", "rb").read()
+    # forked workers: the same archives per block (their order inside the container is the order of completion), decodable
     assert subprocess.run([BLOCK_REF, "-a", algo, "-b", str(blk), "-g", "3", str(src), "-o", ref3_c], capture_output=True).returncode == 0
-    assert open(ref_c, "rb").read() == open(ref3_c, "rb").read()
+    assert _block_container(ref3_c) == _block_container(ref_c)
+    assert subprocess.run([BLOCK_REF, "-d", ref3_c, "-o", str(tmp_path / "back3.bin")], capture_output=True).returncode == 0
+    assert open(tmp_path / "back3.bin", "rb").read() == data
     b, a, arcs = _block_container(gpu_c)
     assert (b, a, len(arcs)) == (blk, algo, -(-len(data) // blk))
     for i, arc in enumerate(arcs):

@@ -27,6 +27,8 @@ int factorize_lzss_lcp(Ctx& c, u32 threshold) {
         return -6;
     }
     const u32 n = u32(c.n);
+    // (len << 1 | side) words: only a text beyond 2^31 bytes can have a common prefix that long (include/tdcgpu.h, tdcgpu_set_text)
+    if (c.max_lcp >= (1u << 31)) { set_error("lzss_lcp: common prefixes of 2^31 bytes or more are not supported (max_lcp = %u)", c.max_lcp); return -5; }
     cudaStream_t st = c.stream;
     c.num_factors = 0;
     c.flen_min = 0xffffffffu;

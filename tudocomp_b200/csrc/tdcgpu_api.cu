@@ -305,7 +305,12 @@ void tdcgpu_destroy(tdcgpu_ctx* ctx) {
 int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_device) {
     API_GUARD(ctx);
     if (!text || n == 0) { set_error("empty text (the path always sees at least the sentinel)"); return TDCGPU_ERR_ARG; }
-    if (n >= (uint64_t(1) << 31)) { set_error("n = %llu: indices are 32-bit, n must be < 2^31", (unsigned long long)n); return TDCGPU_ERR_ARG; }
+    // indices are UNSIGNED 32-bit: the reference's default build stops at 2^31 (divsufsort's sign bit); here a text may have
+    // up to 2^32 - 2^20 bytes (the margin keeps tile-rounded indices below 2^32).  Beyond 2^31 two restrictions apply:
+    // common prefixes must stay below 2^31 (the (len << 1 | side) words of the factoriser and a flag bit of the PLCP
+    // pass) — checked by tdcgpu_lzss_lcp_factorize / the LCP build through max_lcp — and the archive needs the
+    // reference's wide-index format (tdcgpu_set_len_bits(ctx, 64)) to be decodable by a -DLEN_BITS=40 build.
+    if (n > (uint64_t(1) << 32) - (uint64_t(1) << 20)) { set_error("n = %llu: indices are 32-bit, n must be <= 2^32 - 2^20", (unsigned long long)n); return TDCGPU_ERR_ARG; }
     if (!on_device && text[n - 1] != 0) {  // device input: checked by the builder (suffix_array.cu), which reads d_text[n-1]
         set_error("Input has no sentinel! (the last text byte must be 0, ds/TextDS.hpp:132-138)");
         return TDCGPU_ERR_SENTINEL;

@@ -10,13 +10,17 @@
 //        -c  keep one device context per worker alive across its blocks (TDCGPU_CTX_CACHE=1, GpuTextDS.hpp)
 //   tdc_block -d output.tdcb -o roundtrip
 //
-// Container: "TDCBLOCK1\n", u64 block_bytes, u64 nblocks, u32 algo_len, algo string, then per block u64 archive_len and
-// the raw archive.  All integers little-endian.
+// Container: "TDCBLOCK2\n", u64 block_bytes, u64 nblocks, u32 algo_len, algo string; then the raw block archives in the
+// order the workers finished them (every worker writes its archive straight into the output file with pwrite at an offset
+// reserved from a cursor shared between the processes — nothing is copied a second time); then the index, nblocks x
+// (u64 offset, u64 length) in BLOCK order; then u64 index_offset and "TDCBEND\n".  All integers little-endian.
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -26,6 +30,7 @@
 #include <iostream>
 #include <future>
 #include <memory>
+#include <new>
 #include <streambuf>
 #include <string>
 #include <thread>
@@ -44,7 +49,8 @@ using namespace tdc;
 
 namespace {
 
-const char MAGIC[] = "TDCBLOCK1\n";
+const char MAGIC[] = "TDCBLOCK2\n";
+const char MAGIC_END[] = "TDCBEND\n";
 
 std::vector<uint8_t> read_file(const std::string& path) {
     std::ifstream f(path, std::ios::binary | std::ios::ate);
@@ -194,7 +200,11 @@ std::vector<uint8_t> decompress_block(const std::string& algo, const uint8_t* ar
     return text;
 }
 
-std::string block_tmp(const std::string& ofile, uint64_t b) { return ofile + ".blk." + std::to_string(b); }
+// state shared between the forked workers (anonymous shared mapping): where the next archive goes, and the index
+struct Shared {
+    std::atomic<uint64_t> cursor;
+    uint64_t* entry(uint64_t b) { return reinterpret_cast<uint64_t*>(this + 1) + 2 * b; }  // {offset, length}
+};
 
 int usage() {
     std::cerr << "usage: tdc_block -a ALGO [-b BLOCK_BYTES] [-g WORKERS] [-c] INPUT -o OUTPUT\n"
@@ -237,14 +247,22 @@ int main(int argc, char** argv) {
             if (uint64_t(end - p) < alen) throw std::runtime_error("truncated container");
             const std::string stored(reinterpret_cast<const char*>(p), alen);
             p += alen;
+            // trailer: index offset + end mark; the index holds (offset, length) per block in block order
+            const size_t tail = 8 + sizeof(MAGIC_END) - 1;
+            if (size_t(end - p) < tail || std::memcmp(end - (sizeof(MAGIC_END) - 1), MAGIC_END, sizeof(MAGIC_END) - 1) != 0) throw std::runtime_error("truncated container");
+            const uint8_t* q = end - tail;
+            const uint64_t index_off = get_u64(q, end);
+            if (index_off > c.size() || (c.size() - index_off - tail) / 16 < nblocks) throw std::runtime_error("corrupt container index");
+            const uint8_t* idx = c.data() + index_off;
             std::ofstream out(ofile, std::ios::binary | std::ios::trunc);
             for (uint64_t b = 0; b < nblocks; b++) {
-                const uint64_t len = get_u64(p, end);
-                if (uint64_t(end - p) < len) throw std::runtime_error("truncated container");
-                const std::vector<uint8_t> text = decompress_block(algo.empty() ? stored : algo, p, len);
+                const uint64_t off = get_u64(idx, end), len = get_u64(idx, end);
+                if (off > index_off || len > index_off - off) throw std::runtime_error("corrupt container index");
+                const std::vector<uint8_t> text = decompress_block(algo.empty() ? stored : algo, c.data() + off, len);
                 out.write(reinterpret_cast<const char*>(text.data()), std::streamsize(text.size()));
-                p += len;
             }
+            out.close();
+            if (!out) throw std::runtime_error("cannot write " + ofile);
             return 0;
         }
         const int fd = open(input.c_str(), O_RDONLY);
@@ -254,7 +272,24 @@ int main(int argc, char** argv) {
         const uint64_t in_size = uint64_t(sb.st_size);
         const uint64_t nblocks = (in_size + block - 1) / block;
         workers = int(std::min<uint64_t>(uint64_t(workers), nblocks ? nblocks : 1));
+        // the output file with its header, and the state shared with the workers: write cursor + index
+        const int out_fd = open(ofile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (out_fd < 0) throw std::runtime_error("cannot create " + ofile);
+        std::vector<uint8_t> head(MAGIC, MAGIC + sizeof(MAGIC) - 1);
+        auto head_u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) head.push_back(uint8_t(v >> (8 * i))); };
+        head_u64(block);
+        head_u64(nblocks);
+        for (int i = 0; i < 4; i++) head.push_back(uint8_t(uint32_t(algo.size()) >> (8 * i)));
+        head.insert(head.end(), algo.begin(), algo.end());
+        if (pwrite(out_fd, head.data(), head.size(), 0) != ssize_t(head.size())) throw std::runtime_error("cannot write " + ofile);
+        const size_t shared_bytes = sizeof(Shared) + size_t(nblocks) * 16;
+        void* shm = mmap(nullptr, shared_bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+        if (shm == MAP_FAILED) throw std::runtime_error("mmap failed");
+        Shared* shared = new (shm) Shared();
+        shared->cursor.store(head.size());
+        for (uint64_t bb = 0; bb < nblocks; bb++) { shared->entry(bb)[0] = 0; shared->entry(bb)[1] = ~uint64_t(0); }
         auto run_worker = [&](int k) {
+            const auto tw0 = std::chrono::steady_clock::now();
             if (workers > 1) setenv("TDCGPU_DEVICE", std::to_string(k).c_str(), 1);  // device k for worker k (GPU registry)
 #ifdef TDC_GPU_DEFAULT_TEXTDS
             if (const char* e = std::getenv("TDCGPU_DEVICE")) tdcgpu_set_device(std::atoi(e));  // pinned buffers belong to this worker's device
@@ -262,6 +297,8 @@ int main(int argc, char** argv) {
             const size_t cap = size_t(std::min<uint64_t>(block, in_size)) + 1;
             std::unique_ptr<BlockBuffer> bufs[2] = {std::make_unique<BlockBuffer>(cap), std::make_unique<BlockBuffer>(cap)};
             auto span = [&](uint64_t b) { return std::make_pair(b * block, size_t(std::min<uint64_t>(block, in_size - b * block))); };
+            if (std::getenv("TDC_BLOCK_VERBOSE"))
+                std::cerr << "[worker " << k << "] block buffers ready after " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count() << " ms\n";
             std::vector<uint8_t> arcs[2];  // archives of the current and the previous block (the latter being written)
             std::future<LoadedBlock> next;
             std::future<void> writing;
@@ -286,24 +323,22 @@ int main(int argc, char** argv) {
                               << ", " << arc->size() << " bytes out\n";
                     if (std::getenv("TDC_BLOCK_VERBOSE")[0] == '2') std::cerr << stats << "\n";
                 }
-                const std::string tmp = block_tmp(ofile, b);
-                writing = std::async(std::launch::async, [arc, tmp] {
-                    const std::string part = tmp + ".part";
-                    {
-                        std::ofstream t(part, std::ios::binary | std::ios::trunc);
-                        t.write(reinterpret_cast<const char*>(arc->data()), std::streamsize(arc->size()));
-                        t.close();
-                        if (!t) throw std::runtime_error("cannot write " + part);
+                writing = std::async(std::launch::async, [arc, b, shared, out_fd] {
+                    const uint64_t len = arc->size();
+                    const uint64_t off = shared->cursor.fetch_add(len);  // reserve the archive's place in the container
+                    for (uint64_t done = 0; done < len;) {
+                        const ssize_t w = pwrite(out_fd, arc->data() + done, size_t(std::min<uint64_t>(len - done, uint64_t(1) << 30)), off_t(off + done));
+                        if (w <= 0) throw std::runtime_error("cannot write the container");
+                        done += uint64_t(w);
                     }
-                    if (std::rename(part.c_str(), tmp.c_str()) != 0) throw std::runtime_error("cannot rename " + part);  // complete: visible to the assembler
+                    shared->entry(b)[0] = off;
+                    shared->entry(b)[1] = len;
                 });
                 cur ^= 1;
             }
             if (writing.valid()) writing.get();
         };
-        // Workers are always forked (before any CUDA call: every worker creates its own context on its own device), so
-        // that this process can assemble the container in block order WHILE they run: a finished block archive appears
-        // under its final name by rename() and is appended as soon as all earlier blocks are in.
+        // Workers are always forked (before any CUDA call: every worker creates its own context on its own device).
         std::vector<pid_t> pids;
         for (int k = 0; k < workers; k++) {
             const pid_t pid = fork();
@@ -320,62 +355,33 @@ int main(int argc, char** argv) {
             }
             pids.push_back(pid);
         }
-        auto cleanup = [&] {
-            for (uint64_t b = 0; b < nblocks; b++) {
-                std::remove(block_tmp(ofile, b).c_str());
-                std::remove((block_tmp(ofile, b) + ".part").c_str());
-            }
-        };
-        size_t live = pids.size();
         bool failed = false;
-        auto reap = [&](bool block_until_all) {  // collect exited workers; a failed one fails the run
-            while (live > 0) {
-                int st = 0;
-                const pid_t r = waitpid(-1, &st, block_until_all ? 0 : WNOHANG);
-                if (r <= 0) break;
-                live--;
-                if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) failed = true;
-            }
-        };
-        std::ofstream out(ofile, std::ios::binary | std::ios::trunc);
-        out.write(MAGIC, sizeof(MAGIC) - 1);
-        put_u64(out, block);
-        put_u64(out, nblocks);
-        put_u32(out, uint32_t(algo.size()));
-        out.write(algo.data(), std::streamsize(algo.size()));
-        uint64_t total = 0;
-        std::vector<char> chunk(size_t(16) << 20);
-        for (uint64_t b = 0; b < nblocks && !failed; b++) {
-            struct stat bs;
-            while (stat(block_tmp(ofile, b).c_str(), &bs) != 0) {  // not there yet
-                reap(false);
-                if (failed) break;
-                if (live == 0 && stat(block_tmp(ofile, b).c_str(), &bs) != 0) { failed = true; break; }
-                usleep(500);
-            }
-            if (failed) break;
-            std::ifstream t(block_tmp(ofile, b), std::ios::binary);
-            if (!t) { failed = true; break; }
-            const uint64_t alen = uint64_t(bs.st_size);
-            put_u64(out, alen);
-            for (uint64_t left = alen; left > 0;) {
-                const std::streamsize want = std::streamsize(std::min<uint64_t>(left, chunk.size()));
-                if (!t.read(chunk.data(), want)) { failed = true; break; }
-                out.write(chunk.data(), want);
-                left -= uint64_t(want);
-            }
-            total += alen;
-            t.close();
-            std::remove(block_tmp(ofile, b).c_str());
+        for (pid_t pid : pids) {
+            int st = 0;
+            waitpid(pid, &st, 0);
+            if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) failed = true;
         }
-        reap(true);
+        for (uint64_t bb = 0; bb < nblocks && !failed; bb++)
+            if (shared->entry(bb)[1] == ~uint64_t(0)) failed = true;  // a block nobody finished
         if (failed) {
-            cleanup();
-            out.close();
+            close(out_fd);
             std::remove(ofile.c_str());
             throw std::runtime_error("a worker failed");
         }
-        if (!out) throw std::runtime_error("cannot write " + ofile);
+        // index + trailer behind the last archive
+        const uint64_t index_off = shared->cursor.load();
+        std::vector<uint8_t> trailer;
+        auto push_u64 = [&](uint64_t v) { for (int i = 0; i < 8; i++) trailer.push_back(uint8_t(v >> (8 * i))); };
+        uint64_t total = 0;
+        for (uint64_t bb = 0; bb < nblocks; bb++) {
+            push_u64(shared->entry(bb)[0]);
+            push_u64(shared->entry(bb)[1]);
+            total += shared->entry(bb)[1];
+        }
+        push_u64(index_off);
+        trailer.insert(trailer.end(), MAGIC_END, MAGIC_END + sizeof(MAGIC_END) - 1);
+        if (pwrite(out_fd, trailer.data(), trailer.size(), off_t(index_off)) != ssize_t(trailer.size()) || close(out_fd) != 0)
+            throw std::runtime_error("cannot write " + ofile);
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::cerr << "tdc_block: " << in_size << " bytes in " << nblocks << " block(s) of " << block << " on " << workers
                   << " worker(s) -> " << total << " bytes, " << secs << " s (" << (secs > 0 ? in_size / 1e6 / secs : 0.0) << " MB/s)\n";
