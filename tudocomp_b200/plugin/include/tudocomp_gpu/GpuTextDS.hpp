@@ -73,8 +73,21 @@ inline tdcgpu_ctx* acquire_ctx() {
         cached_ctx() = nullptr;
         return c;
     }
+    // The first context of the process: unless the user restricted the visible devices, restrict them to the one device this
+    // process uses — the CUDA runtime then initialises one GPU instead of every GPU of the box (seconds of start-up on an
+    // 8-GPU node; the variable is read at the first CUDA call, which is the tdcgpu_create below).
+    static bool first = true;
+    int device = device_from_env();
+    if (first) {
+        first = false;
+        if (!std::getenv("CUDA_VISIBLE_DEVICES") && !std::getenv("TDCGPU_KEEP_ALL_DEVICES_VISIBLE")) {
+            setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1);
+            setenv("TDCGPU_DEVICE", "0", 1);
+            device = 0;
+        }
+    }
     tdcgpu_ctx* raw = nullptr;
-    check(tdcgpu_create(device_from_env(), &raw), "create");
+    check(tdcgpu_create(device, &raw), "create");
     return raw;
 }
 inline void release_ctx(tdcgpu_ctx* c) {

@@ -290,9 +290,28 @@ int main(int argc, char** argv) {
         for (uint64_t bb = 0; bb < nblocks; bb++) { shared->entry(bb)[0] = 0; shared->entry(bb)[1] = ~uint64_t(0); }
         auto run_worker = [&](int k) {
             const auto tw0 = std::chrono::steady_clock::now();
-            if (workers > 1) setenv("TDCGPU_DEVICE", std::to_string(k).c_str(), 1);  // device k for worker k (GPU registry)
 #ifdef TDC_GPU_DEFAULT_TEXTDS
-            if (const char* e = std::getenv("TDCGPU_DEVICE")) tdcgpu_set_device(std::atoi(e));  // pinned buffers belong to this worker's device
+            {
+                // Worker k sees ONLY its own GPU (CUDA_VISIBLE_DEVICES, set before the first CUDA call of this process): the
+                // runtime then initialises one device instead of all of the box (2.9 s of a worker's start on an 8-GPU
+                // box, profiles/r2_summary.md §5).  An existing CUDA_VISIBLE_DEVICES list is honoured: its k-th entry.
+                int dev = workers > 1 ? k : (std::getenv("TDCGPU_DEVICE") ? std::atoi(std::getenv("TDCGPU_DEVICE")) : 0);
+                std::string pick = std::to_string(dev);
+                if (const char* cvd = std::getenv("CUDA_VISIBLE_DEVICES")) {
+                    std::vector<std::string> ids;
+                    std::string cur;
+                    for (const char* p = cvd;; p++) {
+                        if (*p == ',' || *p == 0) { if (!cur.empty()) ids.push_back(cur); cur.clear(); if (!*p) break; }
+                        else cur.push_back(*p);
+                    }
+                    if (!ids.empty()) pick = ids[size_t(dev) % ids.size()];
+                }
+                setenv("CUDA_VISIBLE_DEVICES", pick.c_str(), 1);
+                setenv("TDCGPU_DEVICE", "0", 1);
+                tdcgpu_set_device(0);
+            }
+#else
+            if (workers > 1) setenv("TDCGPU_DEVICE", std::to_string(k).c_str(), 1);
 #endif
             const size_t cap = size_t(std::min<uint64_t>(block, in_size)) + 1;
             std::unique_ptr<BlockBuffer> bufs[2] = {std::make_unique<BlockBuffer>(cap), std::make_unique<BlockBuffer>(cap)};
