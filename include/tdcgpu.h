@@ -10,7 +10,8 @@
  *
  * Text contract (same as the reference, ds/TextDS.hpp:132-138, ds/SADivSufSort.hpp:21-26, driver.cpp:268-270):
  * `text` is the escaped input followed by exactly one 0 byte; n counts that byte; no other 0 occurs.
- * All indices are 32-bit (len_t = uint32_t, def.hpp:103,114); n must be < 2^31 like the reference's divsufsort path.
+ * All indices are UNSIGNED 32-bit (len_t = uint32_t, def.hpp:103,114).  The reference's default build stops at n < 2^31
+ * (divsufsort's sign bit); here n may reach 2^32 - 2^20 as long as common prefixes stay below 2^31 (checked).
  */
 #ifndef TDCGPU_H
 #define TDCGPU_H
@@ -36,7 +37,7 @@ typedef struct tdcgpu_ctx tdcgpu_ctx;
 #define TDCGPU_ERR_NOMEM (-2)     /* device scratch too small */
 #define TDCGPU_ERR_SENTINEL (-3)  /* text violates the sentinel contract ("Input has no sentinel!", TextDS.hpp:132-138) */
 #define TDCGPU_ERR_INTERNAL (-4)
-#define TDCGPU_ERR_ARG (-5)       /* bad argument (threshold 0, NULL, n >= 2^31, buffer too small) */
+#define TDCGPU_ERR_ARG (-5)       /* bad argument (threshold 0, NULL, n > 2^32 - 2^20, buffer too small) */
 #define TDCGPU_ERR_STATE (-6)     /* a required structure has not been built */
 
 /* lzss::Factor — compressors/lzss/LZSSFactors.hpp:13-20 (packed pos, src, len; len_compact_t = uint32_t) */

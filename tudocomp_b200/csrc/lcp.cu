@@ -68,16 +68,17 @@ int build_plcp_lcp(Ctx& c, bool want_lcp) {
     if (!tmp || !queue || !agg) { set_error("plcp: scratch arena too small"); return -2; }
     u32* d_qlen = c.d_scalars + 0;
     u32* d_max = c.d_scalars + 1;
-    TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 2 * sizeof(u32), st));
+    TDC_CUDA(cudaMemsetAsync(c.d_scalars, 0, 3 * sizeof(u32), st));
     TDC_LAUNCH(plcp_irreducible_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_text, c.d_phi, n, tmp, queue, d_qlen);
-    TDC_LAUNCH(plcp_long_kernel, u32(c.sm_count * 4), 256, 0, st, c.d_text, c.d_phi, tmp, queue, d_qlen);
+    TDC_LAUNCH(plcp_long_kernel, u32(c.sm_count * 4), 256, 0, st, c.d_text, c.d_phi, tmp, queue, d_qlen, c.d_scalars + 2);
     TDC_LAUNCH(plcp_fill_reduce_kernel, ntiles, PF_THREADS, 0, st, tmp, n, agg);
     TDC_LAUNCH(plcp_fill_scan_kernel, 1, 1024, 0, st, agg, ntiles);
     TDC_LAUNCH(plcp_fill_apply_kernel, ntiles, PF_THREADS, 0, st, tmp, c.d_phi, n, agg, c.d_plcp, d_max);
     if (want_lcp) TDC_LAUNCH(lcp_gather_kernel, u32(div_up(n, 256)), 256, 0, st, c.d_sa, c.d_plcp, n, c.d_lcp);
     TDC_KCHECK();
-    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    TDC_CUDA(cudaMemcpyAsync(c.h_scalars, c.d_scalars, 3 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     TDC_CUDA(cudaStreamSynchronize(st));
+    if (c.h_scalars[2]) { set_error("plcp: common prefixes of 2^31 bytes or more are not supported"); return -5; }
     c.max_lcp = c.h_scalars[1];
     return 0;
 }

@@ -66,7 +66,7 @@ plcp_irreducible_kernel(const uint8_t* __restrict__ text, const u32* __restrict_
 
 static __global__ void __launch_bounds__(256)
 plcp_long_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ phi, u32* __restrict__ tmp,
-                 const u32* __restrict__ queue, const u32* __restrict__ queue_len) {
+                 const u32* __restrict__ queue, const u32* __restrict__ queue_len, u32* __restrict__ too_long) {
     const u32 nq = *queue_len;
     const u32 warps = (gridDim.x * blockDim.x) >> 5;
     for (u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
@@ -74,7 +74,10 @@ plcp_long_kernel(const uint8_t* __restrict__ text, const u32* __restrict__ phi, 
         const u32 l0 = tmp[i] & ~PLCP_IRRED;
         const u32 l = lce_warp(text, i, phi[i], l0);
         __syncwarp();
-        if (lane_id() == 0) tmp[i] = l | PLCP_IRRED;
+        if (lane_id() == 0) {
+            tmp[i] = l | PLCP_IRRED;
+            if (l & PLCP_IRRED) *too_long = 1;  // a common prefix of 2^31 bytes or more (only possible beyond n = 2^31): reported by the host
+        }
     }
 }
 

@@ -41,7 +41,16 @@ for mode in none mixed only; do
     g++ $CXXFLAGS $extra -I$gen -c "$ROOT/tudocomp_b200/plugin/tdc_block.cpp" -o "$gen/tdc_block.o"
     bobjs=$(echo $objs | tr ' ' '\n' | grep -v tudocomp_driver.o | tr '\n' ' ')
     if [ "$mode" = only ]; then
-      g++ -o "$ROOT/build/$bbin" $bobjs "$gen/tdc_block.o" -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+      # tdc_block_gpu runs one worker THREAD per GPU (CUDA starts once per process), so its registry units are a second
+      # compile of the same generated sources with the reference's own -DSTATS_DISABLED (StatPhase is not thread-safe)
+      ns="$OUT/gen_only_nostats"; rm -rf "$ns"; mkdir -p "$ns"
+      nsobjs=""
+      for s in $srcs $REF/src/tudocomp_stat/StatPhase.cpp; do nsobjs="$nsobjs $ns/$(basename "${s%.cpp}").o"; done
+      for s in $srcs $REF/src/tudocomp_stat/StatPhase.cpp; do
+        echo "g++ $CXXFLAGS $extra -DSTATS_DISABLED -I$gen -c $s -o $ns/$(basename "${s%.cpp}").o"
+      done | xargs -P "$JOBS" -I{} sh -c '{}'
+      g++ $CXXFLAGS $extra -DSTATS_DISABLED -DTDC_BLOCK_THREADS -I$gen -c "$ROOT/tudocomp_b200/plugin/tdc_block.cpp" -o "$ns/tdc_block.o"
+      g++ -o "$ROOT/build/$bbin" $nsobjs "$ns/tdc_block.o" -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl -lpthread
     else
       g++ -o "$ROOT/build/$bbin" $bobjs "$gen/tdc_block.o" -ldl
     fi

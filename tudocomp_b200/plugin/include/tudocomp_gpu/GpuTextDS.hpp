@@ -50,21 +50,29 @@ namespace gpu_detail {
 inline void check(int rc, const char* what) {
     if (rc < 0) throw std::runtime_error(std::string("tdcgpu: ") + what + ": " + tdcgpu_last_error());
 }
+// Device of the calling THREAD: TDCGPU_DEVICE (default 0) unless the host program dealt this thread a device of its own
+// (tdc_block's worker threads: one thread per GPU in one process, so that CUDA is initialised once and not once per worker).
+inline int& thread_device_override() {
+    static thread_local int d = -1;
+    return d;
+}
 inline int device_from_env() {
+    if (thread_device_override() >= 0) return thread_device_override();
     const char* e = std::getenv("TDCGPU_DEVICE");
     return e ? std::atoi(e) : 0;
 }
-// One device context is kept alive between compress() calls of a process instead of creating and destroying one per text
+// One device context is kept alive between compress() calls of a thread instead of creating and destroying one per text
 // (TDCGPU_CTX_CACHE=0 switches this off): the arrays, the scratch arena (~57 n bytes) and the pinned staging buffers are
 // then allocated once for the largest text seen — per-call cudaMalloc/cudaFree of that much memory costs more than the
-// kernels for mid-size texts.  tdc itself is single-threaded, so one cached context is enough.  The cached
-// context is deliberately not destroyed at process exit (static destructors may run after the CUDA runtime has shut down).
+// kernels for mid-size texts.  tdc itself is single-threaded; the cache is per thread, so a multi-threaded host
+// gets one cached context per worker thread.  The cached context is deliberately not destroyed at exit (static destructors
+// may run after the CUDA runtime has shut down).
 inline bool ctx_cache_enabled() {
     const char* e = std::getenv("TDCGPU_CTX_CACHE");
     return !(e && *e == '0');
 }
 inline tdcgpu_ctx*& cached_ctx() {
-    static tdcgpu_ctx* c = nullptr;
+    static thread_local tdcgpu_ctx* c = nullptr;
     return c;
 }
 inline tdcgpu_ctx* acquire_ctx() {
@@ -73,12 +81,12 @@ inline tdcgpu_ctx* acquire_ctx() {
         cached_ctx() = nullptr;
         return c;
     }
-    // The first context of the process: unless the user restricted the visible devices, restrict them to the one device this
-    // process uses — the CUDA runtime then initialises one GPU instead of every GPU of the box (seconds of start-up on an
-    // 8-GPU node; the variable is read at the first CUDA call, which is the tdcgpu_create below).
+    // The first context of a single-device process: unless the user restricted the visible devices, restrict them to the one
+    // device this process uses — the CUDA runtime then initialises one GPU instead of every GPU of the box (seconds of
+    // start-up on an 8-GPU node; the variable is read at the first CUDA call, which is the tdcgpu_create below).
     static bool first = true;
     int device = device_from_env();
-    if (first) {
+    if (first && thread_device_override() < 0) {
         first = false;
         if (!std::getenv("CUDA_VISIBLE_DEVICES") && !std::getenv("TDCGPU_KEEP_ALL_DEVICES_VISIBLE")) {
             setenv("CUDA_VISIBLE_DEVICES", std::to_string(device).c_str(), 1);
@@ -244,7 +252,7 @@ struct PinnedBuffer {
 // the 16 MiB drain buffer of the archive streams, allocated once per process (tdc is single-threaded; like the cached
 // context it is deliberately not released at exit): cudaMallocHost + cudaFreeHost per compress() cost a few ms each
 inline PinnedBuffer& drain_buffer() {
-    static PinnedBuffer* b = new PinnedBuffer(size_t(16) << 20);
+    static thread_local PinnedBuffer* b = new PinnedBuffer(size_t(16) << 20);
     return *b;
 }
 

@@ -43,6 +43,10 @@
 
 #ifdef TDC_GPU_DEFAULT_TEXTDS
 #include "tdcgpu.h"  // pinned block buffers: the text goes to the device by DMA straight from where the file was read
+#include <tudocomp_gpu/GpuTextDS.hpp>  // gpu_detail::thread_device_override
+#endif
+#ifdef TDC_BLOCK_THREADS
+#include <mutex>
 #endif
 
 using namespace tdc;
@@ -157,9 +161,16 @@ protected:
 void compress_block(const std::string& algo, const uint8_t* data, size_t len, bool sentinel_follows, std::vector<uint8_t>& arc,
                     std::string* stats_json = nullptr) {
     auto& registry = tdc_algorithms::COMPRESSOR_REGISTRY;
+#ifdef TDC_BLOCK_THREADS
+    static std::mutex registry_mu;  // the registry is only read, but nothing in the reference promises that is thread-safe
+    std::unique_lock<std::mutex> registry_lock(registry_mu);
+#endif
     auto av = registry.parse_algorithm_id(algo);
     auto restrictions = av.textds_flags();
     auto compressor = registry.select_algorithm(av);
+#ifdef TDC_BLOCK_THREADS
+    registry_lock.unlock();
+#endif
     arc.clear();
     if (arc.capacity() < len / 2 + 4096) arc.reserve(len / 2 + 4096);
     {
@@ -180,7 +191,9 @@ void compress_block(const std::string& algo, const uint8_t* data, size_t len, bo
             compressor->compress(inp, out);
         }
         os.flush();
+#ifndef STATS_DISABLED
         if (stats_json) *stats_json = root.to_json().str();
+#endif
     }
 }
 
@@ -290,11 +303,18 @@ int main(int argc, char** argv) {
         for (uint64_t bb = 0; bb < nblocks; bb++) { shared->entry(bb)[0] = 0; shared->entry(bb)[1] = ~uint64_t(0); }
         auto run_worker = [&](int k) {
             const auto tw0 = std::chrono::steady_clock::now();
-#ifdef TDC_GPU_DEFAULT_TEXTDS
+#if defined(TDC_GPU_DEFAULT_TEXTDS) && defined(TDC_BLOCK_THREADS)
+            // worker THREAD k drives device k (first device of the process + k): its contexts, pinned buffers and copies
             {
-                // Worker k sees ONLY its own GPU (CUDA_VISIBLE_DEVICES, set before the first CUDA call of this process): the
-                // runtime then initialises one device instead of all of the box (2.9 s of a worker's start on an 8-GPU
-                // box, profiles/r2_summary.md §5).  An existing CUDA_VISIBLE_DEVICES list is honoured: its k-th entry.
+                const int dev = (std::getenv("TDCGPU_DEVICE") ? std::atoi(std::getenv("TDCGPU_DEVICE")) : 0) + k;
+                gpu_detail::thread_device_override() = dev;
+                tdcgpu_set_device(dev);
+            }
+#elif defined(TDC_GPU_DEFAULT_TEXTDS)
+            {
+                // Worker PROCESS k sees ONLY its own GPU (CUDA_VISIBLE_DEVICES, set before the first CUDA call of this process):
+                // the runtime then initialises one device instead of all of the box.  An existing CUDA_VISIBLE_DEVICES
+                // list is honoured: its k-th entry.
                 int dev = workers > 1 ? k : (std::getenv("TDCGPU_DEVICE") ? std::atoi(std::getenv("TDCGPU_DEVICE")) : 0);
                 std::string pick = std::to_string(dev);
                 if (const char* cvd = std::getenv("CUDA_VISIBLE_DEVICES")) {
@@ -357,7 +377,29 @@ int main(int argc, char** argv) {
             }
             if (writing.valid()) writing.get();
         };
-        // Workers are always forked (before any CUDA call: every worker creates its own context on its own device).
+        bool failed = false;
+#ifdef TDC_BLOCK_THREADS
+        // One worker THREAD per GPU in this process (the registry units of this build are compiled with -DSTATS_DISABLED, the
+        // reference's own switch, because StatPhase keeps an unsynchronised global): CUDA is initialised once.  With one
+        // PROCESS per GPU the eight concurrent CUDA start-ups of an 8-GPU box took 10.4 s before the first block
+        // (profiles/r2_summary.md §5).
+        {
+            std::vector<std::thread> th;
+            std::vector<int> rcs(size_t(workers), 0);
+            for (int k = 0; k < workers; k++)
+                th.emplace_back([&, k] {
+                    try {
+                        run_worker(k);
+                    } catch (const std::exception& e) {
+                        std::cerr << "Error (worker " << k << "): " << e.what() << std::endl;
+                        rcs[size_t(k)] = 1;
+                    }
+                });
+            for (auto& t : th) t.join();
+            for (int rc : rcs) failed = failed || rc != 0;
+        }
+#else
+        // Workers are forked before any CUDA call: every worker creates its own context on its own device.
         std::vector<pid_t> pids;
         for (int k = 0; k < workers; k++) {
             const pid_t pid = fork();
@@ -374,12 +416,12 @@ int main(int argc, char** argv) {
             }
             pids.push_back(pid);
         }
-        bool failed = false;
         for (pid_t pid : pids) {
             int st = 0;
             waitpid(pid, &st, 0);
             if (!(WIFEXITED(st) && WEXITSTATUS(st) == 0)) failed = true;
         }
+#endif
         for (uint64_t bb = 0; bb < nblocks && !failed; bb++)
             if (shared->entry(bb)[1] == ~uint64_t(0)) failed = true;  // a block nobody finished
         if (failed) {
