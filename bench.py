@@ -311,6 +311,7 @@ def dist_record(args, lib, rank, local_rank, world, dist, n_body, seed, steps, w
             verified["how"] = "every SA/ISA/LCP slot and every parse position, device checkers (csrc/check.cu)"
         except Exception as e:  # noqa: BLE001  (e.g. the gathered arrays do not fit next to the shards)
             verified = {"ok": None, "error": f"{type(e).__name__}: {e}"[:300]}
+    resident_result = (int(zt), int(mn), int(mx))
     barrier()
     t1 = time.perf_counter()
     ctx.event_record(2)
@@ -320,6 +321,8 @@ def dist_record(args, lib, rank, local_rank, world, dist, n_body, seed, steps, w
     ctx.event_record(3)
     barrier()
     e2e_ms = max(ctx.event_elapsed_ms(2, 3), 1e3 * (time.perf_counter() - t1))
+    # the host-text route (slice upload + peer exchange on several GPUs) must give the verified resident step's factorisation
+    e2e_consistent = (int(zt), int(mn), int(mx)) == resident_result
     ms_step = blockmode.reduce_step_time(dev_ms / steps, dist if world > 1 else None)
     ms_step_e2e = blockmode.reduce_step_time(e2e_ms / steps, dist if world > 1 else None)
     ctx.close()
@@ -342,7 +345,8 @@ def dist_record(args, lib, rank, local_rank, world, dist, n_body, seed, steps, w
             "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
                     "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
             "gpu_launches": int(launches), "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
-            "dist_stats": stats, "shard_rank0": info, "verify": verified, "kernels": kernel_table(prof),
+            "dist_stats": stats, "shard_rank0": info, "verify": verified, "e2e_same_factorisation_as_verified_step": e2e_consistent,
+            "kernels": kernel_table(prof),
             "last_step_phases_ms": {k: round(v, 3) for k, v in phases}}
 
 

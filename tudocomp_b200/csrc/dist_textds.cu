@@ -871,11 +871,45 @@ int tdcgpu_dist_set_text(tdcgpu_dist* h, const uint8_t* text, uint64_t n, int on
     c.max_lcp = 0;
     c.num_factors = 0;
     c.phases.clear();
-    // EXPERIMENT (TDCGPU_DIST_SLICE_UPLOAD=1, off by default until measured on >= 2 GPUs): every rank uploads only its own
-    // n/P slice over PCIe and receives the other slices from its peers over NVLink, instead of n bytes over PCIe per rank
-    // (the end-to-end figure of the sharded path is bounded by exactly that copy, profiles/r1m_summary.md).
+    // Slice upload: every rank uploads only its own n/P slice over PCIe and receives the other slices from its peers over
+    // NVLink, instead of n bytes over PCIe per rank (which bounds the end-to-end figure of the sharded path: 8 ranks x 4 GB
+    // through one host, profiles/r2_summary.md §4).  Peer-memory transport: the slice is pushed into every peer's
+    // SCRATCH ARENA (the window all ranks have mapped; its content is dead between two texts) at the slice's own text
+    // offset, and every rank then copies the received slices from its arena into its text buffer.  Two host barriers:
+    // "your arena is free" before the pushes, "all pushes have landed" after them.  Default when the peer window exists;
+    // TDCGPU_DIST_SLICE_UPLOAD=0 switches it off, =nccl takes grouped ncclSend/ncclRecv into the text buffer instead
+    // (measured 8x slower than the redundant upload at 8 GPUs, r2o_distab.txt).
     const char* slice_env = std::getenv("TDCGPU_DIST_SLICE_UPLOAD");
-    if (!on_device && d.P > 1 && slice_env && *slice_env && *slice_env != '0') {
+    const bool slice_off = slice_env && slice_env[0] == '0';
+    const bool slice_nccl = slice_env && slice_env[0] == 'n';
+    if (!on_device && d.P > 1 && !slice_off && d.p2p && !slice_nccl && c.arena.cap >= n) {
+        cudaStream_t st = c.stream;
+        TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, st));
+        if (d.pos_cnt) TDC_TRY(host_copy(c, c.d_text + d.pos_lo, text + d.pos_lo, d.pos_cnt, true));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        u64 token = 1;
+        std::vector<u64> all(d.P);
+        TDC_TRY(d.comm->allgather_host(&token, all.data(), sizeof(u64)));  // every rank is done with its previous text: arenas are free
+        u64 bytes = 0;
+        if (d.pos_cnt) {
+            for (int p = 0; p < d.P; p++) {
+                if (p == d.rank) continue;
+                TDC_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(d.peer_arena[p]) + d.pos_lo, c.d_text + d.pos_lo, d.pos_cnt, cudaMemcpyDeviceToDevice, d.copy_streams[p]));
+                bytes += d.pos_cnt;
+            }
+            for (int p = 0; p < d.P; p++)
+                if (p != d.rank) TDC_CUDA(cudaStreamSynchronize(d.copy_streams[p]));
+        }
+        d.p2p_bytes += bytes;
+        TDC_TRY(d.comm->allgather_host(&token, all.data(), sizeof(u64)));  // all pushes have landed
+        // the peers' slices: arena -> text (everything but the own slice)
+        if (d.pos_lo) TDC_CUDA(cudaMemcpyAsync(c.d_text, c.arena.base, d.pos_lo, cudaMemcpyDeviceToDevice, st));
+        const u64 hi = d.pos_lo + d.pos_cnt;
+        if (hi < n) TDC_CUDA(cudaMemcpyAsync(c.d_text + hi, c.arena.base + hi, n - hi, cudaMemcpyDeviceToDevice, st));
+        TDC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }
+    if (!on_device && d.P > 1 && slice_nccl) {
         TDC_CUDA(cudaMemsetAsync(c.d_text + n, 0, 1024 + 16, c.stream));
         if (d.pos_cnt) TDC_TRY(host_copy(c, c.d_text + d.pos_lo, text + d.pos_lo, d.pos_cnt, true));
         TDC_CUDA(cudaStreamSynchronize(c.stream));
