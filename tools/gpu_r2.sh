@@ -109,7 +109,7 @@ PY
       echo "ncu rc=$?"; tail -3 gpurun_out/${tag}_ncu.log ;;
     distab)  # sharded path A/B on all GPUs of the box: every rank uploads the whole text vs its own slice (+ peer exchange)
       N=$(nvidia-smi -L | wc -l)
-      for su in 0 1; do
+      for su in ${SLICE_MODES:-0 1}; do
         TDCGPU_DIST_SLICE_UPLOAD=$su timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2961$su bench.py --gpus $N --mode dist --bytes ${DIST_BYTES:-2000000000} --steps 3 --warmup 2 > gpurun_out/${tag}_dist_n${N}_slice$su.json 2> gpurun_out/${tag}_dist_n${N}_slice$su.err
         python - <<PY
 import json
