@@ -342,7 +342,10 @@ def dist_record(args, lib, rank, local_rank, world, dist, n_body, seed, steps, w
                        "l2_policy": "working set per GPU far larger than the 126 MB L2; no flush needed",
                        "parallelism": (f"one text sharded over {world} GPUs; all-to-all of rank buckets, rank updates and rank requests"
                                        if not single else "N = 1 point of the strong-scaling curve: the single-GPU context on the same text")},
-            "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s", "h2d_bytes_per_step": n * world,
+            # slice upload (default on several GPUs with the peer-memory window): every rank copies its n/P slice from the host
+            # and the peers exchange the rest over NVLink; otherwise every rank uploads the whole text
+            "e2e": {"value": blockmode.job_throughput_mb_s(n_body, ms_step_e2e), "unit": "MB/s",
+                    "h2d_bytes_per_step": n if (world > 1 and stats.get("p2p") and os.environ.get("TDCGPU_DIST_SLICE_UPLOAD", "1")[:1] not in ("0", "n")) else n * world,
                     "d2h_bytes_per_step": int(12 * zt), "ms_per_step": ms_step_e2e},
             "gpu_launches": int(launches), "roofline": roof, "factors": int(zt), "factor_len": [int(mn), int(mx)],
             "dist_stats": stats, "shard_rank0": info, "verify": verified, "e2e_same_factorisation_as_verified_step": e2e_consistent,
@@ -361,6 +364,7 @@ def main():
     ap.add_argument("--bytes", type=int, default=0, help="text body size in bytes (overrides --log2-bytes), e.g. 4000000000")
     ap.add_argument("--no-verify", action="store_true", help="skip the full device-side verification after the timed regions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-block-driver", action="store_true", help="skip the tdc_block_gpu sub-record (config 5 through the plugin driver)")
     ap.add_argument("--no-dist", action="store_true", help="default mode: skip the sharded-text sub-records (config 4)")
     ap.add_argument("--no-pipeline", action="store_true", help="skip the double-buffered (2 contexts) end-to-end measurement")
     ap.add_argument("--dist-bytes", type=int, default=2_000_000_000, help="text size of the sharded sub-record (strong scaling over N)")
@@ -710,12 +714,69 @@ def main():
                 recs.append(rec)
         if rank == 0:
             line["dist"] = recs
+    # ---- config 5 through the real plugin driver: tdc_block_gpu over the GPU registry, 256 MiB blocks, Huffman coder ----
+    if rank == 0 and not args.no_block_driver:
+        try:
+            bd = block_driver_record(world, local_rank)
+        except Exception as e:  # noqa: BLE001
+            bd = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if bd:
+            line["block_driver"] = bd
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def block_driver_record(world, device):
+    """BASELINE config 5 as a cold command-line run: `build/tdc_block_gpu -a "lzss_lcp(coder=huff)" -b 268435456 -g N` on an
+    order-3 Markov text in /dev/shm (4 blocks per GPU, generated on the GPU), one worker thread per GPU, wall clock of the
+    whole process incl. CUDA start-up.  The per-block times come from the driver's own log.  Absent binary -> no record."""
+    import re
+    import shutil
+    import subprocess
+    import torch
+    from tudocomp_b200 import synth
+    exe = os.path.join(ROOT, "build", "tdc_block_gpu")
+    if not os.path.exists(exe) or not os.path.isdir("/dev/shm"):
+        return None
+    gib = 4 if world == 1 else world
+    if shutil.disk_usage("/dev/shm").free < (2 * gib + 1) << 30:
+        return {"skipped": "not enough room in /dev/shm"}
+    src, dst = "/dev/shm/tdc_bench_block_in.txt", "/dev/shm/tdc_bench_block_out.tdcb"
+    try:
+        with open(src, "wb") as f:
+            for i in range(gib):
+                f.write(synth.markov_text_device(1 << 30, 500 + i, f"cuda:{device}").cpu().numpy().tobytes())
+        torch.cuda.empty_cache()
+        env = dict(os.environ, TDC_BLOCK_VERBOSE="1")
+        for k in ("CUDA_VISIBLE_DEVICES",):  # the workers address the GPUs of the box themselves
+            env.pop(k, None)
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, "-a", "lzss_lcp(coder=huff)", "-b", str(1 << 28), "-g", str(world), src, "-o", dst],
+                           capture_output=True, text=True, timeout=600, env=env)
+        wall = time.perf_counter() - t0
+        if r.returncode != 0:
+            return {"error": r.stderr[-300:]}
+        comp = [float(x) for x in re.findall(r"compress ([0-9.]+) ms", r.stderr)]
+        ready = [float(x) for x in re.findall(r"block buffers ready after ([0-9.]+) ms", r.stderr)]
+        out_bytes = os.path.getsize(dst)
+        comp_sorted = sorted(comp)
+        return {"what": "tdc_block_gpu -a lzss_lcp(coder=huff) -b 268435456 -g N: cold command-line run over the GPU-only registry, file in "
+                        "/dev/shm -> container in /dev/shm, wall clock of the whole process (CUDA context creation included)",
+                "input_bytes": gib << 30, "blocks": len(comp), "gpus": world, "wall_s": round(wall, 3),
+                "MB_per_s": round((gib << 30) / 1e6 / wall, 1), "container_bytes": out_bytes,
+                "worker_ready_after_ms": [round(x) for x in ready],
+                "compress_ms_per_block_median": round(comp_sorted[len(comp_sorted) // 2], 1) if comp else None,
+                "compress_ms_per_block_first": round(comp[0], 1) if comp else None}
+    finally:
+        for p_ in (src, dst):
+            try:
+                os.remove(p_)
+            except OSError:
+                pass
 
 
 def plugin_e2e(text, n_body, steps):

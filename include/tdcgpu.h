@@ -80,7 +80,7 @@ int tdcgpu_textds_get(tdcgpu_ctx* ctx, uint32_t which, void* dst, int to_device)
  * (bits_for(n) for SA/ISA/Phi, bits_for(max_lcp) for PLCP/LCP: ds/SADivSufSort.hpp:53-63, LCPFromPLCP.hpp:56-66); doing
  * it here replaces the serial re-pack of BitPackingVector::resize (ds/BitPackingVector.hpp:478-540) and shrinks the
  * device-to-host copy from 4n to n*width/8 bytes.  dst holds cap_words >= ceil(n*width/64) words; unused high bits of the
- * last word are 0.  1 <= width <= 32.  Uses (and thereby invalidates) the context's scratch. */
+ * last word are 0.  1 <= width <= 64 (the values are 32-bit: widths above 32 widen, for wide-index builds of the caller).  Uses (and thereby invalidates) the context's scratch. */
 int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, uint64_t* dst, uint64_t cap_words, int to_device);
 
 /* Device pointer of a built structure (valid until the next set_text/destroy); NULL if not built. */

@@ -113,6 +113,34 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
     assert open(tmp_path / "h.tdc", "rb").read() == open(tmp_path / "ref.tdc", "rb").read()
 
 
+@pytest.mark.sim
+def test_plugin_in_a_wide_index_build_of_the_reference(tmp_path):
+    """-DLEN_BITS=40 (def.hpp:100-114: len_t becomes 64-bit, the archive's length field 64 bits wide): the plugin compiles
+    against that build and LZSSLCPCompressor<coder, GpuTextDS> (over the interpreter library) writes the archive that the
+    same build's CPU TextDS<> writes — 4 bytes longer than the default build's."""
+    wide, narrow = os.path.join(ROOT, "build", "tdc_plugin_bench40"), os.path.join(ROOT, "build", "tdc_plugin_bench")
+    if not (os.path.exists(wide) and os.path.exists(narrow)):
+        pytest.skip("tdc_plugin_bench40 not built (bash tudocomp_b200/plugin/build_tdc.sh; needs /root/reference)")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    simdir = tmp_path / "simlib"
+    simdir.mkdir()
+    os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
+    import json
+    for name, data in (("markov", synth.markov_text(9000, 5)[:-1].tobytes()), ("dna", synth.dna(5000, 6)[:-1].tobytes()), ("one", b"a")):
+        src = tmp_path / f"{name}.bin"
+        src.write_bytes(data)
+        for coder in ("huff", "bit"):
+            rec = {}
+            for exe, gpu in ((wide, "1"), (wide, "0"), (narrow, "1")):
+                r = subprocess.run([exe, str(src), coder, "3", "1", gpu, str(tmp_path / "o.bin")], capture_output=True, text=True, env=env)
+                assert r.returncode == 0, (name, coder, r.stderr)
+                d = json.loads(r.stdout.strip().splitlines()[-1])
+                rec[(exe, gpu)] = (d["archive_bytes"], d["archive_fnv1a"])
+            assert rec[(wide, "1")] == rec[(wide, "0")], (name, coder, rec)
+            assert rec[(wide, "1")][0] == rec[(narrow, "1")][0] + 4, (name, coder, rec)
+
+
 def _block_container(path):
     """(block_bytes, algo, [archive bytes per block]) of a tdc_block container (tudocomp_b200/plugin/tdc_block.cpp):
     header, archives in completion order, index (offset, length per block, in block order), index offset, end mark."""

@@ -20,7 +20,7 @@ for stage in "$@"; do
       echo "bench rc=$?"; head -c 3000 gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err ;;
     launches)
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${tag}_launches.csv \
-        python bench.py --steps 2 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
+        python bench.py --steps 2 --warmup 1 --no-dist --no-block-driver --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_launches_bench.log 2>&1
       echo "launches rc=$?" ;;
     sortbench)  # A/B of radix-pass variants built by: nvcc ... -D<flag> tools/sortbench.cu -o build/sortbench_<name>
       { for b in build/sortbench_*; do echo "== $b"; timeout 120 $b ${SORT_LG:-28} 48; timeout 120 $b ${SORT_LG:-28} 33 keys; done; } 2>&1 | tee gpurun_out/${tag}_sortbench.txt ;;
@@ -30,7 +30,7 @@ for stage in "$@"; do
       echo "ncusort rc=$?"; tail -2 gpurun_out/${tag}_ncu_sortpass.log ;;
     benchmodes)  # the initial-sort layouts side by side (resident timing only)
       for mode in wide packed; do
-        TDCGPU_SA_MODE=$mode timeout 600 python bench.py --steps 5 --warmup 2 --no-dist --no-pipeline --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_$mode.json 2> gpurun_out/${tag}_bench_$mode.err
+        TDCGPU_SA_MODE=$mode timeout 600 python bench.py --steps 5 --warmup 2 --no-dist --no-block-driver --no-pipeline --no-cpu-baseline ${BENCH_ARGS:-} > gpurun_out/${tag}_bench_$mode.json 2> gpurun_out/${tag}_bench_$mode.err
         echo "$mode rc=$?"; python - <<PY
 import json
 d=json.load(open("gpurun_out/${tag}_bench_$mode.json"))
@@ -41,9 +41,9 @@ PY
     plugintests)
       timeout 900 python -m pytest tests/test_plugin.py tests/test_encode.py tests/test_check.py tests/test_stream_stages.py -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${tag}_plugintests.txt ;;
     workloads)  # the other single-GPU configs of BASELINE.json: 100 MB Markov (1), 2^30 B repetitive (3); resident + e2e, verified
-      timeout 600 python bench.py --steps 5 --warmup 2 --workload markov --bytes 100000000 --no-dist --no-cpu-baseline > gpurun_out/${tag}_bench_markov1e8.json 2> gpurun_out/${tag}_bench_markov1e8.err
+      timeout 600 python bench.py --steps 5 --warmup 2 --workload markov --bytes 100000000 --no-dist --no-block-driver --no-cpu-baseline > gpurun_out/${tag}_bench_markov1e8.json 2> gpurun_out/${tag}_bench_markov1e8.err
       echo "markov rc=$?"
-      timeout 900 python bench.py --steps 3 --warmup 1 --workload repetitive --log2-bytes 30 --no-dist --no-cpu-baseline --no-pipeline > gpurun_out/${tag}_bench_rep30.json 2> gpurun_out/${tag}_bench_rep30.err
+      timeout 900 python bench.py --steps 3 --warmup 1 --workload repetitive --log2-bytes 30 --no-dist --no-block-driver --no-cpu-baseline --no-pipeline > gpurun_out/${tag}_bench_rep30.json 2> gpurun_out/${tag}_bench_rep30.err
       echo "repetitive rc=$?"
       python - <<PY
 import json
@@ -105,7 +105,7 @@ PY
       } 2>&1 | tee gpurun_out/${tag}_chain.txt ;;
     ncu)  # one `ncu --set full` capture of the dominant kernel inside the real bench (full-size launch: skip the sample sort)
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:${NCU_KERNEL:-rs_onesweep} -s ${NCU_SKIP:-3} -c 1 -o gpurun_out/${tag}_ncu -f \
-        python bench.py --steps 1 --warmup 1 --no-dist --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_ncu.log 2>&1
+        python bench.py --steps 1 --warmup 1 --no-dist --no-block-driver --no-pipeline --no-cpu-baseline --no-verify > gpurun_out/${tag}_ncu.log 2>&1
       echo "ncu rc=$?"; tail -3 gpurun_out/${tag}_ncu.log ;;
     distab)  # sharded path A/B on all GPUs of the box: every rank uploads the whole text vs its own slice (+ peer exchange)
       N=$(nvidia-smi -L | wc -l)

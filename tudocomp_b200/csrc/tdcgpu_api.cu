@@ -358,7 +358,7 @@ int tdcgpu_textds_get_packed(tdcgpu_ctx* ctx, uint32_t which, uint32_t width, ui
     void* src = array_ptr(c, which, &elem);
     if (!dst) { set_error("null destination"); return TDCGPU_ERR_ARG; }
     if (!src || !(c.have & which)) { set_error("structure 0x%x has not been built", which); return TDCGPU_ERR_STATE; }
-    if (elem != 4 || width < 1 || width > 32) { set_error("get_packed: 32-bit arrays only, 1 <= width <= 32"); return TDCGPU_ERR_ARG; }
+    if (elem != 4 || width < 1 || width > 64) { set_error("get_packed: 32-bit arrays only, 1 <= width <= 64"); return TDCGPU_ERR_ARG; }
     const u64 nwords = div_up(c.n * u64(width), 64);
     ComputeLock lock(c.device);
     if (cap_words < nwords) { set_error("get_packed: buffer too small: %llu < %llu words", (unsigned long long)cap_words, (unsigned long long)nwords); return TDCGPU_ERR_ARG; }

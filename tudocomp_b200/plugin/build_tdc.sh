@@ -62,4 +62,9 @@ gen="$OUT/gen_only"
 g++ $CXXFLAGS -I"$gen" "$ROOT/tudocomp_b200/plugin/tdc_plugin_bench.cpp" "$REF/src/tudocomp_stat/StatPhase.cpp" -o "$ROOT/build/tdc_plugin_bench" \
   -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
 echo "built build/tdc_plugin_bench"
+# the same harness against a WIDE-INDEX build of the reference (-DLEN_BITS=40: 64-bit len_t, def.hpp:100-114): shows that the
+# plugin compiles there and checks its archives against the reference's own wide-index code (tests/test_plugin.py)
+g++ $CXXFLAGS -DLEN_BITS=40 -I"$gen" "$ROOT/tudocomp_b200/plugin/tdc_plugin_bench.cpp" "$REF/src/tudocomp_stat/StatPhase.cpp" -o "$ROOT/build/tdc_plugin_bench40" \
+  -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+echo "built build/tdc_plugin_bench40"
 

@@ -316,14 +316,15 @@ private:
                 const size_t n = m_text.size();
                 gpu_detail::check(tdcgpu_textds_build(m_ctx.get(), which), title);
                 gpu_detail::log_phases(m_ctx.get());
-                static_assert(INDEX_FAST_BITS == 32, "the C ABI hands back 32-bit indices (default build, def.hpp:103,128)");
+                // the device holds 32-bit indices; a wide-index build of the reference (-DLEN_BITS=40: INDEX_FAST_BITS == 64,
+                // def.hpp:100-128) gets them widened by the same packing kernel that narrows them for `compress`
                 uint32_t mx = 0;
                 if (lcp_width) gpu_detail::check(tdcgpu_textds_max_lcp(m_ctx.get(), &mx), title);
                 // "delayed" and "compressed" end in the same narrowed state (bits_for(n) / bits_for(max_lcp)); the device
                 // packs to that width, so neither 4n bytes cross PCIe nor BitPackingVector::resize re-packs serially
                 const uint8_t width = m_cm == CompressMode::plain ? uint8_t(INDEX_FAST_BITS) : uint8_t(lcp_width ? bits_for(mx) : bits_for(n));
                 DynamicIntVector iv(n, 0, width);
-                if (width == INDEX_FAST_BITS) {
+                if (width == 32) {
                     gpu_detail::check(tdcgpu_textds_get(m_ctx.get(), which, iv.data(), 0), title);
                 } else {
                     gpu_detail::check(tdcgpu_textds_get_packed(m_ctx.get(), which, width, iv.data(), (uint64_t(n) * width + 63) / 64, 0), title);
