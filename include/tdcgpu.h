@@ -63,6 +63,13 @@ void tdcgpu_destroy(tdcgpu_ctx* ctx);
  * call returns after the copy has finished, so the source may be overwritten afterwards. */
 int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_device);
 
+/* tdcgpu_set_text for a HOST text, except that the structures already built stay valid when the context's resident text
+ * has exactly these bytes (the new text is uploaded next to it and compared on the device).  For callers that meet the same
+ * text several times without being able to say so: the per-provider classes of the plugin (`textds(sa=gpu, lcp=gpu, ...)`,
+ * tudocomp_gpu/GpuProviders.hpp), which the reference's TextDS constructs one after the other (ds/TextDS.hpp:247-292).
+ * *reused = 1 if nothing had to be invalidated. */
+int tdcgpu_set_text_cached(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int* reused);
+
 /* Build the requested structures on the device (they stay resident).  Replaces TextDS::require
  * (ds/TextDS.hpp:247-292) and the provider constructors it calls: SADivSufSort.hpp:28-51, PhiFromSA.hpp:24-48,
  * PLCPFromPhi.hpp:27-53, LCPFromPLCP.hpp:27-54, ISAFromSA.hpp:24-46.  Dependencies are built implicitly. */

@@ -87,6 +87,21 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
         back = str(tmp_path / "back.bin")
         r = subprocess.run([GPU_ONLY, "-d", b, "-o", back, "--force"], capture_output=True, text=True, env=env)
         assert r.returncode == 0 and open(back, "rb").read() == src.read_bytes(), (algo, r.stderr)
+    # per-provider GPU classes inside the reference's own TextDS (GpuProviders.hpp; the provider concept of ds/TextDS.hpp:23-29):
+    # `textds(sa=gpu)`, `textds(sa=gpu, lcp=gpu, isa=gpu)`; the later providers find the text resident (gpu_text_reused = 1)
+    for name in ("markov", "binary_with_escapes", "empty"):
+        src = str(tmp_path / f"{name}.bin")
+        for algo, sel in (("lzss_lcp(coder=huff)", "lzss_lcp(coder=huff, textds=textds(sa=gpu))"),
+                          ("lzss_lcp(coder=bit)", "lzss_lcp(coder=bit, textds=textds(sa=gpu, lcp=gpu, isa=gpu))"),
+                          ("lzss_lcp(coder=huff)", 'lzss_lcp(coder=huff, textds=textds(lcp=gpu, isa=gpu, compress="plain"))'),
+                          ("bwt", "bwt(textds=textds(sa=gpu))")):
+            a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "sim.tdc")
+            assert _run(REF, algo, src, a, ["--raw"]).returncode == 0
+            r = subprocess.run([GPU, "-a", sel, src, "-o", b, "--force", "--raw", "--stats"], capture_output=True, text=True, env=env)
+            assert r.returncode == 0, (name, sel, r.stderr)
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, sel)
+            if "sa=gpu, lcp=gpu, isa=gpu" in sel and name == "markov":
+                assert r.stdout.count('"gpu_text_reused"') == 3 and r.stdout.count('"value": "1"') >= 2, r.stdout[:2000]
     # lcpcomp: the reference's own strategies consume the GPU text index through require_* / release_*
     # (arrays come back bit-packed by the device, compress=delayed); mixed registry, so compare under --raw
     for name in ("markov", "empty"):
@@ -252,6 +267,20 @@ def test_archives_byte_identical_to_reference_driver(tmp_path):
         r = subprocess.run([REF, "-d", c, "-o", back, "--force"], capture_output=True, text=True)
         assert r.returncode == 0, r.stderr
         assert open(back, "rb").read() == open(src, "rb").read(), name
+
+
+@pytest.mark.gpu
+def test_per_provider_gpu_classes(tmp_path):
+    """`textds(sa=gpu, ...)`: GPU providers inside the reference's TextDS, the rest of the pipeline is the reference's CPU code."""
+    _need_bins()
+    for name, src in _inputs(tmp_path).items():
+        for algo, sel in (("lzss_lcp(coder=huff)", "lzss_lcp(coder=huff, textds=textds(sa=gpu, lcp=gpu, isa=gpu))"),
+                          ("lzss_lcp(coder=bit,threshold=5)", "lzss_lcp(coder=bit, threshold=5, textds=textds(sa=gpu))"),
+                          ("bwt", "bwt(textds=textds(sa=gpu))")):
+            a, b = str(tmp_path / "ref.tdc"), str(tmp_path / "gpu.tdc")
+            assert _run(REF, algo, src, a, ["--raw"]).returncode == 0
+            assert _run(GPU, sel, src, b, ["--raw"]).returncode == 0, (name, sel)
+            assert open(a, "rb").read() == open(b, "rb").read(), (name, sel)
 
 
 @pytest.mark.gpu

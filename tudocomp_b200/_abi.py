@@ -21,7 +21,7 @@ EXPORTS = [
     "tdcgpu_profile_reset", "tdcgpu_profile_count", "tdcgpu_profile_entry",
     "tdcgpu_lzss_literal_histogram", "tdcgpu_lzss_encode", "tdcgpu_lzss_encode_get", "tdcgpu_textds_get_packed",
     "tdcgpu_mtf_encode", "tdcgpu_rle_encode", "tdcgpu_literal_encode_begin", "tdcgpu_literal_encode", "tdcgpu_literal_encode_get",
-    "tdcgpu_lzss_encode_get_chunk", "tdcgpu_literal_encode_get_chunk", "tdcgpu_pinned_alloc", "tdcgpu_pinned_free", "tdcgpu_set_device", "tdcgpu_set_len_bits", "tdcgpu_device_alloc", "tdcgpu_device_free", "tdcgpu_device_copy",
+    "tdcgpu_lzss_encode_get_chunk", "tdcgpu_literal_encode_get_chunk", "tdcgpu_pinned_alloc", "tdcgpu_pinned_free", "tdcgpu_set_device", "tdcgpu_set_text_cached", "tdcgpu_set_len_bits", "tdcgpu_device_alloc", "tdcgpu_device_free", "tdcgpu_device_copy",
     "tdcgpu_sa_layout", "tdcgpu_check_index", "tdcgpu_check_factors", "tdcgpu_text_device_ptr", "tdcgpu_factors_device_ptr",
 ]
 

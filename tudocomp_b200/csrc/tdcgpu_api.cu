@@ -224,6 +224,18 @@ pack_bits_kernel(const u32* __restrict__ a, u64 n, u32 w, u64* __restrict__ out,
     out[j] = acc;
 }
 
+// do two device buffers of n bytes differ?  (both readable up to the next multiple of 16)
+static __global__ void __launch_bounds__(256) bytes_differ_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, u64 n, u32* __restrict__ flag) {
+    const u64 nvec = n / 16;
+    bool diff = false;
+    for (u64 v = u64(blockIdx.x) * blockDim.x + threadIdx.x; v < nvec; v += u64(gridDim.x) * blockDim.x) {
+        const uint4 x = reinterpret_cast<const uint4*>(a)[v], y = reinterpret_cast<const uint4*>(b)[v];
+        diff |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 15u)) diff |= a[nvec * 16 + threadIdx.x] != b[nvec * 16 + threadIdx.x];
+    if (diff) *flag = 1;
+}
+
 static void* array_ptr(Ctx& c, u32 which, size_t* elem) {
     *elem = 4;
     switch (which) {
@@ -331,6 +343,33 @@ int tdcgpu_set_text(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int on_dev
         TDC_TRY(host_copy(c, c.d_text, text, n, true));  // blocking: the caller may reuse its buffer
     }
     return 0;
+}
+
+int tdcgpu_set_text_cached(tdcgpu_ctx* ctx, const uint8_t* text, uint64_t n, int* reused) {
+    if (reused) *reused = 0;
+    {
+        API_GUARD(ctx);
+        if (text && n > 0 && c.n == n && c.d_text && c.arena.cap >= n + 64) {
+            // the same length as the resident text: upload next to it and compare on the device (exact, not a hash)
+            c.arena.reset();
+            uint8_t* tmp = c.arena.take<uint8_t>(n + 16);
+            u32* flag = c.d_scalars + 3;
+            if (tmp) {
+                TDC_CUDA(cudaMemsetAsync(flag, 0, sizeof(u32), c.stream));
+                TDC_TRY(host_copy(c, tmp, text, n, true));
+                TDC_LAUNCH(bytes_differ_kernel, u32(std::min<u64>(u64(c.sm_count) * 8, div_up(n / 16 + 1, 256))), 256, 0, c.stream, tmp, c.d_text, n, flag);
+                TDC_KCHECK();
+                u32 h = 1;
+                TDC_CUDA(cudaMemcpyAsync(&h, flag, sizeof(u32), cudaMemcpyDeviceToHost, c.stream));
+                TDC_CUDA(cudaStreamSynchronize(c.stream));
+                if (h == 0) {
+                    if (reused) *reused = 1;
+                    return 0;
+                }
+            }
+        }
+    }
+    return tdcgpu_set_text(ctx, text, n, 0);
 }
 
 int tdcgpu_textds_build(tdcgpu_ctx* ctx, uint32_t flags) {

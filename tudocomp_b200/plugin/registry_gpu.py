@@ -28,6 +28,15 @@ lcp = [AlgorithmConfig(name="LCPFromPLCP", header="ds/LCPFromPLCP.hpp")]
 isa = [AlgorithmConfig(name="ISAFromSA", header="ds/ISAFromSA.hpp")]
 
 cpu_textds = [AlgorithmConfig(name="TextDS", header="ds/TextDS.hpp", sub=[sa, phi, plcp, lcp, isa])]
+# added lines (mixed registry): GPU-backed PROVIDERS next to the reference's, selectable one by one inside the unchanged
+# TextDS — `textds(sa=gpu)`, `textds(sa=gpu, lcp=gpu, isa=gpu)` (tudocomp_gpu/GpuProviders.hpp; the provider concept of
+# ds/TextDS.hpp:23-29).  Phi / PLCP have GPU classes too (GpuPhi, GpuPLCP); they are left out of THIS registry only to keep
+# the number of TextDS<...> instantiations of the offline build at 8 instead of 32.
+if mode == "mixed":
+    sa_m = sa + [AlgorithmConfig(name="GpuSA", header="../tudocomp_gpu/GpuProviders.hpp")]
+    lcp_m = lcp + [AlgorithmConfig(name="GpuLCP", header="../tudocomp_gpu/GpuProviders.hpp")]
+    isa_m = isa + [AlgorithmConfig(name="GpuISA", header="../tudocomp_gpu/GpuProviders.hpp")]
+    cpu_textds = [AlgorithmConfig(name="TextDS", header="ds/TextDS.hpp", sub=[sa_m, phi, plcp, lcp_m, isa_m])]
 # the added line: a GPU-backed text index (tudocomp_b200/plugin/include/tudocomp_gpu/GpuTextDS.hpp)
 gpu_textds = [AlgorithmConfig(name="GpuTextDS", header="../tudocomp_gpu/GpuTextDS.hpp")]
 
