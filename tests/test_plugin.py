@@ -156,6 +156,45 @@ def test_plugin_in_a_wide_index_build_of_the_reference(tmp_path):
             assert rec[(wide, "1")][0] == rec[(narrow, "1")][0] + 4, (name, coder, rec)
 
 
+PROVIDERS_CHECK = os.path.join(ROOT, "build", "tdc_providers_check")
+
+
+def _providers_cases(tmp_path, big):
+    cases = {"markov": synth.markov_text(200000 if big else 9000, 5)[:-1].tobytes(), "dna": synth.dna(150000 if big else 5000, 6)[:-1].tobytes(),
+             "repetitive": synth.repetitive(100000 if big else 6000, 7, block=700, p=0.01)[:-1].tobytes(),
+             "binary_with_escapes": bytes(np.random.default_rng(3).integers(0, 256, 20000 if big else 3000, dtype=np.uint8)),
+             "run": b"a" * 2000, "one": b"a", "empty": b""}
+    for k, v in cases.items():
+        p = tmp_path / f"prov_{k}.bin"
+        p.write_bytes(v)
+        yield k, str(p)
+
+
+@pytest.mark.sim
+def test_gpu_providers_equal_reference_providers_over_the_simulator_library(tmp_path):
+    """TextDS<GpuSA, GpuPhi, GpuPLCP, GpuLCP, GpuISA> == TextDS<> array by array (values, widths, max_lcp) in every
+    CompressMode (plugin/tdc_providers_check.cpp), with the interpreter library in place of libtdcgpu.so."""
+    if not os.path.exists(PROVIDERS_CHECK):
+        pytest.skip("tdc_providers_check not built (bash tudocomp_b200/plugin/build_tdc.sh; needs /root/reference)")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    simdir = tmp_path / "simlib"
+    simdir.mkdir()
+    os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
+    for name, src in _providers_cases(tmp_path, big=False):
+        r = subprocess.run([PROVIDERS_CHECK, src], capture_output=True, text=True, env=env)
+        assert r.returncode == 0 and '"providers_equal": true' in r.stdout, (name, r.stdout, r.stderr)
+
+
+@pytest.mark.gpu
+def test_gpu_providers_equal_reference_providers(tmp_path):
+    if not os.path.exists(PROVIDERS_CHECK):
+        pytest.skip("tdc_providers_check not built")
+    for name, src in _providers_cases(tmp_path, big=True):
+        r = subprocess.run([PROVIDERS_CHECK, src], capture_output=True, text=True)
+        assert r.returncode == 0 and '"providers_equal": true' in r.stdout, (name, r.stdout, r.stderr)
+
+
 def _block_container(path):
     """(block_bytes, algo, [archive bytes per block]) of a tdc_block container (tudocomp_b200/plugin/tdc_block.cpp):
     header, archives in completion order, index (offset, length per block, in block order), index offset, end mark."""

@@ -67,4 +67,8 @@ echo "built build/tdc_plugin_bench"
 g++ $CXXFLAGS -DLEN_BITS=40 -I"$gen" "$ROOT/tudocomp_b200/plugin/tdc_plugin_bench.cpp" "$REF/src/tudocomp_stat/StatPhase.cpp" -o "$ROOT/build/tdc_plugin_bench40" \
   -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
 echo "built build/tdc_plugin_bench40"
+# checker of the per-provider GPU classes (GpuProviders.hpp): TextDS<GpuSA, GpuPhi, GpuPLCP, GpuLCP, GpuISA> against TextDS<>
+g++ $CXXFLAGS -I"$gen" "$ROOT/tudocomp_b200/plugin/tdc_providers_check.cpp" "$REF/src/tudocomp_stat/StatPhase.cpp" -o "$ROOT/build/tdc_providers_check" \
+  -L"$ROOT/tudocomp_b200" -ltdcgpu '-Wl,-rpath,$ORIGIN/../tudocomp_b200' -ldl
+echo "built build/tdc_providers_check"
 
