@@ -127,7 +127,7 @@ def test_sim_bit_packed_arrays(simlib):
             c.build(_abi.SA | _abi.ISA | _abi.LCP | _abi.PLCP | _abi.PHI)
             for which in (_abi.SA, _abi.ISA, _abi.LCP, _abi.PLCP, _abi.PHI):
                 a = c.get(which)
-                for w in (1, 7, 13, 17, 31, 32, int(t.size).bit_length()):
+                for w in (1, 7, 13, 17, 31, 32, 33, 40, 64, int(t.size).bit_length()):  # > 32: widened (wide-index builds of the caller)
                     assert np.array_equal(c.get_packed(which, w), _pack_reference(a, w)), (name, which, w)
             with pytest.raises(_abi.TdcGpuError):
-                c.get_packed(_abi.SA, 33)
+                c.get_packed(_abi.SA, 65)
