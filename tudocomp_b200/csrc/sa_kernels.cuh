@@ -492,10 +492,11 @@ static void choose_key_layout(const u32* hist, u64 n, PackParams* pp, u32* sigbi
             const double passes = double((kb + 7) / 8);
             double rounds_left;
             const double residue = residue_of(double(kb) / double(b), &rounds_left);
-            // measured (profiles/r2c_summary.md, dna 2^30): a keys-only pass takes 0.72 of a pair pass although it moves 0.67 of
-            // the bytes (both are issue bound), and a suffix left to the doubling rounds costs ~540 B of pair-pass time
-            // (round-2 sort, rank gather, re-rank, rank scatter, direct LCP of its slot)
-            const double cost = passes * 17.5 - 8.0 + residue * SA_PACKED_ACTIVE_COST * (1.0 + rounds_left);
+            // measured (profiles/r2h_sortbench.txt, 2^28 elements): a keys-only pass takes 0.79 of a pair pass (1.544 vs 1.956 ms)
+            // although it moves 0.67 of the bytes (both are bound by the shared-memory pipe, not by DRAM), and a suffix left
+            // to the doubling rounds costs ~540 B of pair-pass time (round-2 sort, rank gather, re-rank, rank scatter,
+            // direct LCP of its slot)
+            const double cost = passes * 19.0 - 8.0 + residue * SA_PACKED_ACTIVE_COST * (1.0 + rounds_left);
             if (cost <= best_pcost) { best_pcost = cost; best_kb = kb; }
         }
     }
