@@ -138,14 +138,15 @@ __device__ __forceinline__ int walk_nsv(const Tree& T, u32 p, u32 v, u32 thr, u3
 // divergence; per-chunk recurrences + tree walks for the leftovers spend even more on the walks.)
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef LPF_CHUNK_CFG
-#define LPF_CHUNK_CFG 16
+#define LPF_CHUNK_CFG 8
 #endif
-static const int LPF_CHUNK = LPF_CHUNK_CFG;  // ranks per thread (16 or 32)
+static const int LPF_CHUNK = LPF_CHUNK_CFG;  // ranks per thread (4, 8, 16 or 32: a chunk must not straddle 32 ranks, see lpf_phys)
 #if defined(TDC_CUSIM) && !defined(LPF_THREADS_CFG)
 static const int LPF_THREADS = 32;  // small tiles so that the CPU tests leave their tile often
 #else
 #ifndef LPF_THREADS_CFG
-#define LPF_THREADS_CFG 64  // 2 warps x 32 chunks: one block-level merge; measured best (profiles/r1l_summary.md)
+#define LPF_THREADS_CFG 128  // 128 chunks of 8 ranks = tiles of 1024 ranks: measured best (profiles/r2v_lpf_variants.txt:
+                             // 5.92 ms at dna 2^28 against 6.33 for 64 x 16, 5.94 for 32 x 16, 6.6 for 256 x 8, 7.5-9.4 for chunks of 4)
 #endif
 static const int LPF_THREADS = LPF_THREADS_CFG;  // chunks per tile (power of two)
 #endif
