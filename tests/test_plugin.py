@@ -59,9 +59,9 @@ def test_plugin_logic_over_the_simulator_library(tmp_path):
     simdir.mkdir()
     os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
     env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
-    cases = {"markov": synth.markov_text(12000, 5)[:-1].tobytes(), "dna": synth.dna(6000, 6)[:-1].tobytes(),
-             "binary_with_escapes": bytes(np.random.default_rng(3).integers(0, 256, 4000, dtype=np.uint8)),
-             "run": b"a" * 3000, "empty": b""}
+    cases = {"markov": synth.markov_text(8000, 5)[:-1].tobytes(), "dna": synth.dna(4000, 6)[:-1].tobytes(),
+             "binary_with_escapes": bytes(np.random.default_rng(3).integers(0, 256, 3000, dtype=np.uint8)),
+             "run": b"a" * 2000, "empty": b""}
     for name, data in cases.items():
         src = tmp_path / f"{name}.bin"
         src.write_bytes(data)

@@ -87,9 +87,9 @@ def test_sim_key_layouts(simlib, oracle):
     rng = np.random.default_rng(77)
     cases = []
     for sigma in (1, 2, 3, 4, 8, 100, 255):
-        body = rng.integers(1, sigma + 1, 2500, dtype=np.uint16).astype(np.uint8)
+        body = rng.integers(1, sigma + 1, 1500, dtype=np.uint16).astype(np.uint8)
         cases.append((f"sigma{sigma}", synth.with_sentinel(body)))
-        tail = np.concatenate([body[:700], np.full(40, 1, np.uint8)])  # ...AAAA$ : padded keys would tie
+        tail = np.concatenate([body[:500], np.full(40, 1, np.uint8)])  # ...AAAA$ : padded keys would tie
         cases.append((f"sigma{sigma}_tailrun", synth.with_sentinel(tail)))
     try:
         for ksym in (None, "1"):
