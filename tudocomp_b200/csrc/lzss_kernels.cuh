@@ -390,13 +390,22 @@ lpf_tile_kernel(MinTree T, u32 n, u32 thr, u32* __restrict__ out_lenside, LpfDis
 // ---------------------------------------------------------------------------------------------------------------
 // greedy chain
 // ---------------------------------------------------------------------------------------------------------------
-static const int CH_THREADS = 512;
 #ifdef TDC_CUSIM
+static const int CH_THREADS = 512;
 static const int CH_IPT = 2;  // small tiles so that the CPU tests cross many tile/region boundaries
 #else
-static const int CH_IPT = 16;
+#ifndef CH_THREADS_CFG
+#define CH_THREADS_CFG 256
+#endif
+#ifndef CH_IPT_CFG
+#define CH_IPT_CFG 8  // 256 x 8 = tiles of 2048 positions (round 1: 512 x 16): chain_mark 0.49 instead of 0.83 ms, chain_exit 1.17
+                      // instead of 1.31 ms at dna 2^28 (profiles/r2y_variants.txt, r2z_variants.txt)
+#endif
+static const int CH_THREADS = CH_THREADS_CFG;
+static const int CH_IPT = CH_IPT_CFG;
 #endif
 static const int CH_TILE = CH_THREADS * CH_IPT;  // text positions per tile
+static_assert(CH_TILE % 1024 == 0, "emit_factors runs CH_TILE / 32 threads per tile and reduces over whole warps");
 static const u32 CH_NONE = 0xffffffffu;
 
 __device__ __forceinline__ u32 next_of(u32 i, u32 ls) {

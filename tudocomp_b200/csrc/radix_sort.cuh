@@ -28,7 +28,10 @@ static const int RS_THREADS = RS_THREADS_CFG;  // >= 256: one thread per digit i
 static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
 static const int RS_WARPS = RS_THREADS / 32;
 static const int RS_RADIX = 256;
-static const int RS_HIST_EPT = 4;
+#ifndef RS_HIST_EPT_CFG
+#define RS_HIST_EPT_CFG 4
+#endif
+static const int RS_HIST_EPT = RS_HIST_EPT_CFG;
 static const int RS_MAX_PASSES = 8;
 
 struct PassPlan {
@@ -524,7 +527,10 @@ static int radix_sort_keys(SortWorkspace& ws, cudaStream_t st, u64* k[2], u64 m,
 // One element per thread, CTAs in index order: the in-order CTA dispatch keeps all resident CTAs inside the same window
 // (measured with tools/scatterbench.cu: 160 Gelem/s for 16 MiB windows vs 23 Gelem/s unpartitioned; a grid-stride
 // loop loses the locality and most of the gain).
-static const int SP_EPT = 4;  // pairs per thread (two 16-byte loads); a CTA still covers one contiguous run of the pairs
+#ifndef SP_EPT_CFG
+#define SP_EPT_CFG 4
+#endif
+static const int SP_EPT = SP_EPT_CFG;  // pairs per thread (two 16-byte loads); a CTA still covers one contiguous run of the pairs
 static __global__ void __launch_bounds__(256)
 scatter_pairs_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 m, u32* __restrict__ dst) {
     const u64 t0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * SP_EPT;

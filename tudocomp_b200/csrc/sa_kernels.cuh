@@ -54,7 +54,10 @@ struct PackParams {
 };
 
 static const int PK_THREADS = 256;
-static const int PK_IPT = 8;
+#ifndef PK_IPT_CFG
+#define PK_IPT_CFG 8
+#endif
+static const int PK_IPT = PK_IPT_CFG;
 static const int PK_TILE = PK_THREADS * PK_IPT;
 static const int PK_HALO = 64;  // k <= 64 (b >= 1)
 
@@ -136,8 +139,14 @@ __device__ __forceinline__ u32 key_common_symbols(u64 a, u64 c, PackParams pp) {
 // ---------------------------------------------------------------------------------------------------------------
 // 2. rerank (reduce -> scan of tile aggregates -> apply)
 // ---------------------------------------------------------------------------------------------------------------
-static const int RR_THREADS = 256;
-static const int RR_IPT = 8;
+#ifndef RR_THREADS_CFG
+#define RR_THREADS_CFG 512  // tiles of 2048 elements: with 256 threads the single-CTA scan over the tile aggregates doubles (r2z_variants.txt)
+#endif
+static const int RR_THREADS = RR_THREADS_CFG;
+#ifndef RR_IPT_CFG
+#define RR_IPT_CFG 4  // measured (profiles/r2y_variants.txt, dna 2^28): rerank_apply 1.79 ms with 4, 2.53 with 8, 2.49 with 16
+#endif
+static const int RR_IPT = RR_IPT_CFG;  // elements per thread (multiple of 4, < 32)
 static const int RR_TILE = RR_THREADS * RR_IPT;
 
 // RR_IPT consecutive keys of this thread plus one neighbour on either side: kv[q] = key[t0 - 1 + q] (0 outside [0, m)).
