@@ -426,7 +426,7 @@ static int dist_build_sa(DistCtx& d) {
             TDC_TRY(a2a_elems(d, S[0], S[1], 4, back.data()));
         }
         if (m) {
-            TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256 * SP_EPT)), 256, 0, st, S[2], S[1], m, S[3]);
+            TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, SP_THREADS * SP_EPT)), SP_THREADS, 0, st, S[2], S[1], m, S[3]);
             TDC_LAUNCH(build_keys_from_kernel, u32(div_up(m, 256)), 256, 0, st, G, S[3], m, rbits, K[0]);
             TDC_KCHECK();
         }

@@ -28,6 +28,10 @@ static const int RS_THREADS = RS_THREADS_CFG;  // >= 256: one thread per digit i
 static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
 static const int RS_WARPS = RS_THREADS / 32;
 static const int RS_RADIX = 256;
+#ifndef RS_HIST_GRID_MULT_CFG
+#define RS_HIST_GRID_MULT_CFG 8  // (5.12 ms at dna 2^30 against 5.75 with 4 and 5.95 with 2, profiles/r2ad_variants_2p30.txt)
+#endif
+static const int RS_HIST_GRID_MULT = RS_HIST_GRID_MULT_CFG;  // histogram CTAs (of 512 threads) per SM
 #ifndef RS_HIST_EPT_CFG
 #define RS_HIST_EPT_CFG 4
 #endif
@@ -90,14 +94,20 @@ struct SortWorkspace {
 
 template <class K> struct RsCfg;
 template <> struct RsCfg<u64> { static const int IPT = RS_IPT64_CFG; static const int MIN_CTAS = RS_MIN_CTAS_CFG; };
-template <> struct RsCfg<u32> { static const int IPT = 16; static const int MIN_CTAS = 4; };
+#ifndef RS_IPT32_CFG
+#define RS_IPT32_CFG 24  // u32 pairs (scatter partitions): 24 x 256 @ 3 CTAs is 8 % faster than 16 @ 4 (profiles/r2aa_variants.txt)
+#endif
+#ifndef RS_MIN_CTAS32_CFG
+#define RS_MIN_CTAS32_CFG 3
+#endif
+template <> struct RsCfg<u32> { static const int IPT = RS_IPT32_CFG; static const int MIN_CTAS = RS_MIN_CTAS32_CFG; };
 #ifndef RS_MIN_CTAS_KEYS_CFG
-#define RS_MIN_CTAS_KEYS_CFG 4
+#define RS_MIN_CTAS_KEYS_CFG 3  // 24 keys x 256 threads @ 3 CTAs: 4.3 % faster than 16 @ 4 (profiles/r2ab_variants.txt)
 #endif
 // KEYSONLY passes (packed records: the value lives in the low bits of the key) move 16 B per element instead of 24 and
 // need neither the value registers nor the value half of the staging buffer
 #ifndef RS_IPT_KEYS_CFG
-#define RS_IPT_KEYS_CFG 16
+#define RS_IPT_KEYS_CFG 24
 #endif
 template <class K, bool KEYSONLY> struct RsOcc { static const int MIN_CTAS = RsCfg<K>::MIN_CTAS; static const int IPT = RsCfg<K>::IPT; };
 template <> struct RsOcc<u64, true> { static const int MIN_CTAS = RS_MIN_CTAS_KEYS_CFG; static const int IPT = RS_IPT_KEYS_CFG; };
@@ -422,7 +432,7 @@ static int radix_sort_pairs(SortWorkspace& ws, cudaStream_t st, K* k[2], u32* v[
         TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
         if (!hist_ready) {
             TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
-            const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
+            const u32 hgrid = u32(min(u64(ws.sm_count) * RS_HIST_GRID_MULT, div_up(m, 512 * 8)));
             auto rs_histogram = rs_histogram_kernel<K>;
             TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
             prof_add_bytes("rs_histogram", double(m) * sizeof(K));
@@ -491,7 +501,7 @@ static int radix_sort_keys(SortWorkspace& ws, cudaStream_t st, u64* k[2], u64 m,
     }
     TDC_CUDA(cudaMemsetAsync(ws.hist, 0, sizeof(u32) * RS_MAX_PASSES * RS_RADIX, st));
     TDC_CUDA(cudaMemsetAsync(ws.uniform, 0, sizeof(u32) * RS_MAX_PASSES, st));
-    const u32 hgrid = u32(min(u64(ws.sm_count) * 4, div_up(m, 512 * 8)));
+    const u32 hgrid = u32(min(u64(ws.sm_count) * RS_HIST_GRID_MULT, div_up(m, 512 * 8)));
     auto rs_histogram = rs_histogram_kernel<u64>;
     TDC_LAUNCH(rs_histogram, hgrid, 512, 0, st, k[0], m, plan, ws.hist);
     prof_add_bytes("rs_histogram", double(m) * 8);
@@ -531,7 +541,11 @@ static int radix_sort_keys(SortWorkspace& ws, cudaStream_t st, u64* k[2], u64 m,
 #define SP_EPT_CFG 4
 #endif
 static const int SP_EPT = SP_EPT_CFG;  // pairs per thread (two 16-byte loads); a CTA still covers one contiguous run of the pairs
-static __global__ void __launch_bounds__(256)
+#ifndef SP_THREADS_CFG
+#define SP_THREADS_CFG 256
+#endif
+static const int SP_THREADS = SP_THREADS_CFG;
+static __global__ void __launch_bounds__(SP_THREADS)
 scatter_pairs_kernel(const u32* __restrict__ idx, const u32* __restrict__ val, u64 m, u32* __restrict__ dst) {
     const u64 t0 = (u64(blockIdx.x) * blockDim.x + threadIdx.x) * SP_EPT;
     const bool aligned = ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(val)) & 15u) == 0;  // kernel-uniform
@@ -566,7 +580,7 @@ static inline int partitioned_scatter(SortWorkspace& ws, cudaStream_t st, u32* i
         const int wbits = bits - PS_WINDOW_BITS > 8 ? 8 : bits - PS_WINDOW_BITS;  // at most 256 windows
         TDC_TRY(radix_sort_pairs<u32>(ws, st, idx, val, m, bits - wbits, bits, false, &res, full_perm && m == n_dst));
     }
-    TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, 256 * SP_EPT)), 256, 0, st, idx[res], val[res], m, dst);
+    TDC_LAUNCH(scatter_pairs_kernel, u32(div_up(m, SP_THREADS * SP_EPT)), SP_THREADS, 0, st, idx[res], val[res], m, dst);
     prof_add_bytes("scatter_pairs_kernel", double(m) * 12);
     TDC_KCHECK();
     return 0;

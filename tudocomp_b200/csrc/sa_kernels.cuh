@@ -53,7 +53,10 @@ struct PackParams {
     u32 pow2;     // power-of-two alphabet: symbols are coded 0..s-1 and code 0 is shared with the sentinel / the padding
 };
 
-static const int PK_THREADS = 256;
+#ifndef PK_THREADS_CFG
+#define PK_THREADS_CFG 256
+#endif
+static const int PK_THREADS = PK_THREADS_CFG;
 #ifndef PK_IPT_CFG
 #define PK_IPT_CFG 8
 #endif
