@@ -29,7 +29,7 @@ static const int RS_MIN_CTAS = RS_MIN_CTAS_CFG;
 static const int RS_WARPS = RS_THREADS / 32;
 static const int RS_RADIX = 256;
 #ifndef RS_HIST_GRID_MULT_CFG
-#define RS_HIST_GRID_MULT_CFG 8  // (5.12 ms at dna 2^30 against 5.75 with 4 and 5.95 with 2, profiles/r2ad_variants_2p30.txt)
+#define RS_HIST_GRID_MULT_CFG 16  // (dna 2^30: 5.95 ms with 2, 5.75 with 4, 5.12 with 8, 4.97 with 16, 4.89 with 32; profiles/r2ad/r2ae_variants_2p30.txt)
 #endif
 static const int RS_HIST_GRID_MULT = RS_HIST_GRID_MULT_CFG;  // histogram CTAs (of 512 threads) per SM
 #ifndef RS_HIST_EPT_CFG
@@ -566,7 +566,10 @@ static const u64 PS_DIRECT_BELOW = 1000;  // tiny thresholds so that the CPU tes
 static const int PS_WINDOW_BITS = 8;
 #else
 static const u64 PS_DIRECT_BELOW = u64(1) << 22;  // small batches stay L2-resident anyway
-static const int PS_WINDOW_BITS = 22;             // window = 2^22 elements = 16 MiB
+#ifndef PS_WINDOW_BITS_CFG
+#define PS_WINDOW_BITS_CFG 22
+#endif
+static const int PS_WINDOW_BITS = PS_WINDOW_BITS_CFG;  // window = 2^22 elements = 16 MiB
 #endif
 
 // idx[0]/val[0] hold the pairs; idx[1]/val[1] are scratch of the same size.  n_dst = size of dst (bounds the idx bits).

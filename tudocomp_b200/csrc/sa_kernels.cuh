@@ -54,7 +54,7 @@ struct PackParams {
 };
 
 #ifndef PK_THREADS_CFG
-#define PK_THREADS_CFG 256
+#define PK_THREADS_CFG 128  // 3.55 ms at dna 2^30 against 4.01 with 256 (profiles/r2ae_variants_2p30.txt)
 #endif
 static const int PK_THREADS = PK_THREADS_CFG;
 #ifndef PK_IPT_CFG
@@ -75,7 +75,7 @@ pack_keys_kernel(const uint8_t* __restrict__ text, u64 n, const uint8_t* __restr
     __shared__ uint8_t codes[PK_TILE + PK_HALO];
     __shared__ uint8_t cmap[256];
     __shared__ u32 sh_hist[HIST ? RS_MAX_PASSES * RS_RADIX : 1];
-    cmap[threadIdx.x] = code_map[threadIdx.x];
+    for (u32 i = threadIdx.x; i < 256; i += PK_THREADS) cmap[i] = code_map[i];
     if (HIST)
         for (u32 i = threadIdx.x; i < u32(RS_MAX_PASSES * RS_RADIX); i += PK_THREADS) sh_hist[i] = 0;
     __syncthreads();
