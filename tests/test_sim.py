@@ -109,6 +109,38 @@ def test_sim_key_layouts(simlib, oracle):
         os.environ.pop("TDCGPU_SA_SYMBOLS", None)
 
 
+def test_sim_set_text_cached(simlib, oracle):
+    """tdcgpu_set_text_cached (the per-provider classes' entry point): structures survive exactly when the resident text has
+    the same bytes; a different text of the SAME length must invalidate them."""
+    from tudocomp_b200 import synth
+    t1 = synth.markov_text(3000, 11)
+    t2 = t1.copy()
+    t2[1500] = t2[1500] % 26 + 97 if t2[1500] != 97 else 98  # one byte differs, same length
+    assert t2[1500] != t1[1500]
+    t3 = synth.dna(777, 12)
+    with _abi.Context(simlib) as c:
+        assert c.set_text_cached(t1) is False
+        c.build(_abi.SA | _abi.LCP)
+        assert np.array_equal(c.get(_abi.SA), oracle.textds(t1)["sa"])
+        assert c.set_text_cached(t1.copy()) is True  # same bytes at another address: nothing rebuilt
+        assert c.device_ptr(_abi.SA) is not None
+        c.build(_abi.SA | _abi.ISA)
+        assert np.array_equal(c.get(_abi.ISA), oracle.textds(t1)["isa"])
+        assert c.set_text_cached(t2) is False  # same length, one byte differs
+        assert c.device_ptr(_abi.SA) is None
+        c.build(_abi.SA | _abi.ISA | _abi.LCP)
+        ds2 = oracle.textds(t2)
+        assert np.array_equal(c.get(_abi.SA), ds2["sa"]) and np.array_equal(c.get(_abi.LCP), ds2["lcp"])
+        assert c.set_text_cached(t3) is False  # another length
+        c.build(_abi.SA)
+        assert np.array_equal(c.get(_abi.SA), oracle.textds(t3)["sa"])
+        for tail in (15, 16, 17):  # the comparison's 16-byte vector part and its tail
+            a = synth.markov_text(160 + tail, 13)
+            b = a.copy()
+            b[-2] = 98 if b[-2] != 98 else 99
+            assert c.set_text_cached(a) is False and c.set_text_cached(a.copy()) is True and c.set_text_cached(b) is False
+
+
 def _pack_reference(a, w):
     """DynamicIntVector layout (ds/BitPackingVector.hpp:62-98): element i at bits [i*w, (i+1)*w), 64-bit LE words."""
     m = np.uint64((1 << w) - 1)

@@ -157,6 +157,14 @@ class Context:
         self.lib.check(self.lib.lib.tdcgpu_set_text(self._h, _host_ptr(text), text.size, 0))
         self.n = int(text.size)
 
+    def set_text_cached(self, text: np.ndarray) -> bool:
+        """tdcgpu_set_text_cached: True if the resident text had exactly these bytes (built structures stay valid)."""
+        text = np.ascontiguousarray(text, np.uint8)
+        reused = C.c_int(0)
+        self.lib.check(self.lib.lib.tdcgpu_set_text_cached(self._h, _host_ptr(text), C.c_uint64(text.size), C.byref(reused)))
+        self.n = int(text.size)
+        return bool(reused.value)
+
     def set_text_device(self, dev_ptr: int, n: int) -> None:
         self.lib.check(self.lib.lib.tdcgpu_set_text(self._h, C.c_void_p(dev_ptr), n, 1))
         self.n = int(n)
