@@ -112,6 +112,9 @@ def worker(rank: int, world: int, port: int, case: str):
     if case == "strings":
         cases = list(roundtrip_batch()) + list(generator_strings(7))
         thr = (1, 2, 3)
+    elif case == "few":  # a short run for variants of the text upload: every third reference string, one threshold
+        cases = list(roundtrip_batch())[::3]
+        thr = (2,)
     else:
         cases = [(nm, t) for nm, t in small_synthetic() if t.size <= 12000]
         thr = (3,)

@@ -57,4 +57,4 @@ def test_three_ranks_gloo_reference_strings(simbuilt):
 def test_two_ranks_slice_upload_experiment(simbuilt):
     """TDCGPU_DIST_SLICE_UPLOAD=nccl: every rank uploads its n/P slice and the peers exchange the rest through the collective
     (the peer-memory route, the default on GPUs with a mapped window, is covered by tests/test_gpu_dist.py on >= 2 GPUs)."""
-    _run_world(2, "strings", env={"TDCGPU_DIST_SLICE_UPLOAD": "nccl"})
+    _run_world(2, "few", env={"TDCGPU_DIST_SLICE_UPLOAD": "nccl"})
