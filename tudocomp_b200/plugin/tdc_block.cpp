@@ -265,7 +265,7 @@ int main(int argc, char** argv) {
             if (size_t(end - p) < tail || std::memcmp(end - (sizeof(MAGIC_END) - 1), MAGIC_END, sizeof(MAGIC_END) - 1) != 0) throw std::runtime_error("truncated container");
             const uint8_t* q = end - tail;
             const uint64_t index_off = get_u64(q, end);
-            if (index_off > c.size() || (c.size() - index_off - tail) / 16 < nblocks) throw std::runtime_error("corrupt container index");
+            if (index_off > c.size() - tail || (c.size() - tail - index_off) / 16 < nblocks) throw std::runtime_error("corrupt container index");
             const uint8_t* idx = c.data() + index_off;
             std::ofstream out(ofile, std::ios::binary | std::ios::trunc);
             for (uint64_t b = 0; b < nblocks; b++) {
