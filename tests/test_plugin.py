@@ -265,6 +265,14 @@ def test_block_mode_driver_over_the_simulator_library(tmp_path):
     back = str(tmp_path / "back.bin")
     assert subprocess.run([BLOCK_REF, "-d", gpu_c, "-o", back], capture_output=True).returncode == 0
     assert open(back, "rb").read() == data
+    # damaged containers are refused (exit code 1, "Error: ..."), never decoded into something else
+    good = open(gpu_c, "rb").read()
+    for name, bad in (("truncated", good[:-9]), ("no_end_mark", good[:-1] + b"X"), ("index_offset_past_the_end", good[:-16] + (2 ** 40).to_bytes(8, "little") + good[-8:]),
+                      ("not_a_container", b"hello world, this is not a container at all")):
+        p = tmp_path / f"bad_{name}.tdcb"
+        p.write_bytes(bad)
+        r = subprocess.run([BLOCK_REF, "-d", str(p), "-o", str(tmp_path / "bad.out")], capture_output=True, text=True)
+        assert r.returncode == 1 and "Error" in r.stderr, (name, r.returncode, r.stderr)
 
 
 def _inputs(tmp_path):
