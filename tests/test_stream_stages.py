@@ -83,6 +83,68 @@ def test_sim_stream_stages(oracle, gold):
             c.literal_encode(np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8))  # nothing staged
 
 
+def _device_resident_pipeline(lib, oracle, data, offset=0):
+    """mtf -> rle -> encode(bit) with the bytes between the stages in DEVICE memory (the C-ABI calls of the plugin's
+    GpuChainCompressor): host in -> device (TDCGPU_BUF_OUT_DEVICE), device -> device, device -> coded stream on the host."""
+    import ctypes as C
+    L = lib.lib
+    L.tdcgpu_device_alloc.restype = C.c_void_p
+    L.tdcgpu_device_alloc.argtypes = [C.c_void_p, C.c_uint64]
+    L.tdcgpu_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.tdcgpu_device_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.tdcgpu_mtf_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+    L.tdcgpu_rle_encode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+    L.tdcgpu_literal_encode_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]
+    data = np.ascontiguousarray(data, np.uint8)
+    n = data.size
+    worst = 12 * n + 32
+    codes, lens = np.arange(256, dtype=np.uint64), np.full(256, 8, np.uint8)
+    with _abi.Context(lib) as c:
+        h = c._h
+        d_m, d_r = L.tdcgpu_device_alloc(h, n), L.tdcgpu_device_alloc(h, worst)
+        assert d_m and d_r
+        try:
+            lib.check(L.tdcgpu_mtf_encode(h, data.ctypes.data, n, d_m, 2))        # TDCGPU_BUF_OUT_DEVICE
+            produced = C.c_uint64()
+            lib.check(L.tdcgpu_rle_encode(h, d_m, n, offset, d_r, worst, C.byref(produced), 1))  # TDCGPU_BUF_DEVICE
+            back = np.empty(produced.value, np.uint8)
+            lib.check(L.tdcgpu_device_copy(h, back.ctypes.data, d_r, produced.value, 1))
+            want_r = oracle.rle_encode(oracle.mtf_encode(data), offset)
+            assert np.array_equal(back, want_r)
+            m_host = np.empty(n, np.uint8)
+            lib.check(L.tdcgpu_mtf_encode(h, d_m, n, m_host.ctypes.data, 3))      # TDCGPU_BUF_IN_DEVICE (mtf of the mtf output)
+            assert np.array_equal(m_host, oracle.mtf_encode(oracle.mtf_encode(data)))
+            hist = np.zeros(256, np.uint64)
+            lib.check(L.tdcgpu_literal_encode_begin(h, d_r, produced.value, 1, hist.ctypes.data))
+            assert np.array_equal(hist, np.bincount(want_r, minlength=256).astype(np.uint64))
+            got = c.literal_encode(codes, lens)
+            assert np.array_equal(got, oracle.literal_encode(want_r, codes, lens)[0])
+            with pytest.raises(_abi.TdcGpuError):
+                lib.check(L.tdcgpu_mtf_encode(h, data.ctypes.data, n, d_m, 7))    # not a TDCGPU_BUF_* value
+        finally:
+            L.tdcgpu_device_free(h, d_m)
+            L.tdcgpu_device_free(None, d_r)
+
+
+@pytest.mark.sim
+def test_sim_device_resident_stage_pipeline(oracle):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    lib = _abi.TdcGpuLib(SIM)
+    rng = np.random.default_rng(5)
+    for data, off in ((np.repeat(rng.integers(0, 256, 300, dtype=np.uint8), rng.integers(1, 9, 300)), 0),
+                      (rng.integers(97, 101, 4000, dtype=np.uint8), 3), (np.full(1, 65, np.uint8), 0)):
+        _device_resident_pipeline(lib, oracle, data, off)
+
+
+@pytest.mark.gpu
+def test_gpu_device_resident_stage_pipeline(oracle):
+    import tudocomp_b200 as tdc
+    rng = np.random.default_rng(6)
+    for data, off in ((np.repeat(rng.integers(0, 256, 1 << 14, dtype=np.uint8), rng.integers(1, 300, 1 << 14)), 0),
+                      (rng.integers(97, 101, 1 << 22, dtype=np.uint8), 5)):
+        _device_resident_pipeline(tdc.load(), oracle, data, off)
+
+
 @pytest.mark.gpu
 def test_gpu_stream_stages_golden(oracle, gold):
     import tudocomp_b200 as tdc
