@@ -275,6 +275,32 @@ def test_block_mode_driver_over_the_simulator_library(tmp_path):
         assert r.returncode == 1 and "Error" in r.stderr, (name, r.returncode, r.stderr)
 
 
+@pytest.mark.sim
+def test_block_mode_block_size_edge_cases_over_the_simulator_library(tmp_path):
+    """Block sizes from 1 byte to larger than the file, data with bytes that need escaping: the GPU registry's container (interpreter
+    library) equals the reference registry's and decodes to the input."""
+    _need_block_bins()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "tudocomp_b200", "csrc"), "sim"])
+    simdir = tmp_path / "simlib"
+    simdir.mkdir()
+    os.symlink(os.path.join(ROOT, "tests", "sim", "_build", "libtdcsim.so"), simdir / "libtdcgpu.so")
+    env = dict(os.environ, LD_LIBRARY_PATH=str(simdir))
+    rng = np.random.default_rng(12)
+    data = bytes(rng.integers(0, 256, 3000, dtype=np.uint8)) + b"a" * 500 + bytes(rng.integers(97, 100, 2000, dtype=np.uint8))
+    for blk in (1, 7, 999, 5500, 100000):
+        d = data[:40] if blk == 1 else data
+        src = tmp_path / f"in{blk}.bin"
+        src.write_bytes(d)
+        g, r_ = str(tmp_path / "g.tdcb"), str(tmp_path / "r.tdcb")
+        rr = subprocess.run([BLOCK_GPU, "-a", "lzss_lcp(coder=huff)", "-b", str(blk), str(src), "-o", g], capture_output=True, text=True, env=env)
+        assert rr.returncode == 0, (blk, rr.stderr)
+        assert subprocess.run([BLOCK_REF, "-a", "lzss_lcp(coder=huff)", "-b", str(blk), str(src), "-o", r_], capture_output=True).returncode == 0
+        assert open(g, "rb").read() == open(r_, "rb").read(), blk
+        back = str(tmp_path / "back.bin")
+        assert subprocess.run([BLOCK_REF, "-d", g, "-o", back], capture_output=True).returncode == 0
+        assert open(back, "rb").read() == d, blk
+
+
 def _inputs(tmp_path):
     cases = {
         "markov": synth.markov_text(300000, 5)[:-1].tobytes(),
