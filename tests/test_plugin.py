@@ -288,7 +288,7 @@ def test_block_mode_block_size_edge_cases_over_the_simulator_library(tmp_path):
     rng = np.random.default_rng(12)
     data = bytes(rng.integers(0, 256, 3000, dtype=np.uint8)) + b"a" * 500 + bytes(rng.integers(97, 100, 2000, dtype=np.uint8))
     for blk in (1, 7, 999, 5500, 100000):
-        d = data[:40] if blk == 1 else data
+        d = data[:40] if blk == 1 else (data[2990:3200] if blk == 7 else data)  # (few blocks: every block is a whole interpreter run)
         src = tmp_path / f"in{blk}.bin"
         src.write_bytes(d)
         g, r_ = str(tmp_path / "g.tdcb"), str(tmp_path / "r.tdcb")
